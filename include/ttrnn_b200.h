@@ -1,0 +1,135 @@
+/*
+ * ttrnn_b200 -- C ABI of the B200 (sm_100a) tensor-train recurrent engine.
+ *
+ * The reference (onucharles/tensorized-rnn) has no FFI: its boundary for this
+ * path is the PyTorch nn.Module API.  This header is the
+ * C-ABI a maintainer binds in place of the reference's Python hot loop; each
+ * entry point names the reference code it replaces.  The Python mirror of the
+ * module API (tensorized_rnn_b200/) binds exactly these symbols through ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to FP32
+ *     data unless stated otherwise; the library never allocates or frees device
+ *     memory (the caller owns every buffer, sized by the *_workspace_bytes calls)
+ *   - all tensors are dense row-major: x (B, T, I), out (B, T, H), states (B, H)
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synced
+ *   - return 0 on success; non-zero = error, text via ttrnn_last_error()
+ *   - there is no CPU path: without a CUDA device every compute call fails
+ */
+#ifndef TTRNN_B200_H
+#define TTRNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTRNN_ABI_VERSION 1
+#define TTRNN_MAX_CORES   6
+#define TTRNN_MAX_LAYERS  8
+
+#define TTRNN_CELL_LSTM 0   /* gates i, f, g, o  (tensorized_rnn/lstm.py:23-41)  */
+#define TTRNN_CELL_GRU  1   /* gates r, z, n     (tensorized_rnn/gru.py:25-50)   */
+
+/* One TT matrix W (M x N), M = prod(out_modes), N = prod(in_modes).
+ * Core k is stored as the reference stores `weight_t` parameters
+ * (t3nsor/layers.py:113, t3nsor/ops.py:47-51): shape
+ * (ranks[k], out_modes[k], in_modes[k], ranks[k+1]), contiguous, cores
+ * concatenated in order k = 0..d-1.  ranks[0] = ranks[d] = 1. */
+typedef struct ttrnn_tt_shape {
+    int32_t d;
+    int32_t in_modes[TTRNN_MAX_CORES];
+    int32_t out_modes[TTRNN_MAX_CORES];
+    int32_t ranks[TTRNN_MAX_CORES + 1];
+} ttrnn_tt_shape;
+
+/* A stack of TT-LSTM / TT-GRU layers run over a whole sequence:
+ * replaces LSTM.forward (tensorized_rnn/lstm.py:101-135) / GRU.forward
+ * (tensorized_rnn/gru.py:104-136) with TT weights from tt_lstm.py:16-40 /
+ * gru.py:148-172.
+ *
+ * Parameter blob layout (FP32, contiguous), per layer l = 0..L-1:
+ *   [ih cores 0..d-1][ih bias (G*H) if has_bias][hh cores 0..d-1][hh bias (G*H) if has_bias]
+ * which is the order of the reference's state_dict keys
+ *   cell{l}.input_weights.parameters.{k}, cell{l}.input_weights.bias,
+ *   cell{l}.hidden_weights.parameters.{k}, cell{l}.hidden_weights.bias.
+ * Gradients come back in a blob of the same layout. */
+typedef struct ttrnn_rnn_desc {
+    int32_t cell;          /* TTRNN_CELL_*                                   */
+    int32_t num_layers;    /* L                                              */
+    int32_t input_size;    /* I                                              */
+    int32_t hidden_size;   /* H                                              */
+    int32_t has_bias;      /* both TTLinears of every cell carry a bias or none */
+    int32_t seq_len;       /* T  (>= 1)                                      */
+    int64_t batch;         /* B  (>= 1)                                      */
+    ttrnn_tt_shape ih[TTRNN_MAX_LAYERS];   /* (G*H) x I for l = 0, (G*H) x H above */
+    ttrnn_tt_shape hh[TTRNN_MAX_LAYERS];   /* (G*H) x H                      */
+} ttrnn_rnn_desc;
+
+typedef struct ttrnn_rnn_workspace {
+    int64_t saved_bytes;        /* forward -> backward activations (training only) */
+    int64_t fwd_scratch_bytes;  /* scratch for one forward call                    */
+    int64_t bwd_scratch_bytes;  /* scratch for one backward call                   */
+} ttrnn_rnn_workspace;
+
+int         ttrnn_abi_version(void);
+const char *ttrnn_last_error(void);            /* thread-local, never NULL */
+
+/* number of floats in the parameter blob of `desc`; < 0 on a malformed desc */
+int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc);
+
+int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws);
+
+/* Forward over the whole stack.  h0 / c0 may be NULL (zeros); one (h0, c0) seeds
+ * every layer (lstm.py:120-121).  c0 / cT / d_c* are ignored for GRU.
+ * `saved` NULL = inference (nothing kept for backward).  Returns outputs of the
+ * last layer for every t, and (h_T, c_T) of the last layer (lstm.py:135). */
+int ttrnn_rnn_forward(const ttrnn_rnn_desc *desc, const float *x, const float *h0, const float *c0,
+                      const float *params, float *out, float *hT, float *cT,
+                      void *saved, void *scratch, void *stream);
+
+/* BPTT through the stack: what autograd does for the reference
+ * (SURVEY.md section 8a-10).  d_out (B,T,H), d_hT, d_cT: upstream gradients (any may be
+ * NULL = zero).  d_params is OVERWRITTEN with the gradient blob.  d_x (B,T,I) may
+ * be NULL.  d_h0 / d_c0 (B,H) may be NULL; they receive the SUM over layers
+ * because every layer shares the same initial state. */
+int ttrnn_rnn_backward(const ttrnn_rnn_desc *desc, const float *x, const float *h0, const float *c0,
+                       const float *params, const float *out, const void *saved,
+                       const float *d_out, const float *d_hT, const float *d_cT,
+                       float *d_params, float *d_x, float *d_h0, float *d_c0,
+                       void *scratch, void *stream);
+
+/* Stand-alone TT linear map y = x W^T + bias over `rows` rows:
+ * replaces TTLinear.forward (t3nsor/layers.py:121-127) -> tt_dense_matmul
+ * (t3nsor/ops.py:54-93).  bias may be NULL. */
+int64_t ttrnn_ttlinear_param_count(const ttrnn_tt_shape *shape);
+int64_t ttrnn_ttlinear_workspace_bytes(const ttrnn_tt_shape *shape, int64_t rows);
+int ttrnn_ttlinear_forward(const ttrnn_tt_shape *shape, int64_t rows, const float *x,
+                           const float *cores, const float *bias, float *y,
+                           void *scratch, void *stream);
+/* d_cores / d_bias are OVERWRITTEN; d_x and d_bias may be NULL. */
+int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const float *x,
+                            const float *cores, const float *dy,
+                            float *d_x, float *d_cores, float *d_bias,
+                            void *scratch, void *stream);
+
+/* Measurement helpers (bench.py only).
+ * ttrnn_ffma_probe: dependent-chain-free FP32 FFMA loop on every SM; writes the
+ * number of FLOPs executed to *flops_out (host) and leaves a checksum in sink
+ * (device, >= 4 bytes).  Time it with CUDA events to get the FP32 roofline peak. */
+int ttrnn_ffma_probe(int32_t iters, float *sink, double *flops_out, void *stream);
+/* counts kernels launched by this library since the last reset (host counter) */
+int64_t ttrnn_launch_count(int32_t reset);
+
+/* Tuning knobs (process-wide; also read from the environment at load time):
+ *   "rows_per_cta"  batch rows owned by one CTA of the recurrent kernels (0 = auto)
+ *   "chunk_steps"   timesteps per ih-projection chunk (0 = auto, bounded by memory)
+ * returns 0 if the key is known. */
+int ttrnn_set_option(const char *key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTRNN_B200_H */

@@ -1,0 +1,108 @@
+"""ctypes binding of the C ABI in include/ttrnn_b200.h.
+
+The shared library is built in-tree by `tensorized_rnn_b200.build`.  There is no
+fallback of any kind: if the library is missing, or a compute entry point is called
+without a CUDA device / with CPU tensors, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+MAX_CORES = 6
+MAX_LAYERS = 8
+CELL_LSTM, CELL_GRU = 0, 1
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libttrnn_b200.so")
+_lib: Optional[C.CDLL] = None
+
+
+class TTShape(C.Structure):
+    _fields_ = [("d", C.c_int32),
+                ("in_modes", C.c_int32 * MAX_CORES),
+                ("out_modes", C.c_int32 * MAX_CORES),
+                ("ranks", C.c_int32 * (MAX_CORES + 1))]
+
+
+class RnnDesc(C.Structure):
+    _fields_ = [("cell", C.c_int32), ("num_layers", C.c_int32), ("input_size", C.c_int32),
+                ("hidden_size", C.c_int32), ("has_bias", C.c_int32), ("seq_len", C.c_int32),
+                ("batch", C.c_int64),
+                ("ih", TTShape * MAX_LAYERS), ("hh", TTShape * MAX_LAYERS)]
+
+
+class RnnWorkspace(C.Structure):
+    _fields_ = [("saved_bytes", C.c_int64), ("fwd_scratch_bytes", C.c_int64), ("bwd_scratch_bytes", C.c_int64)]
+
+
+# every symbol include/ttrnn_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "ttrnn_abi_version": (C.c_int, []),
+    "ttrnn_last_error": (C.c_char_p, []),
+    "ttrnn_rnn_param_count": (C.c_int64, [C.POINTER(RnnDesc)]),
+    "ttrnn_rnn_workspace_bytes": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)]),
+    "ttrnn_rnn_forward": (C.c_int, [C.POINTER(RnnDesc)] + [_P] * 10),
+    "ttrnn_rnn_backward": (C.c_int, [C.POINTER(RnnDesc)] + [_P] * 15),
+    "ttrnn_ttlinear_param_count": (C.c_int64, [C.POINTER(TTShape)]),
+    "ttrnn_ttlinear_workspace_bytes": (C.c_int64, [C.POINTER(TTShape), C.c_int64]),
+    "ttrnn_ttlinear_forward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 6),
+    "ttrnn_ttlinear_backward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 8),
+    "ttrnn_ffma_probe": (C.c_int, [C.c_int32, _P, C.POINTER(C.c_double), _P]),
+    "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
+    "ttrnn_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
+}
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            "tensorized_rnn_b200: CUDA library %s is missing. Build it with "
+            "`python -m tensorized_rnn_b200.build` (needs nvcc). There is no CPU or PyTorch fallback." % _LIB_PATH)
+    lib = C.CDLL(_LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ttrnn_abi_version() != 1:
+        raise RuntimeError("tensorized_rnn_b200: ABI version mismatch between %s and the Python binding" % _LIB_PATH)
+    for key, env in (("rows_per_cta", "TTRNN_ROWS_PER_CTA"), ("chunk_steps", "TTRNN_CHUNK_STEPS"),
+                     ("chunk_bytes", "TTRNN_CHUNK_BYTES")):
+        if os.environ.get(env):
+            lib.ttrnn_set_option(key.encode(), int(os.environ[env]))
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().ttrnn_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError("%s failed: %s" % (what, last_error()))
+
+
+def make_tt_shape(in_modes: Sequence[int], out_modes: Sequence[int], ranks: Sequence[int]) -> TTShape:
+    d = len(in_modes)
+    if d > MAX_CORES:
+        raise ValueError("at most %d TT cores are supported, got %d" % (MAX_CORES, d))
+    if len(out_modes) != d or len(ranks) != d + 1:
+        raise ValueError("inconsistent TT shape: in %r out %r ranks %r" % (in_modes, out_modes, ranks))
+    s = TTShape()
+    s.d = d
+    for k in range(d):
+        s.in_modes[k] = int(in_modes[k])
+        s.out_modes[k] = int(out_modes[k])
+    for k in range(d + 1):
+        s.ranks[k] = int(ranks[k])
+    return s

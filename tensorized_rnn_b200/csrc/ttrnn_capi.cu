@@ -1,0 +1,588 @@
+// C ABI of the engine (include/ttrnn_b200.h): validation, planning, workspace layout and
+// the host-side launch sequence (layer by layer, time chunk by time chunk).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "tt_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err = "";
+std::atomic<long long> g_launches{0};
+std::atomic<long long> g_opt_rows{0};
+std::atomic<long long> g_opt_chunk{0};
+std::atomic<long long> g_opt_chunk_bytes{4LL << 30};
+
+int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CU_CHECK(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct DevInfo {
+    int sms = 0;
+    int smem_optin = 0;
+    bool ok = false;
+};
+
+int get_dev(DevInfo *d) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess)
+        return fail("no CUDA device available (%s): ttrnn_b200 has no CPU path", cudaGetErrorString(e));
+    CU_CHECK(cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev));
+    CU_CHECK(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    d->ok = true;
+    return 0;
+}
+
+inline int gates_of(int cell) { return cell == TTRNN_CELL_LSTM ? 4 : 3; }
+inline long long r4(long long v) { return (v + 3) & ~3LL; }
+
+// ---- tile heuristics --------------------------------------------------------------------
+int choose_fwd_tile(const StagePlan &s, int R) {
+    if (s.K % 4 != 0 || s.N % 4 != 0) return TT_TILE_GEN;
+    const long long per = (long long)R * s.Mrow * s.N / TT_NTHREADS;
+    if (s.N % 8 == 0 && per >= 64) return TT_TILE_8x8;
+    if (s.N % 8 == 0 && per >= 32) return TT_TILE_4x8;
+    if (per >= 32) return TT_TILE_8x4;
+    if (per >= 16) return TT_TILE_4x4;
+    if (per >= 8) return TT_TILE_2x4;
+    return TT_TILE_1x4;
+}
+int choose_bd_tile(const StagePlan &s, int R) {
+    if (s.K % 4 != 0) return TT_TILE_GEN;
+    const long long per = (long long)R * s.Mrow * s.K / TT_NTHREADS;
+    if (s.K % 8 == 0 && per >= 64) return TT_TILE_8x8;
+    if (s.K % 8 == 0 && per >= 32) return TT_TILE_4x8;
+    if (per >= 32) return TT_TILE_8x4;
+    if (per >= 16) return TT_TILE_4x4;
+    if (per >= 8) return TT_TILE_2x4;
+    return TT_TILE_1x4;
+}
+int choose_mg(const StagePlan &s, int R) {
+    const int tk = (s.K % 4 == 0) ? 4 : 2;
+    const int tn = (s.K % 4 == 0 || s.r % 4 == 0) ? 4 : 2;
+    const int items = ((s.K + tk - 1) / tk) * ((s.N + tn - 1) / tn);
+    const int M = R * s.Mrow;
+    int mg = TT_NTHREADS / items;
+    if (mg < 1) mg = 1;
+    const int cap = M / 4 > 1 ? M / 4 : 1;
+    return mg > cap ? cap : mg;
+}
+void fill_tiles(const ChainPlan &p, int R, int *tf, int *tb, int *mg) {
+    for (int k = 0; k < p.d; ++k) {
+        if (tf) tf[k] = choose_fwd_tile(p.st[k], R);
+        if (tb) tb[k] = choose_bd_tile(p.st[k], R);
+        if (mg) mg[k] = choose_mg(p.st[k], R);
+    }
+}
+
+// ---- shared-memory footprints (floats) --------------------------------------------------
+long long smem_ttlin_fwd(const ChainPlan &p, int R) {
+    return p.w_floats + (long long)R * (p.in_BS + p.pp_floats[0] + p.pp_floats[1] + p.g_BS);
+}
+long long smem_rnn_fwd(const ChainPlan &p, int R, int H, int G) {
+    return p.w_floats + r4(G * H) + r4((long long)R * H) + r4((long long)R * G * H) +
+           (long long)R * (p.g_BS + p.in_BS + p.pp_floats[0] + p.pp_floats[1]);
+}
+long long smem_ttlin_bwd(const ChainPlan &p, int R) {
+    return 2LL * p.w_floats + r4(p.n_out) + (long long)R * (p.all_floats + p.g_BS + p.in_BS);
+}
+long long smem_rnn_bwd(const ChainPlan &p, int R, int H, int G) {
+    return 2LL * p.w_floats + 2 * r4(G * H) + (long long)R * (p.all_floats + p.g_BS + p.in_BS) +
+           r4((long long)R * G * H) + 3 * r4((long long)R * H);
+}
+
+template <class F>
+int pick_rows(F smem_floats, int smem_limit_bytes, int rmax, long long units, int sms, int want_ctas_per_sm) {
+    int R = 0;
+    for (int r = 1; r <= rmax; ++r)
+        if (smem_floats(r) * 4 <= smem_limit_bytes) R = r;
+    if (R == 0) return 0;
+    const long long opt = g_opt_rows.load();
+    if (opt > 0) return (int)(opt < R ? opt : R);
+    while (R > 1 && (units + R - 1) / R < (long long)want_ctas_per_sm * sms) --R;
+    return R;
+}
+
+template <class K>
+int grid_for(K kernel, size_t smem_bytes, long long ntiles, const DevInfo &dv, int *grid) {
+    CU_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    int occ = 0;
+    CU_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, TT_NTHREADS, smem_bytes));
+    if (occ < 1) return fail("kernel does not fit on an SM (%zu bytes of shared memory)", smem_bytes);
+    if (occ > 4) occ = 4;
+    long long g = (long long)occ * dv.sms;
+    if (g > ntiles) g = ntiles;
+    *grid = (int)g;
+    return 0;
+}
+constexpr int kMaxSlotsPerSM = 4;
+
+// ---- descriptor validation / parameter blob layout -----------------------------------------
+struct LayerPlan {
+    ChainPlan ih, hh;
+    long long off_ih_cores, off_ih_bias, off_hh_cores, off_hh_bias;   // floats into the blob
+};
+struct RnnPlan {
+    int G = 0;
+    long long param_floats = 0;
+    LayerPlan layer[TTRNN_MAX_LAYERS];
+};
+
+int build_rnn_plan(const ttrnn_rnn_desc *d, RnnPlan *rp) {
+    if (!d) return fail("null descriptor");
+    if (d->cell != TTRNN_CELL_LSTM && d->cell != TTRNN_CELL_GRU) return fail("unknown cell kind %d", d->cell);
+    if (d->num_layers < 1 || d->num_layers > TTRNN_MAX_LAYERS)
+        return fail("num_layers %d out of range [1, %d]", d->num_layers, TTRNN_MAX_LAYERS);
+    if (d->input_size < 1 || d->hidden_size < 1) return fail("input_size / hidden_size must be positive");
+    if (d->batch < 1 || d->seq_len < 1) return fail("batch and seq_len must be >= 1 (got %lld, %d)", (long long)d->batch, d->seq_len);
+    rp->G = gates_of(d->cell);
+    const int GH = rp->G * d->hidden_size;
+    long long off = 0;
+    for (int l = 0; l < d->num_layers; ++l) {
+        LayerPlan &lp = rp->layer[l];
+        int rc = tt_build_plan(&d->ih[l], &lp.ih);
+        if (rc) return fail("layer %d: malformed ih TT shape (code %d)", l, rc);
+        rc = tt_build_plan(&d->hh[l], &lp.hh);
+        if (rc) return fail("layer %d: malformed hh TT shape (code %d)", l, rc);
+        const int want_in = (l == 0) ? d->input_size : d->hidden_size;
+        if (lp.ih.n_in != want_in || lp.ih.n_out != GH)
+            return fail("layer %d: ih TT matrix is %d x %d, expected %d x %d", l, lp.ih.n_out, lp.ih.n_in, GH, want_in);
+        if (lp.hh.n_in != d->hidden_size || lp.hh.n_out != GH)
+            return fail("layer %d: hh TT matrix is %d x %d, expected %d x %d", l, lp.hh.n_out, lp.hh.n_in, GH, d->hidden_size);
+        lp.off_ih_cores = off; off += lp.ih.core_floats;
+        lp.off_ih_bias = off;  if (d->has_bias) off += GH;
+        lp.off_hh_cores = off; off += lp.hh.core_floats;
+        lp.off_hh_bias = off;  if (d->has_bias) off += GH;
+    }
+    rp->param_floats = off;
+    return 0;
+}
+
+// ---- workspace layout --------------------------------------------------------------------
+struct RnnLayout {
+    int Tc = 0;                 // timesteps per chunk
+    long long BTH = 0, BH = 0;
+    long long xg_floats = 0;
+    // saved (floats)
+    long long sv_hs = 0, sv_cs = 0, sv_total = 0;
+    // fwd scratch (floats)
+    long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_total = 0;
+    // bwd scratch (floats)
+    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_total = 0;
+    long long part_stride = 0;  // floats per partial slot
+    int nslots = 0;
+};
+
+int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, RnnLayout *lo) {
+    const long long B = d->batch, T = d->seq_len, H = d->hidden_size, L = d->num_layers;
+    const long long GH = (long long)rp.G * H;
+    lo->BTH = B * T * H;
+    lo->BH = B * H;
+    long long tc = g_opt_chunk.load();
+    if (tc <= 0) {
+        tc = g_opt_chunk_bytes.load() / (B * GH * 4);
+        if (tc < 1) tc = 1;
+    }
+    if (tc > T) tc = T;
+    lo->Tc = (int)tc;
+    lo->xg_floats = r4(B * tc * GH);
+    const bool lstm = d->cell == TTRNN_CELL_LSTM;
+    // saved: inner-layer outputs, then cell states of every layer
+    lo->sv_hs = 0;
+    lo->sv_cs = r4((L - 1) * lo->BTH);
+    lo->sv_total = lo->sv_cs + (lstm ? r4(L * lo->BTH) : 0);
+    // forward scratch
+    long long o = 0;
+    lo->f_xg = o; o += lo->xg_floats;
+    lo->f_sh = o; o += r4(lo->BH);
+    lo->f_sc = o; o += r4(lo->BH);
+    lo->f_hs = o; o += (L > 1 ? 2 * r4(lo->BTH) : 0);     // used only when nothing is saved
+    lo->f_total = o;
+    // backward scratch
+    long long maxp = 0;
+    for (int l = 0; l < L; ++l) {
+        long long a = rp.layer[l].ih.core_floats + GH, b = rp.layer[l].hh.core_floats + GH;
+        if (a > maxp) maxp = a;
+        if (b > maxp) maxp = b;
+    }
+    lo->part_stride = r4(maxp);
+    lo->nslots = dv.sms * kMaxSlotsPerSM;
+    o = 0;
+    lo->b_xg = o; o += lo->xg_floats;
+    lo->b_dhs = o; o += (L > 1 ? 2 * r4(lo->BTH) : 0);
+    lo->b_sdh = o; o += r4(lo->BH);
+    lo->b_sdc = o; o += r4(lo->BH);
+    lo->b_part_hh = o; o += lo->part_stride * lo->nslots;
+    lo->b_part_ih = o; o += lo->part_stride * lo->nslots;
+    lo->b_total = o;
+    return 0;
+}
+
+// ---- launch helpers ------------------------------------------------------------------------
+int launch_ttlinear_fwd(const ChainPlan &p, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
+                        long long x_bstride, const float *cores, const float *bias, const float *bias2, float *y,
+                        long long y_bstride, cudaStream_t st) {
+    TTLinFwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.p = p;
+    const int R = pick_rows([&](int r) { return smem_ttlin_fwd(p, r); }, dv.smem_optin, 8, rows, dv.sms, 2);
+    if (R == 0)
+        return fail("TT shape needs %lld bytes of shared memory per row tile (limit %d): unsupported",
+                    smem_ttlin_fwd(p, 1) * 4, dv.smem_optin);
+    a.R = R;
+    fill_tiles(p, R, a.tile, nullptr, nullptr);
+    a.rows = rows; a.rows_per_b = rows_per_b; a.x_bstride = x_bstride; a.y_bstride = y_bstride;
+    a.x = x; a.cores = cores; a.bias = bias; a.bias2 = bias2; a.y = y;
+    const size_t smem = (size_t)smem_ttlin_fwd(p, R) * 4;
+    int grid = 0;
+    if (grid_for(k_ttlinear_fwd, smem, (rows + R - 1) / R, dv, &grid)) return 1;
+    k_ttlinear_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_ttlinear_bwd(const ChainPlan &p, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
+                        long long x_bstride, const float *cores, const float *dy, long long dy_bstride, float *dx,
+                        long long dx_bstride, float *partial, long long part_stride, int nslots, int want_dbias,
+                        cudaStream_t st) {
+    TTLinBwdArgs a;
+    memset(&a, 0, sizeof a);
+    a.p = p;
+    const int R = pick_rows([&](int r) { return smem_ttlin_bwd(p, r); }, dv.smem_optin, 8, rows, dv.sms, 2);
+    if (R == 0)
+        return fail("TT shape needs %lld bytes of shared memory for the backward row tile (limit %d): unsupported",
+                    smem_ttlin_bwd(p, 1) * 4, dv.smem_optin);
+    a.R = R;
+    fill_tiles(p, R, a.tile, a.tile_bd, a.mg);
+    a.rows = rows; a.rows_per_b = rows_per_b;
+    a.x_bstride = x_bstride; a.dy_bstride = dy_bstride; a.dx_bstride = dx_bstride;
+    a.x = x; a.cores = cores; a.dy = dy; a.dx = dx; a.partial = partial; a.want_dbias = want_dbias;
+    if (p.core_floats + p.n_out > part_stride) return fail("internal: partial slot too small");
+    const size_t smem = (size_t)smem_ttlin_bwd(p, R) * 4;
+    int grid = 0;
+    if (grid_for(k_ttlinear_bwd, smem, (rows + R - 1) / R, dv, &grid)) return 1;
+    if (grid > nslots) grid = nslots;
+    // the kernel addresses its slot as blockIdx.x * (core_floats + n_out); keep that contract
+    (void)part_stride;
+    k_ttlinear_bwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return grid > 0 ? -grid : 1;   // negative = number of slots used (success)
+}
+
+int reduce_partials(const float *partial, int nslots, long long slot_stride, long long off, int n, float *out,
+                    cudaStream_t st) {
+    if (n <= 0) return 0;
+    k_reduce_partials<<<(n + 255) / 256, 256, 0, st>>>(partial + off, nslots, n, slot_stride, out);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int axpy1(const float *src, float *dst, long long n, int accumulate, cudaStream_t st) {
+    k_axpy1<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n, accumulate);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int ttrnn_abi_version(void) { return TTRNN_ABI_VERSION; }
+const char *ttrnn_last_error(void) { return g_err.c_str(); }
+
+int64_t ttrnn_launch_count(int32_t reset) {
+    long long v = g_launches.load();
+    if (reset) g_launches.store(0);
+    return v;
+}
+
+int ttrnn_set_option(const char *key, int64_t value) {
+    if (!key) return 1;
+    if (!strcmp(key, "rows_per_cta")) { g_opt_rows.store(value); return 0; }
+    if (!strcmp(key, "chunk_steps")) { g_opt_chunk.store(value); return 0; }
+    if (!strcmp(key, "chunk_bytes")) { g_opt_chunk_bytes.store(value > 0 ? value : (4LL << 30)); return 0; }
+    return 1;
+}
+
+int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc) {
+    RnnPlan rp;
+    if (build_rnn_plan(desc, &rp)) return -1;
+    return rp.param_floats;
+}
+
+int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
+    if (!ws) return fail("null workspace struct");
+    RnnPlan rp;
+    if (build_rnn_plan(desc, &rp)) return 1;
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    RnnLayout lo;
+    if (build_layout(desc, rp, dv, &lo)) return 1;
+    ws->saved_bytes = lo.sv_total * 4;
+    ws->fwd_scratch_bytes = lo.f_total * 4;
+    ws->bwd_scratch_bytes = lo.b_total * 4;
+    return 0;
+}
+
+int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, const float *c0,
+                      const float *params, float *out, float *hT, float *cT, void *saved, void *scratch,
+                      void *stream) {
+    RnnPlan rp;
+    if (build_rnn_plan(d, &rp)) return 1;
+    if (!x || !params || !out || !scratch) return fail("x, params, out and scratch must be non-null");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    RnnLayout lo;
+    if (build_layout(d, rp, dv, &lo)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long B = d->batch;
+    const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = rp.G;
+    const int GH = G * H;
+    const bool lstm = d->cell == TTRNN_CELL_LSTM;
+    float *sc = (float *)scratch;
+    float *sv = (float *)saved;
+    float *xg = sc + lo.f_xg;
+    float *st_h = sc + lo.f_sh, *st_c = sc + lo.f_sc;
+
+    for (int l = 0; l < L; ++l) {
+        const LayerPlan &lp = rp.layer[l];
+        const int nin = lp.ih.n_in;
+        const float *lin;       // input of this layer (B, T, nin)
+        if (l == 0) lin = x;
+        else lin = sv ? sv + lo.sv_hs + (long long)(l - 1) * lo.BTH : sc + lo.f_hs + ((l - 1) & 1) * r4(lo.BTH);
+        float *lout;            // output of this layer (B, T, H)
+        if (l == L - 1) lout = out;
+        else lout = sv ? sv + lo.sv_hs + (long long)l * lo.BTH : sc + lo.f_hs + (l & 1) * r4(lo.BTH);
+        float *csave = (sv && lstm) ? sv + lo.sv_cs + (long long)l * lo.BTH : nullptr;
+        const float *b_ih = d->has_bias ? params + lp.off_ih_bias : nullptr;
+        const float *b_hh = d->has_bias ? params + lp.off_hh_bias : nullptr;
+
+        // recurrent kernel configuration for this layer
+        RnnFwdArgs a;
+        memset(&a, 0, sizeof a);
+        a.p = lp.hh;
+        const int R = pick_rows([&](int r) { return smem_rnn_fwd(lp.hh, r, H, G); }, dv.smem_optin, 8, B, dv.sms, 2);
+        if (R == 0)
+            return fail("layer %d: hh TT shape needs %lld bytes of shared memory per CTA (limit %d): unsupported", l,
+                        smem_rnn_fwd(lp.hh, 1, H, G) * 4, dv.smem_optin);
+        a.R = R;
+        fill_tiles(lp.hh, R, a.tile, nullptr, nullptr);
+        a.cell = d->cell; a.H = H; a.G = G; a.B = B;
+        a.cores = params + lp.off_hh_cores;
+        a.bias_hh = lstm ? nullptr : b_hh;
+        const size_t smem = (size_t)smem_rnn_fwd(lp.hh, R, H, G) * 4;
+        int grid = 0;
+        if (grid_for(k_rnn_fwd, smem, (B + R - 1) / R, dv, &grid)) return 1;
+
+        for (int t0 = 0; t0 < T; t0 += lo.Tc) {
+            const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
+            // (1) batched ih projection of the chunk: xg[b, t, :] = W_ih x[b, t0+t, :] + b_ih (+ b_hh for LSTM)
+            if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st))
+                return 1;
+            // (2) persistent recurrence over the chunk
+            const bool first = (t0 == 0), last = (t0 + tc == T);
+            a.steps = tc;
+            a.xg = xg; a.xg_bstride = (long long)tc * GH;
+            a.h_in = first ? h0 : st_h;
+            a.c_in = first ? c0 : st_c;
+            a.out = lout + (long long)t0 * H; a.out_bstride = (long long)T * H;
+            a.c_save = csave ? csave + (long long)t0 * H : nullptr;
+            a.h_out = (last && l == L - 1 && hT) ? hT : st_h;
+            a.c_out = (last && l == L - 1 && cT) ? cT : st_c;
+            k_rnn_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+            ++g_launches;
+            CU_CHECK(cudaGetLastError());
+        }
+    }
+    return 0;
+}
+
+int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0, const float *c0,
+                       const float *params, const float *out, const void *saved, const float *d_out,
+                       const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
+                       void *scratch, void *stream) {
+    RnnPlan rp;
+    if (build_rnn_plan(d, &rp)) return 1;
+    if (!x || !params || !out || !scratch || !d_params) return fail("x, params, out, scratch, d_params must be non-null");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    RnnLayout lo;
+    if (build_layout(d, rp, dv, &lo)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long B = d->batch;
+    const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = rp.G;
+    const int GH = G * H;
+    const bool lstm = d->cell == TTRNN_CELL_LSTM;
+    if ((L > 1 || lstm) && !saved) return fail("backward needs the `saved` buffer written by a training forward");
+    float *sc = (float *)scratch;
+    const float *sv = (const float *)saved;
+    float *xg = sc + lo.b_xg;
+    float *sdh = sc + lo.b_sdh, *sdc = sc + lo.b_sdc;
+    float *part_hh = sc + lo.b_part_hh, *part_ih = sc + lo.b_part_ih;
+
+    for (int l = L - 1; l >= 0; --l) {
+        const LayerPlan &lp = rp.layer[l];
+        const int nin = lp.ih.n_in;
+        const float *lin = (l == 0) ? x : sv + lo.sv_hs + (long long)(l - 1) * lo.BTH;
+        const float *lout = (l == L - 1) ? out : sv + lo.sv_hs + (long long)l * lo.BTH;
+        const float *lcs = lstm ? sv + lo.sv_cs + (long long)l * lo.BTH : nullptr;
+        // gradient wrt this layer's outputs / wrt its inputs
+        const float *dhs = (l == L - 1) ? d_out : sc + lo.b_dhs + ((l + 1) & 1) * r4(lo.BTH);
+        float *dlin = (l == 0) ? d_x : sc + lo.b_dhs + (l & 1) * r4(lo.BTH);
+        const float *b_ih = d->has_bias ? params + lp.off_ih_bias : nullptr;
+        const float *b_hh = d->has_bias ? params + lp.off_hh_bias : nullptr;
+
+        RnnBwdArgs a;
+        memset(&a, 0, sizeof a);
+        a.p = lp.hh;
+        const int R = pick_rows([&](int r) { return smem_rnn_bwd(lp.hh, r, H, G); }, dv.smem_optin, 8, B, dv.sms, 2);
+        if (R == 0)
+            return fail("layer %d: hh TT shape needs %lld bytes of shared memory per CTA for BPTT (limit %d): unsupported",
+                        l, smem_rnn_bwd(lp.hh, 1, H, G) * 4, dv.smem_optin);
+        a.R = R;
+        fill_tiles(lp.hh, R, a.tile, a.tile_bd, a.mg);
+        a.cell = d->cell; a.H = H; a.G = G; a.B = B; a.T = T;
+        a.cores = params + lp.off_hh_cores;
+        a.bias_hh = lstm ? nullptr : b_hh;
+        a.hs = lout; a.cs = lcs; a.h0 = h0; a.c0 = c0; a.dhs = dhs;
+        const size_t smem = (size_t)smem_rnn_bwd(lp.hh, R, H, G) * 4;
+        int grid = 0;
+        if (grid_for(k_rnn_bwd, smem, (B + R - 1) / R, dv, &grid)) return 1;
+        if (grid > lo.nslots) grid = lo.nslots;
+        const long long hh_slot = lp.hh.core_floats + GH;
+        const long long ih_slot = lp.ih.core_floats + GH;
+        CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)hh_slot * grid * 4, st));
+        CU_CHECK(cudaMemsetAsync(part_ih, 0, (size_t)ih_slot * lo.nslots * 4, st));
+        a.partial = part_hh;
+        int ih_slots_used = 0;
+
+        const int nchunks = (T + lo.Tc - 1) / lo.Tc;
+        for (int ci = nchunks - 1; ci >= 0; --ci) {
+            const int t0 = ci * lo.Tc;
+            const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
+            const bool last = (t0 + tc == T);
+            // (1) recompute the ih projection of the chunk
+            if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st))
+                return 1;
+            // (2) reverse-time recurrence: xg <- delta_ih, hh core grads, dh/dc carried across chunks
+            a.t0 = t0; a.steps = tc;
+            a.xg = xg; a.xg_bstride = (long long)tc * GH;
+            a.dh_in = last ? (l == L - 1 ? d_hT : nullptr) : sdh;
+            a.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
+            a.dh_out = sdh; a.dc_out = sdc;
+            k_rnn_bwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+            ++g_launches;
+            CU_CHECK(cudaGetLastError());
+            // (3) ih backward over the chunk: core grads, bias grad, gradient wrt the layer input
+            int rc = launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                         params + lp.off_ih_cores, xg, (long long)tc * GH,
+                                         dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
+                                         lo.part_stride, lo.nslots, 1, st);
+            if (rc > 0) return 1;
+            if (-rc > ih_slots_used) ih_slots_used = -rc;
+        }
+        // (4) fold the per-CTA partials into the gradient blob
+        if (reduce_partials(part_hh, grid, hh_slot, 0, lp.hh.core_floats, d_params + lp.off_hh_cores, st)) return 1;
+        if (reduce_partials(part_ih, ih_slots_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
+        if (d->has_bias) {
+            if (reduce_partials(part_ih, ih_slots_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) return 1;
+            if (lstm) {
+                if (axpy1(d_params + lp.off_ih_bias, d_params + lp.off_hh_bias, GH, 0, st)) return 1;
+            } else {
+                if (reduce_partials(part_hh, grid, hh_slot, lp.hh.core_floats, GH, d_params + lp.off_hh_bias, st)) return 1;
+            }
+        }
+        // (5) gradient wrt the shared initial state: sum over layers
+        if (d_h0 && axpy1(sdh, d_h0, lo.BH, l != L - 1, st)) return 1;
+        if (lstm && d_c0 && axpy1(sdc, d_c0, lo.BH, l != L - 1, st)) return 1;
+    }
+    return 0;
+}
+
+// ---- stand-alone TTLinear -----------------------------------------------------------------------
+int64_t ttrnn_ttlinear_param_count(const ttrnn_tt_shape *shape) {
+    ChainPlan p;
+    if (!shape || tt_build_plan(shape, &p)) { fail("malformed TT shape"); return -1; }
+    return p.core_floats;
+}
+
+int64_t ttrnn_ttlinear_workspace_bytes(const ttrnn_tt_shape *shape, int64_t rows) {
+    (void)rows;
+    ChainPlan p;
+    if (!shape || tt_build_plan(shape, &p)) { fail("malformed TT shape"); return -1; }
+    DevInfo dv;
+    if (get_dev(&dv)) return -1;
+    return (int64_t)r4(p.core_floats + p.n_out) * dv.sms * kMaxSlotsPerSM * 4;
+}
+
+int ttrnn_ttlinear_forward(const ttrnn_tt_shape *shape, int64_t rows, const float *x, const float *cores,
+                           const float *bias, float *y, void *scratch, void *stream) {
+    (void)scratch;
+    ChainPlan p;
+    if (!shape || tt_build_plan(shape, &p)) return fail("malformed TT shape");
+    if (rows < 1) return fail("rows must be >= 1");
+    if (!x || !cores || !y) return fail("x, cores and y must be non-null");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    if (rows > 0x7fffffffLL) return fail("rows too large");
+    return launch_ttlinear_fwd(p, dv, rows, (int)rows, x, 0, cores, bias, nullptr, y, 0, (cudaStream_t)stream);
+}
+
+int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const float *x, const float *cores,
+                            const float *dy, float *d_x, float *d_cores, float *d_bias, void *scratch, void *stream) {
+    ChainPlan p;
+    if (!shape || tt_build_plan(shape, &p)) return fail("malformed TT shape");
+    if (rows < 1 || rows > 0x7fffffffLL) return fail("rows out of range");
+    if (!x || !cores || !dy || !d_cores || !scratch) return fail("x, cores, dy, d_cores, scratch must be non-null");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nslots = dv.sms * kMaxSlotsPerSM;
+    const long long slot = p.core_floats + p.n_out;
+    float *part = (float *)scratch;
+    CU_CHECK(cudaMemsetAsync(part, 0, (size_t)slot * nslots * 4, st));
+    int rc = launch_ttlinear_bwd(p, dv, rows, (int)rows, x, 0, cores, dy, 0, d_x, 0, part, r4(slot), nslots,
+                                 d_bias != nullptr, st);
+    if (rc > 0) return 1;
+    const int used = -rc;
+    if (reduce_partials(part, used, slot, 0, p.core_floats, d_cores, st)) return 1;
+    if (d_bias && reduce_partials(part, used, slot, p.core_floats, p.n_out, d_bias, st)) return 1;
+    return 0;
+}
+
+int ttrnn_ffma_probe(int32_t iters, float *sink, double *flops_out, void *stream) {
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    if (!sink) return fail("sink must be a device pointer");
+    const int ctas = dv.sms * 8;
+    k_ffma_probe<<<ctas, TT_NTHREADS, 0, (cudaStream_t)stream>>>(iters, sink);
+    CU_CHECK(cudaGetLastError());
+    if (flops_out) *flops_out = 2.0 * 16 * 8 * (double)iters * TT_NTHREADS * ctas;
+    return 0;
+}
+
+}  // extern "C"

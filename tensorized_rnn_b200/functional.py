@@ -1,0 +1,225 @@
+"""autograd glue between the nn.Module mirror and the C ABI.
+
+One `torch.autograd.Function` per whole-sequence call: forward packs every core and bias into one
+contiguous FP32 blob (the layout of include/ttrnn_b200.h), lets torch own every buffer, and calls
+`ttrnn_rnn_forward`; backward calls `ttrnn_rnn_backward` and hands each parameter its slice of the
+gradient blob.  PyTorch is plumbing here (memory, streams, autograd bookkeeping); all arithmetic of
+the path runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor) -> None:
+    if not t.is_cuda:
+        raise RuntimeError("tensorized_rnn_b200: `%s` is on %s; the engine runs on CUDA (sm_100a) only and has "
+                           "no CPU fallback" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("tensorized_rnn_b200: `%s` must be float32 (the path is FP32 end to end), got %s"
+                        % (name, t.dtype))
+
+
+class RnnSpec(object):
+    """Static description of a TT-RNN stack: cell kind, sizes and the TT shape of every weight."""
+
+    def __init__(self, cell: str, input_size: int, hidden_size: int, has_bias: bool,
+                 ih_shapes: Sequence[Tuple[Sequence[int], Sequence[int], Sequence[int]]],
+                 hh_shapes: Sequence[Tuple[Sequence[int], Sequence[int], Sequence[int]]]):
+        assert cell in ("lstm", "gru")
+        self.cell = cell
+        self.n_gates = 4 if cell == "lstm" else 3
+        self.input_size, self.hidden_size, self.has_bias = int(input_size), int(hidden_size), bool(has_bias)
+        self.num_layers = len(ih_shapes)
+        if self.num_layers > _lib.MAX_LAYERS:
+            raise ValueError("at most %d layers are supported" % _lib.MAX_LAYERS)
+        self.ih_shapes = [tuple(list(map(int, v)) for v in s) for s in ih_shapes]   # (in_modes, out_modes, ranks)
+        self.hh_shapes = [tuple(list(map(int, v)) for v in s) for s in hh_shapes]
+        self._cache = {}
+
+    def desc(self, batch: int, seq_len: int) -> _lib.RnnDesc:
+        key = (batch, seq_len)
+        d = self._cache.get(key)
+        if d is None:
+            d = _lib.RnnDesc()
+            d.cell = _lib.CELL_LSTM if self.cell == "lstm" else _lib.CELL_GRU
+            d.num_layers, d.input_size, d.hidden_size = self.num_layers, self.input_size, self.hidden_size
+            d.has_bias, d.seq_len, d.batch = int(self.has_bias), seq_len, batch
+            for l in range(self.num_layers):
+                d.ih[l] = _lib.make_tt_shape(*self.ih_shapes[l])
+                d.hh[l] = _lib.make_tt_shape(*self.hh_shapes[l])
+            if len(self._cache) > 64:
+                self._cache.clear()
+            self._cache[key] = d
+        return d
+
+
+def _bytes_to_floats(nbytes: int) -> int:
+    return max(1, (int(nbytes) + 3) // 4)
+
+
+class _RnnFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, spec: RnnSpec, x, h0, c0, *params):
+        lib = _lib.load()
+        _require_cuda_f32("input", x)
+        for i, p in enumerate(params):
+            _require_cuda_f32("parameter %d" % i, p)
+            if p.device != x.device:
+                raise RuntimeError("parameter %d is on %s but the input is on %s" % (i, p.device, x.device))
+        B, T, I = x.shape
+        H = spec.hidden_size
+        if I != spec.input_size:
+            raise ValueError("input has %d features, the module was built for %d" % (I, spec.input_size))
+        for name, s in (("h0", h0), ("c0", c0)):
+            if s is not None:
+                _require_cuda_f32(name, s)
+                if tuple(s.shape) != (B, H):
+                    raise ValueError("%s must have shape (%d, %d), got %s" % (name, B, H, tuple(s.shape)))
+        x = x.contiguous()
+        h0c = None if h0 is None else h0.contiguous()
+        c0c = None if c0 is None else c0.contiguous()
+        desc = spec.desc(B, T)
+        with torch.cuda.device(x.device):
+            blob = torch.cat([p.detach().reshape(-1) for p in params])
+            want = lib.ttrnn_rnn_param_count(C.byref(desc))
+            if want < 0:
+                raise RuntimeError("ttrnn_rnn_param_count failed: " + _lib.last_error())
+            if want != blob.numel():
+                raise RuntimeError("parameter blob has %d floats, descriptor expects %d" % (blob.numel(), want))
+            ws = _lib.RnnWorkspace()
+            _lib.check(lib.ttrnn_rnn_workspace_bytes(C.byref(desc), C.byref(ws)), "ttrnn_rnn_workspace_bytes")
+            training = any(ctx.needs_input_grad[1:])
+            out = torch.empty((B, T, H), device=x.device, dtype=torch.float32)
+            hT = torch.empty((B, H), device=x.device, dtype=torch.float32)
+            cT = torch.empty((B, H), device=x.device, dtype=torch.float32) if spec.cell == "lstm" else None
+            saved = torch.empty(_bytes_to_floats(ws.saved_bytes), device=x.device, dtype=torch.float32) \
+                if training else None
+            scratch = torch.empty(_bytes_to_floats(ws.fwd_scratch_bytes), device=x.device, dtype=torch.float32)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.ttrnn_rnn_forward(C.byref(desc), _ptr(x), _ptr(h0c), _ptr(c0c), _ptr(blob), _ptr(out),
+                                             _ptr(hT), _ptr(cT), _ptr(saved), _ptr(scratch), stream),
+                       "ttrnn_rnn_forward")
+        if training:
+            ctx.spec = spec
+            ctx.shapes = [tuple(p.shape) for p in params]
+            ctx.bwd_floats = _bytes_to_floats(ws.bwd_scratch_bytes)
+            ctx.has_h0, ctx.has_c0 = h0 is not None, c0 is not None
+            ctx.set_materialize_grads(False)
+            ctx.save_for_backward(x, h0c, c0c, blob, out, saved)
+        if spec.cell == "lstm":
+            return out, hT, cT
+        return out, hT
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        spec: RnnSpec = ctx.spec
+        x, h0, c0, blob, out, saved = ctx.saved_tensors
+        d_out = grads[0]
+        d_hT = grads[1]
+        d_cT = grads[2] if spec.cell == "lstm" else None
+        B, T, _ = x.shape
+        H = spec.hidden_size
+        desc = spec.desc(B, T)
+        d_out = None if d_out is None else d_out.contiguous()
+        d_hT = None if d_hT is None else d_hT.contiguous()
+        d_cT = None if d_cT is None else d_cT.contiguous()
+        with torch.cuda.device(x.device):
+            d_blob = torch.empty_like(blob)
+            d_x = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+            d_h0 = torch.empty((B, H), device=x.device, dtype=torch.float32) \
+                if (ctx.has_h0 and ctx.needs_input_grad[2]) else None
+            d_c0 = torch.empty((B, H), device=x.device, dtype=torch.float32) \
+                if (spec.cell == "lstm" and ctx.has_c0 and ctx.needs_input_grad[3]) else None
+            scratch = torch.empty(ctx.bwd_floats, device=x.device, dtype=torch.float32)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.ttrnn_rnn_backward(C.byref(desc), _ptr(x), _ptr(h0), _ptr(c0), _ptr(blob), _ptr(out),
+                                              _ptr(saved), _ptr(d_out), _ptr(d_hT), _ptr(d_cT), _ptr(d_blob),
+                                              _ptr(d_x), _ptr(d_h0), _ptr(d_c0), _ptr(scratch), stream),
+                       "ttrnn_rnn_backward")
+        d_params: List[Optional[torch.Tensor]] = []
+        off = 0
+        for i, shp in enumerate(ctx.shapes):
+            n = 1
+            for v in shp:
+                n *= v
+            d_params.append(d_blob[off:off + n].view(shp) if ctx.needs_input_grad[4 + i] else None)
+            off += n
+        return (None, d_x, d_h0, d_c0) + tuple(d_params)
+
+
+def rnn_sequence(spec: RnnSpec, x: torch.Tensor, h0: Optional[torch.Tensor], c0: Optional[torch.Tensor],
+                 params: Sequence[torch.Tensor]):
+    """Run the whole stack over the whole sequence.  Returns (out, hT[, cT])."""
+    if x.dim() != 3:
+        raise ValueError("input must be (batch, seq_len, input_size), got shape %s" % (tuple(x.shape),))
+    return _RnnFunction.apply(spec, x, h0, c0, *params)
+
+
+class _TTLinearFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, shape: _lib.TTShape, n_in: int, n_out: int, x, bias, *cores):
+        lib = _lib.load()
+        _require_cuda_f32("input", x)
+        for i, p in enumerate(cores):
+            _require_cuda_f32("core %d" % i, p)
+        if bias is not None:
+            _require_cuda_f32("bias", bias)
+        if x.dim() != 2 or x.shape[1] != n_in:
+            raise ValueError("input must be (rows, %d), got %s" % (n_in, tuple(x.shape)))
+        x = x.contiguous()
+        rows = x.shape[0]
+        with torch.cuda.device(x.device):
+            blob = torch.cat([p.detach().reshape(-1) for p in cores])
+            b = None if bias is None else bias.detach().contiguous()
+            y = torch.empty((rows, n_out), device=x.device, dtype=torch.float32)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.ttrnn_ttlinear_forward(C.byref(shape), rows, _ptr(x), _ptr(blob), _ptr(b), _ptr(y),
+                                                  None, stream), "ttrnn_ttlinear_forward")
+        if any(ctx.needs_input_grad[3:]):
+            ctx.shape, ctx.core_shapes, ctx.has_bias = shape, [tuple(p.shape) for p in cores], bias is not None
+            ctx.save_for_backward(x, blob)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _lib.load()
+        x, blob = ctx.saved_tensors
+        rows = x.shape[0]
+        dy = dy.contiguous()
+        with torch.cuda.device(x.device):
+            nbytes = lib.ttrnn_ttlinear_workspace_bytes(C.byref(ctx.shape), rows)
+            if nbytes < 0:
+                raise RuntimeError("ttrnn_ttlinear_workspace_bytes failed: " + _lib.last_error())
+            scratch = torch.empty(_bytes_to_floats(nbytes), device=x.device, dtype=torch.float32)
+            d_x = torch.empty_like(x) if ctx.needs_input_grad[3] else None
+            d_blob = torch.empty_like(blob)
+            d_bias = torch.empty(dy.shape[1], device=x.device, dtype=torch.float32) \
+                if (ctx.has_bias and ctx.needs_input_grad[4]) else None
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            _lib.check(lib.ttrnn_ttlinear_backward(C.byref(ctx.shape), rows, _ptr(x), _ptr(blob), _ptr(dy), _ptr(d_x),
+                                                   _ptr(d_blob), _ptr(d_bias), _ptr(scratch), stream),
+                       "ttrnn_ttlinear_backward")
+        d_cores, off = [], 0
+        for i, shp in enumerate(ctx.core_shapes):
+            n = 1
+            for v in shp:
+                n *= v
+            d_cores.append(d_blob[off:off + n].view(shp) if ctx.needs_input_grad[5 + i] else None)
+            off += n
+        return (None, None, None, d_x, d_bias) + tuple(d_cores)
+
+
+def ttlinear(shape: _lib.TTShape, n_in: int, n_out: int, x: torch.Tensor, bias: Optional[torch.Tensor],
+             cores: Sequence[torch.Tensor]) -> torch.Tensor:
+    return _TTLinearFunction.apply(shape, n_in, n_out, x, bias, *cores)
