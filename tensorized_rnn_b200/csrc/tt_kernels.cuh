@@ -157,8 +157,8 @@ k_rnn_fwd(const __grid_constant__ RnnFwdArgs a) {
     const int tid = threadIdx.x;
     const int H = a.H, GH = a.G * a.H, R = a.R;
     float *wsm = smem;
-    float *bsm = wsm + p.w_floats;
-    float *csm = bsm + tt_round4(GH);
+    float *bsm = wsm + p.w_floats;                                     // hh bias: GRU only
+    float *csm = bsm + (a.cell == TTRNN_CELL_LSTM ? 0 : tt_round4(GH));
     float *xgs = csm + tt_round4(R * H);
     float *g = xgs + tt_round4(R * GH);
     float *hin = g + R * p.g_BS;
@@ -166,7 +166,8 @@ k_rnn_fwd(const __grid_constant__ RnnFwdArgs a) {
     float *Q = P + R * p.pp_floats[0];
 
     tt_stage_weights(p, a.cores, wsm, tid, TT_NTHREADS);
-    for (int e = tid; e < GH; e += TT_NTHREADS) bsm[e] = a.bias_hh ? __ldg(a.bias_hh + e) : 0.f;
+    if (a.cell != TTRNN_CELL_LSTM)
+        for (int e = tid; e < GH; e += TT_NTHREADS) bsm[e] = a.bias_hh ? __ldg(a.bias_hh + e) : 0.f;
     const long long ntiles = (a.B + R - 1) / R;
     for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
     const long long row0 = tile_i * R;
@@ -291,6 +292,7 @@ struct TTLinBwdArgs {
     const float *dy;
     float *dx;             // or null
     float *partial;        // [gridDim.x][core_floats + n_out]: += at the end of the launch
+    float *spill;          // [gridDim.x][R * spill_floats] or null
     int want_dbias;
 };
 
@@ -316,7 +318,14 @@ struct RnnBwdArgs {
     float *dh_out;         // (B,H) gradient wrt h_{t0-1}
     float *dc_out;         // (B,H)
     float *partial;        // [gridDim.x][core_floats + G*H]: hh core grads + hh bias grad (GRU)
+    float *spill;          // [gridDim.x][R * spill_floats] or null
 };
+
+// base of the X_k slot: shared memory or the per-CTA global spill area
+TT_DEV float *tt_slot(const ChainPlan &p, int k, int R, float *xa, float *spill) {
+    const StagePlan &s = p.st[k];
+    return (s.xsp ? spill : xa) + (long long)R * s.xall;
+}
 
 TT_DEV int tt_bd_tile_m(int code) { return code == TT_TILE_8x8 || code == TT_TILE_8x4 ? 8 : (code == TT_TILE_4x8 || code == TT_TILE_4x4 ? 4 : (code == TT_TILE_2x4 ? 2 : 1)); }
 
@@ -343,12 +352,12 @@ TT_DEV void tt_stage_bwd_weight_dispatch(const StagePlan &s, int R, const float 
 
 // Forward chain keeping every X_k in its own slot (xall offsets); stops before stage `kstop`
 // (kstop = 0 runs all stages and writes G; kstop = 1 skips the last GEMM).
-TT_DEV void tt_chain_fwd_keep(const ChainPlan &p, const int *tile, int R, float *xa, float *g, const float *wsm,
-                              int kstop, int tid) {
+TT_DEV void tt_chain_fwd_keep(const ChainPlan &p, const int *tile, int R, float *xa, float *spill, float *g,
+                              const float *wsm, int kstop, int tid) {
     for (int k = p.d - 1; k >= kstop; --k) {
         const StagePlan &s = p.st[k];
-        const float *X = xa + R * s.xall;
-        float *Y = (k == 0) ? g : xa + R * p.st[k - 1].xall;
+        const float *X = tt_slot(p, k, R, xa, spill);
+        float *Y = (k == 0) ? g : tt_slot(p, k - 1, R, xa, spill);
         tt_stage_fwd(s, tile[k], R, X, wsm + s.w_off, Y, tid, TT_NTHREADS);
         __syncthreads();
     }
@@ -356,12 +365,12 @@ TT_DEV void tt_chain_fwd_keep(const ChainPlan &p, const int *tile, int R, float 
 
 // Backward chain.  On entry G holds dY_0 and slot k holds X_k; on exit `dxin` (X_{d-1} layout)
 // holds dX_{d-1} if want_dx.  Slot k (k < d-1) is overwritten by dX_k.
-TT_DEV void tt_chain_bwd(const ChainPlan &p, const int *tile_bd, const int *mg, int R, float *xa, float *g,
-                         float *dxin, const float *wsm, float *dws, bool want_dx, int tid) {
+TT_DEV void tt_chain_bwd(const ChainPlan &p, const int *tile_bd, const int *mg, int R, float *xa, float *spill,
+                         float *g, float *dxin, const float *wsm, float *dws, bool want_dx, int tid) {
     for (int k = 0; k < p.d; ++k) {
         const StagePlan &s = p.st[k];
-        float *X = xa + R * s.xall;
-        const float *dY = (k == 0) ? g : xa + R * p.st[k - 1].xall;
+        float *X = tt_slot(p, k, R, xa, spill);
+        const float *dY = (k == 0) ? g : tt_slot(p, k - 1, R, xa, spill);
         tt_stage_bwd_weight_dispatch(s, R, X, dY, dws + s.w_off, mg[k], tid, TT_NTHREADS);
         if (k == p.d - 1 && !want_dx) break;
         float *dX = (k == p.d - 1) ? dxin : X;
@@ -404,11 +413,13 @@ k_ttlinear_bwd(const __grid_constant__ TTLinBwdArgs a) {
     float *xa = dbs + tt_round4(p.n_out);
     float *g = xa + R * p.all_floats;
     float *dxin = g + R * p.g_BS;
+    float *spill = a.spill ? a.spill + (long long)blockIdx.x * R * p.spill_floats : nullptr;
 
     tt_stage_weights(p, a.cores, wsm, tid, TT_NTHREADS);
     for (int e = tid; e < p.w_floats; e += TT_NTHREADS) dws[e] = 0.f;
     for (int e = tid; e < p.n_out; e += TT_NTHREADS) dbs[e] = 0.f;
     const StagePlan &sl = p.st[p.d - 1];
+    float *xslot = tt_slot(p, p.d - 1, R, xa, spill);
     const int nin = p.n_in, nout = p.n_out;
     const long long ntiles = (a.rows + R - 1) / R;
     __syncthreads();
@@ -422,7 +433,7 @@ k_ttlinear_bwd(const __grid_constant__ TTLinBwdArgs a) {
                 const long long bb = row / a.rows_per_b, tt = row - bb * a.rows_per_b;
                 v = __ldg(a.x + bb * a.x_bstride + tt * nin + c);
             }
-            xa[R * sl.xall + b * sl.BS + tt_in_index(p, c)] = v;
+            xslot[b * sl.BS + tt_in_index(p, c)] = v;
         }
         // dy rows -> G layout; bias gradient = column sums (one owner thread per column)
         for (int c = tid; c < nout; c += TT_NTHREADS) {
@@ -441,8 +452,8 @@ k_ttlinear_bwd(const __grid_constant__ TTLinBwdArgs a) {
             dbs[c] += sum;
         }
         __syncthreads();
-        tt_chain_fwd_keep(p, a.tile, R, xa, g, wsm, /*kstop=*/1, tid);
-        tt_chain_bwd(p, a.tile_bd, a.mg, R, xa, g, dxin, wsm, dws, a.dx != nullptr, tid);
+        tt_chain_fwd_keep(p, a.tile, R, xa, spill, g, wsm, /*kstop=*/1, tid);
+        tt_chain_bwd(p, a.tile_bd, a.mg, R, xa, spill, g, dxin, wsm, dws, a.dx != nullptr, tid);
         if (a.dx) {
             for (int e = tid; e < R * nin; e += TT_NTHREADS) {
                 const int b = e / nin, c = e - b * nin;
@@ -470,27 +481,30 @@ k_rnn_bwd(const __grid_constant__ RnnBwdArgs a) {
     const int tid = threadIdx.x, R = a.R, H = a.H, GH = a.G * a.H;
     float *wsm = smem;
     float *dws = wsm + p.w_floats;
+    const bool lstm = (a.cell == TTRNN_CELL_LSTM);
+    const int nbias = lstm ? 0 : tt_round4(GH);      // hh bias and its gradient: GRU only
     float *bsm = dws + p.w_floats;
-    float *dbs = bsm + tt_round4(GH);
-    float *xa = dbs + tt_round4(GH);
+    float *dbs = bsm + nbias;
+    float *xa = dbs + nbias;
     float *g = xa + R * p.all_floats;
     float *xgs = g + R * p.g_BS;
+    float *spill = a.spill ? a.spill + (long long)blockIdx.x * R * p.spill_floats : nullptr;
     float *dhc = xgs + tt_round4(R * GH);
     float *dhd = dhc + R * p.in_BS;
     float *dcs = dhd + tt_round4(R * H);
     float *cps = dcs + tt_round4(R * H);
 
     const StagePlan &sl = p.st[p.d - 1];
-    float *hslot = xa + R * sl.xall;
-    const bool lstm = (a.cell == TTRNN_CELL_LSTM);
+    float *hslot = tt_slot(p, p.d - 1, R, xa, spill);
     const bool vec16 = (GH % 4 == 0);
 
     tt_stage_weights(p, a.cores, wsm, tid, TT_NTHREADS);
     for (int e = tid; e < p.w_floats; e += TT_NTHREADS) dws[e] = 0.f;
-    for (int e = tid; e < GH; e += TT_NTHREADS) {
-        bsm[e] = a.bias_hh ? __ldg(a.bias_hh + e) : 0.f;
-        dbs[e] = 0.f;
-    }
+    if (!lstm)
+        for (int e = tid; e < GH; e += TT_NTHREADS) {
+            bsm[e] = a.bias_hh ? __ldg(a.bias_hh + e) : 0.f;
+            dbs[e] = 0.f;
+        }
     const long long ntiles = (a.B + R - 1) / R;
     for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
         const long long row0 = tile_i * R;
@@ -542,8 +556,8 @@ k_rnn_bwd(const __grid_constant__ RnnBwdArgs a) {
             // ---- recompute the hh chain, keeping every intermediate
             for (int k = p.d - 1; k >= 0; --k) {
                 const StagePlan &s = p.st[k];
-                const float *X = xa + R * s.xall;
-                float *Y = (k == 0) ? g : xa + R * p.st[k - 1].xall;
+                const float *X = tt_slot(p, k, R, xa, spill);
+                float *Y = (k == 0) ? g : tt_slot(p, k - 1, R, xa, spill);
                 tt_stage_fwd(s, a.tile[k], R, X, wsm + s.w_off, Y, tid, TT_NTHREADS);
                 if (k == 0) tt_cp_async_wait_all();
                 __syncthreads();
@@ -606,7 +620,7 @@ k_rnn_bwd(const __grid_constant__ RnnBwdArgs a) {
             }
             __syncthreads();
             // ---- backward chain: core gradients and dh_{t-1}
-            tt_chain_bwd(p, a.tile_bd, a.mg, R, xa, g, dhc, wsm, dws, true, tid);
+            tt_chain_bwd(p, a.tile_bd, a.mg, R, xa, spill, g, dhc, wsm, dws, true, tid);
         }
         for (int e = tid; e < R * H; e += TT_NTHREADS) {
             const int b = e / H, h = e - b * H;

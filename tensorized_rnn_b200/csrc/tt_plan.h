@@ -40,7 +40,8 @@ struct StagePlan {
     int w_off;  // offset of W_k inside the shared-memory weight area (floats)
     int c_off;  // offset of core k inside the core blob (floats)
     int xpp;    // ping-pong slot of X_k for forward-only chains: 0 = input slot, 1 = P, 2 = Q
-    int xall;   // per-batch-row offset of X_k when every X_k is kept (backward)
+    int xall;   // per-batch-row offset of X_k when every X_k is kept (backward), inside its space
+    int xsp;    // backward only: 0 = X_k slot in shared memory, 1 = in the global (L2-resident) spill area
 };
 
 struct ChainPlan {
@@ -53,7 +54,8 @@ struct ChainPlan {
     int g_BS;        // stage-0 output buffer G: batch-row stride
     int in_BS;       // per-batch-row floats of X_{d-1} (the chain input)
     int pp_floats[2];// per-batch-row floats of ping-pong slots P, Q
-    int all_floats;  // per-batch-row floats of X_{d-1..0} when all are kept
+    int all_floats;  // per-batch-row shared-memory floats of the kept X_k slots (backward)
+    int spill_floats;// per-batch-row floats of the X_k slots placed in the global spill area
     StagePlan st[TT_MAX_D];
 };
 
@@ -137,5 +139,33 @@ static inline int tt_build_plan(const ttrnn_tt_shape *s, ChainPlan *p) {
         }
     }
     p->all_floats = all;
+    p->spill_floats = 0;
+    for (int k = 0; k < d; ++k) p->st[k].xsp = 0;
     return 0;
+}
+
+// Backward keeps every X_k alive at once.  When they do not fit the shared-memory budget
+// (floats per batch row), the largest slots are moved to a per-CTA global scratch area that
+// stays L1/L2 resident.  Recomputes xall offsets inside each space.
+static inline void tt_place_slots(ChainPlan *p, long long budget_floats_per_row) {
+    const int d = p->d;
+    for (int k = 0; k < d; ++k) p->st[k].xsp = 0;
+    long long in_smem = 0;
+    for (int k = 0; k < d; ++k) in_smem += tt_round4(p->st[k].BS);
+    while (in_smem > budget_floats_per_row) {
+        int big = -1;
+        for (int k = 0; k < d; ++k)
+            if (!p->st[k].xsp && (big < 0 || p->st[k].BS > p->st[big].BS)) big = k;
+        if (big < 0) break;
+        p->st[big].xsp = 1;
+        in_smem -= tt_round4(p->st[big].BS);
+    }
+    int a = 0, sp = 0;
+    for (int k = d - 1; k >= 0; --k) {
+        StagePlan &t = p->st[k];
+        if (t.xsp) { t.xall = sp; sp += tt_round4(t.BS); }
+        else       { t.xall = a;  a += tt_round4(t.BS); }
+    }
+    p->all_floats = a;
+    p->spill_floats = sp;
 }

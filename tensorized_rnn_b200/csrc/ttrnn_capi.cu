@@ -97,15 +97,21 @@ long long smem_ttlin_fwd(const ChainPlan &p, int R) {
     return p.w_floats + (long long)R * (p.in_BS + p.pp_floats[0] + p.pp_floats[1] + p.g_BS);
 }
 long long smem_rnn_fwd(const ChainPlan &p, int R, int H, int G) {
-    return p.w_floats + r4(G * H) + r4((long long)R * H) + r4((long long)R * G * H) +
+    return p.w_floats + (G == 4 ? 0 : r4(G * H)) + r4((long long)R * H) + r4((long long)R * G * H) +
            (long long)R * (p.g_BS + p.in_BS + p.pp_floats[0] + p.pp_floats[1]);
 }
-long long smem_ttlin_bwd(const ChainPlan &p, int R) {
-    return 2LL * p.w_floats + r4(p.n_out) + (long long)R * (p.all_floats + p.g_BS + p.in_BS);
+// backward footprints split into the part that does not depend on where the X_k slots live ...
+long long smem_ttlin_bwd_fixed(const ChainPlan &p, int R) {
+    return 2LL * p.w_floats + r4(p.n_out) + (long long)R * (p.g_BS + p.in_BS);
 }
-long long smem_rnn_bwd(const ChainPlan &p, int R, int H, int G) {
-    return 2LL * p.w_floats + 2 * r4(G * H) + (long long)R * (p.all_floats + p.g_BS + p.in_BS) +
+long long smem_rnn_bwd_fixed(const ChainPlan &p, int R, int H, int G) {
+    return 2LL * p.w_floats + (G == 4 ? 0 : 2 * r4(G * H)) + (long long)R * (p.g_BS + p.in_BS) +
            r4((long long)R * G * H) + 3 * r4((long long)R * H);
+}
+// ... plus the shared-memory X_k slots (p.all_floats reflects the current placement)
+long long smem_ttlin_bwd(const ChainPlan &p, int R) { return smem_ttlin_bwd_fixed(p, R) + (long long)R * p.all_floats; }
+long long smem_rnn_bwd(const ChainPlan &p, int R, int H, int G) {
+    return smem_rnn_bwd_fixed(p, R, H, G) + (long long)R * p.all_floats;
 }
 
 template <class F>
@@ -118,6 +124,38 @@ int pick_rows(F smem_floats, int smem_limit_bytes, int rmax, long long units, in
     if (opt > 0) return (int)(opt < R ? opt : R);
     while (R > 1 && (units + R - 1) / R < (long long)want_ctas_per_sm * sms) --R;
     return R;
+}
+
+// Backward launch configuration: rows per CTA, slot placement (shared vs spill), footprints.
+struct BwdCfg {
+    ChainPlan p;            // plan with the slot placement applied
+    int R = 0;
+    size_t smem = 0;        // bytes
+    long long spill = 0;    // floats of global spill per CTA
+};
+
+template <class Fixed>
+int plan_bwd(const ChainPlan &base, Fixed fixed_floats, const DevInfo &dv, long long units, BwdCfg *c,
+             const char *what) {
+    c->p = base;
+    auto total = [&](int r) { return fixed_floats(r) + (long long)r * base.all_floats; };
+    int R = pick_rows(total, dv.smem_optin, 8, units, dv.sms, 2);
+    if (R > 0) {
+        c->R = R;
+        c->smem = (size_t)total(R) * 4;
+        c->spill = 0;
+        return 0;
+    }
+    // one row per CTA, largest X_k slots moved to the L2-resident spill area
+    const long long budget = dv.smem_optin / 4 - fixed_floats(1);
+    if (budget < 0)
+        return fail("%s: cores alone need %lld bytes of shared memory (limit %d): unsupported TT shape", what,
+                    fixed_floats(1) * 4, dv.smem_optin);
+    tt_place_slots(&c->p, budget);
+    c->R = 1;
+    c->smem = (size_t)(fixed_floats(1) + c->p.all_floats) * 4;
+    c->spill = c->p.spill_floats;
+    return 0;
 }
 
 template <class K>
@@ -185,7 +223,7 @@ struct RnnLayout {
     // fwd scratch (floats)
     long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_total = 0;
     // bwd scratch (floats)
-    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_total = 0;
+    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
     int nslots = 0;
 };
@@ -231,6 +269,18 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->b_sdc = o; o += r4(lo->BH);
     lo->b_part_hh = o; o += lo->part_stride * lo->nslots;
     lo->b_part_ih = o; o += lo->part_stride * lo->nslots;
+    // spill area for backward X_k slots that do not fit in shared memory (worst layer, either kernel)
+    long long spill = 0;
+    for (int l = 0; l < L; ++l) {
+        BwdCfg c;
+        const ChainPlan &hh = rp.layer[l].hh, &ih = rp.layer[l].ih;
+        const int Hh = (int)H, Gg = rp.G;
+        if (plan_bwd(hh, [&](int r) { return smem_rnn_bwd_fixed(hh, r, Hh, Gg); }, dv, B, &c, "hh backward")) return 1;
+        if (c.spill > spill) spill = c.spill;
+        if (plan_bwd(ih, [&](int r) { return smem_ttlin_bwd_fixed(ih, r); }, dv, B * tc, &c, "ih backward")) return 1;
+        if (c.spill > spill) spill = c.spill;
+    }
+    lo->b_spill = o; o += r4(spill) * lo->nslots;
     lo->b_total = o;
     return 0;
 }
@@ -259,33 +309,30 @@ int launch_ttlinear_fwd(const ChainPlan &p, const DevInfo &dv, long long rows, i
     return 0;
 }
 
-int launch_ttlinear_bwd(const ChainPlan &p, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
+int launch_ttlinear_bwd(const ChainPlan &p0, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
                         long long x_bstride, const float *cores, const float *dy, long long dy_bstride, float *dx,
-                        long long dx_bstride, float *partial, long long part_stride, int nslots, int want_dbias,
-                        cudaStream_t st) {
+                        long long dx_bstride, float *partial, int nslots, float *spill, int want_dbias,
+                        cudaStream_t st, int *slots_used) {
+    BwdCfg c;
+    if (plan_bwd(p0, [&](int r) { return smem_ttlin_bwd_fixed(p0, r); }, dv, rows, &c, "TT matvec backward")) return 1;
     TTLinBwdArgs a;
     memset(&a, 0, sizeof a);
-    a.p = p;
-    const int R = pick_rows([&](int r) { return smem_ttlin_bwd(p, r); }, dv.smem_optin, 8, rows, dv.sms, 2);
-    if (R == 0)
-        return fail("TT shape needs %lld bytes of shared memory for the backward row tile (limit %d): unsupported",
-                    smem_ttlin_bwd(p, 1) * 4, dv.smem_optin);
-    a.R = R;
-    fill_tiles(p, R, a.tile, a.tile_bd, a.mg);
+    a.p = c.p;
+    a.R = c.R;
+    fill_tiles(c.p, c.R, a.tile, a.tile_bd, a.mg);
     a.rows = rows; a.rows_per_b = rows_per_b;
     a.x_bstride = x_bstride; a.dy_bstride = dy_bstride; a.dx_bstride = dx_bstride;
     a.x = x; a.cores = cores; a.dy = dy; a.dx = dx; a.partial = partial; a.want_dbias = want_dbias;
-    if (p.core_floats + p.n_out > part_stride) return fail("internal: partial slot too small");
-    const size_t smem = (size_t)smem_ttlin_bwd(p, R) * 4;
+    if (c.spill > 0 && !spill) return fail("internal: spill area required but not provided");
+    a.spill = c.spill > 0 ? spill : nullptr;
     int grid = 0;
-    if (grid_for(k_ttlinear_bwd, smem, (rows + R - 1) / R, dv, &grid)) return 1;
+    if (grid_for(k_ttlinear_bwd, c.smem, (rows + c.R - 1) / c.R, dv, &grid)) return 1;
     if (grid > nslots) grid = nslots;
-    // the kernel addresses its slot as blockIdx.x * (core_floats + n_out); keep that contract
-    (void)part_stride;
-    k_ttlinear_bwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+    k_ttlinear_bwd<<<grid, TT_NTHREADS, c.smem, st>>>(a);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
-    return grid > 0 ? -grid : 1;   // negative = number of slots used (success)
+    if (slots_used && grid > *slots_used) *slots_used = grid;
+    return 0;
 }
 
 int reduce_partials(const float *partial, int nslots, long long slot_stride, long long off, int n, float *out,
@@ -457,18 +504,18 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
 
         RnnBwdArgs a;
         memset(&a, 0, sizeof a);
-        a.p = lp.hh;
-        const int R = pick_rows([&](int r) { return smem_rnn_bwd(lp.hh, r, H, G); }, dv.smem_optin, 8, B, dv.sms, 2);
-        if (R == 0)
-            return fail("layer %d: hh TT shape needs %lld bytes of shared memory per CTA for BPTT (limit %d): unsupported",
-                        l, smem_rnn_bwd(lp.hh, 1, H, G) * 4, dv.smem_optin);
+        BwdCfg cfg;
+        if (plan_bwd(lp.hh, [&](int r) { return smem_rnn_bwd_fixed(lp.hh, r, H, G); }, dv, B, &cfg, "hh backward")) return 1;
+        a.p = cfg.p;
+        const int R = cfg.R;
         a.R = R;
-        fill_tiles(lp.hh, R, a.tile, a.tile_bd, a.mg);
+        a.spill = cfg.spill > 0 ? sc + lo.b_spill : nullptr;
+        fill_tiles(cfg.p, R, a.tile, a.tile_bd, a.mg);
         a.cell = d->cell; a.H = H; a.G = G; a.B = B; a.T = T;
         a.cores = params + lp.off_hh_cores;
         a.bias_hh = lstm ? nullptr : b_hh;
         a.hs = lout; a.cs = lcs; a.h0 = h0; a.c0 = c0; a.dhs = dhs;
-        const size_t smem = (size_t)smem_rnn_bwd(lp.hh, R, H, G) * 4;
+        const size_t smem = cfg.smem;
         int grid = 0;
         if (grid_for(k_rnn_bwd, smem, (B + R - 1) / R, dv, &grid)) return 1;
         if (grid > lo.nslots) grid = lo.nslots;
@@ -498,12 +545,11 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             ++g_launches;
             CU_CHECK(cudaGetLastError());
             // (3) ih backward over the chunk: core grads, bias grad, gradient wrt the layer input
-            int rc = launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                         params + lp.off_ih_cores, xg, (long long)tc * GH,
-                                         dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
-                                         lo.part_stride, lo.nslots, 1, st);
-            if (rc > 0) return 1;
-            if (-rc > ih_slots_used) ih_slots_used = -rc;
+            if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                    params + lp.off_ih_cores, xg, (long long)tc * GH,
+                                    dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
+                                    lo.nslots, sc + lo.b_spill, 1, st, &ih_slots_used))
+                return 1;
         }
         // (4) fold the per-CTA partials into the gradient blob
         if (reduce_partials(part_hh, grid, hh_slot, 0, lp.hh.core_floats, d_params + lp.off_hh_cores, st)) return 1;
@@ -531,12 +577,14 @@ int64_t ttrnn_ttlinear_param_count(const ttrnn_tt_shape *shape) {
 }
 
 int64_t ttrnn_ttlinear_workspace_bytes(const ttrnn_tt_shape *shape, int64_t rows) {
-    (void)rows;
     ChainPlan p;
     if (!shape || tt_build_plan(shape, &p)) { fail("malformed TT shape"); return -1; }
     DevInfo dv;
     if (get_dev(&dv)) return -1;
-    return (int64_t)r4(p.core_floats + p.n_out) * dv.sms * kMaxSlotsPerSM * 4;
+    BwdCfg c;
+    if (plan_bwd(p, [&](int r) { return smem_ttlin_bwd_fixed(p, r); }, dv, rows > 0 ? rows : 1, &c, "TT matvec backward"))
+        return -1;
+    return (int64_t)(r4(p.core_floats + p.n_out) + r4(c.spill)) * dv.sms * kMaxSlotsPerSM * 4;
 }
 
 int ttrnn_ttlinear_forward(const ttrnn_tt_shape *shape, int64_t rows, const float *x, const float *cores,
@@ -565,10 +613,11 @@ int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const flo
     const long long slot = p.core_floats + p.n_out;
     float *part = (float *)scratch;
     CU_CHECK(cudaMemsetAsync(part, 0, (size_t)slot * nslots * 4, st));
-    int rc = launch_ttlinear_bwd(p, dv, rows, (int)rows, x, 0, cores, dy, 0, d_x, 0, part, r4(slot), nslots,
-                                 d_bias != nullptr, st);
-    if (rc > 0) return 1;
-    const int used = -rc;
+    int used = 0;
+    float *spill = part + r4(slot) * nslots;
+    if (launch_ttlinear_bwd(p, dv, rows, (int)rows, x, 0, cores, dy, 0, d_x, 0, part, nslots, spill,
+                            d_bias != nullptr, st, &used))
+        return 1;
     if (reduce_partials(part, used, slot, 0, p.core_floats, d_cores, st)) return 1;
     if (d_bias && reduce_partials(part, used, slot, p.core_floats, p.n_out, d_bias, st)) return 1;
     return 0;
