@@ -122,6 +122,18 @@ int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const flo
 int ttrnn_ffma_probe(int32_t iters, float *sink, double *flops_out, void *stream);
 /* counts kernels launched by this library since the last reset (host counter) */
 int64_t ttrnn_launch_count(int32_t reset);
+/* Per-kernel device timing for the roofline report.  ttrnn_kernel_timing(1) makes every launch
+ * of the four main kernels record a CUDA-event pair on its own stream (bounded pool; extra
+ * launches are simply not recorded); ttrnn_kernel_timing(0) stops.  ttrnn_kernel_times()
+ * synchronises the recorded events, adds their elapsed milliseconds into ms[kind] and the
+ * number of recorded launches into count[kind], and clears the pool.  Kinds: */
+#define TTRNN_K_TTLINEAR_FWD 0
+#define TTRNN_K_RNN_FWD      1
+#define TTRNN_K_RNN_BWD      2
+#define TTRNN_K_TTLINEAR_BWD 3
+#define TTRNN_K_KINDS        4
+int ttrnn_kernel_timing(int32_t enable);
+int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K_KINDS]*/);
 
 /* Tuning knobs (process-wide; also read from the environment at load time):
  *   "rows_per_cta"  batch rows owned by one CTA of the recurrent kernels (0 = auto)

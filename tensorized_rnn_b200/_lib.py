@@ -51,6 +51,8 @@ SYMBOLS = {
     "ttrnn_ttlinear_backward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 8),
     "ttrnn_ffma_probe": (C.c_int, [C.c_int32, _P, C.POINTER(C.c_double), _P]),
     "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
+    "ttrnn_kernel_timing": (C.c_int, [C.c_int32]),
+    "ttrnn_kernel_times": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "ttrnn_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
 }
 

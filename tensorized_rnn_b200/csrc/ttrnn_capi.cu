@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "tt_kernels.cuh"
 
@@ -16,6 +18,36 @@ std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_rows{0};
 std::atomic<long long> g_opt_chunk{0};
 std::atomic<long long> g_opt_chunk_bytes{4LL << 30};
+
+// ---- optional per-kernel event timing (bench only) -----------------------------------------
+struct TimedLaunch { int kind; cudaEvent_t a, b; };
+std::mutex g_time_mu;
+std::vector<TimedLaunch> g_timed;
+std::atomic<int> g_timing{0};
+constexpr size_t kMaxTimed = 8192;
+
+struct KernelTimer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    int kind;
+    cudaStream_t st;
+    bool on = false;
+    KernelTimer(int kind_, cudaStream_t st_) : kind(kind_), st(st_) {
+        if (!g_timing.load()) return;
+        {
+            std::lock_guard<std::mutex> lk(g_time_mu);
+            if (g_timed.size() >= kMaxTimed) return;
+        }
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+        on = true;
+        cudaEventRecord(a, st);
+    }
+    ~KernelTimer() {
+        if (!on) return;
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        g_timed.push_back({kind, a, b});
+    }
+};
 
 int fail(const char *fmt, ...) {
     char buf[1024];
@@ -303,7 +335,10 @@ int launch_ttlinear_fwd(const ChainPlan &p, const DevInfo &dv, long long rows, i
     const size_t smem = (size_t)smem_ttlin_fwd(p, R) * 4;
     int grid = 0;
     if (grid_for(k_ttlinear_fwd, smem, (rows + R - 1) / R, dv, &grid)) return 1;
-    k_ttlinear_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+    {
+        KernelTimer tm(TTRNN_K_TTLINEAR_FWD, st);
+        k_ttlinear_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+    }
     ++g_launches;
     CU_CHECK(cudaGetLastError());
     return 0;
@@ -328,7 +363,10 @@ int launch_ttlinear_bwd(const ChainPlan &p0, const DevInfo &dv, long long rows, 
     int grid = 0;
     if (grid_for(k_ttlinear_bwd, c.smem, (rows + c.R - 1) / c.R, dv, &grid)) return 1;
     if (grid > nslots) grid = nslots;
-    k_ttlinear_bwd<<<grid, TT_NTHREADS, c.smem, st>>>(a);
+    {
+        KernelTimer tm(TTRNN_K_TTLINEAR_BWD, st);
+        k_ttlinear_bwd<<<grid, TT_NTHREADS, c.smem, st>>>(a);
+    }
     ++g_launches;
     CU_CHECK(cudaGetLastError());
     if (slots_used && grid > *slots_used) *slots_used = grid;
@@ -363,6 +401,31 @@ int64_t ttrnn_launch_count(int32_t reset) {
     long long v = g_launches.load();
     if (reset) g_launches.store(0);
     return v;
+}
+
+int ttrnn_kernel_timing(int32_t enable) {
+    g_timing.store(enable ? 1 : 0);
+    return 0;
+}
+
+int ttrnn_kernel_times(double *ms, int64_t *count) {
+    if (!ms || !count) return fail("ms and count must be non-null");
+    std::vector<TimedLaunch> recs;
+    {
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        recs.swap(g_timed);
+    }
+    for (auto &r : recs) {
+        float t = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess &&
+            r.kind >= 0 && r.kind < TTRNN_K_KINDS) {
+            ms[r.kind] += t;
+            count[r.kind] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    return 0;
 }
 
 int ttrnn_set_option(const char *key, int64_t value) {
@@ -459,7 +522,10 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
             a.c_save = csave ? csave + (long long)t0 * H : nullptr;
             a.h_out = (last && l == L - 1 && hT) ? hT : st_h;
             a.c_out = (last && l == L - 1 && cT) ? cT : st_c;
-            k_rnn_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+            {
+                KernelTimer tm(TTRNN_K_RNN_FWD, st);
+                k_rnn_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+            }
             ++g_launches;
             CU_CHECK(cudaGetLastError());
         }
@@ -541,7 +607,10 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             a.dh_in = last ? (l == L - 1 ? d_hT : nullptr) : sdh;
             a.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
             a.dh_out = sdh; a.dc_out = sdc;
-            k_rnn_bwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+            {
+                KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                k_rnn_bwd<<<grid, TT_NTHREADS, smem, st>>>(a);
+            }
             ++g_launches;
             CU_CHECK(cudaGetLastError());
             // (3) ih backward over the chunk: core grads, bias grad, gradient wrt the layer input

@@ -1,0 +1,148 @@
+"""Host-side logic of the module mirror: construction, state_dict contract, init parity, error paths.
+No compute (there is no CPU path to compute with)."""
+import copy
+import ctypes
+import io
+import os
+import re
+from contextlib import redirect_stdout
+
+import numpy as np
+import pytest
+import torch
+
+import tensorized_rnn_b200 as tr
+from tensorized_rnn_b200 import _lib
+from helpers import ROOT, build_module, golden_index, load_golden, quiet, state_dict_from_golden
+
+CASES = golden_index()
+
+
+@pytest.mark.parametrize("case", CASES[:11], ids=[c["name"] for c in CASES[:11]])
+def test_state_dict_keys_shapes_and_init_stream_match_reference(case):
+    """Same seed -> bit-identical parameters (same RNG consumption order, same distribution)."""
+    g = load_golden(case["name"])
+    ref_sd = state_dict_from_golden(g)
+    torch.manual_seed(case["seed"])
+    m = build_module(case)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref_sd.keys())
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(ref_sd[k].shape), k
+        assert torch.equal(sd[k], ref_sd[k]), k
+    m.load_state_dict(ref_sd)            # reference checkpoints load
+
+
+def test_param_count_and_attributes():
+    m = quiet(tr.TTLSTM, 40, 256, 3, torch.device("cpu"), n_cores=3, tt_rank=8)
+    assert m.param_count() == 35840
+    g = quiet(tr.TTGRU, 1, 256, 1, torch.device("cpu"), n_cores=2, tt_rank=4)
+    assert g.param_count() == 5344                        # cfg2
+    for attr in ("input_size", "hidden_size", "num_layers", "bias", "device", "log_grads", "n_cores",
+                 "tt_rank", "is_naive", "new_core", "_all_layers"):
+        assert hasattr(m, attr), attr
+    assert m._all_layers[1] is m.cell1
+    lin = m.cell0.input_weights
+    assert lin.shape == [[2, 4, 5], [8, 8, 16]]
+    assert lin.weight_t.raw_shape == [[8, 8, 16], [2, 4, 5]]
+    assert lin.weight_t.shape == [1024, 40]
+    assert lin.weight_t.ranks == [1, 8, 8, 1]
+    assert lin.weight_t.ndims == 3
+    assert callable(lin.parameters) and len(list(lin.parameters())) == 4
+    h, c = m.init_hidden(5)
+    assert h.shape == (5, 256) and c.shape == (5, 256) and float(h.abs().sum()) == 0.0
+
+
+def test_cores_shared_between_weight_t_and_parameter_list():
+    m = quiet(tr.TTGRU, 12, 24, 2, torch.device("cpu"), n_cores=2, tt_rank=2)
+    for mod in (m, copy.deepcopy(m), copy.deepcopy(m).double()):
+        lin = mod.cell1.hidden_weights
+        plist = lin._modules["parameters"]
+        for a, b in zip(lin.weight_t.tt_cores, plist):
+            assert a is b
+    assert all(getattr(p, "is_tt", False) for p in m.cell1.hidden_weights._modules["parameters"])
+
+
+def test_bias_false_drops_bias_keys():
+    m = quiet(tr.TTGRU, 28, 64, 2, torch.device("cpu"), n_cores=3, tt_rank=3, bias=False)
+    assert not any(k.endswith(".bias") for k in m.state_dict())
+    assert m.cell0.input_weights.bias is None
+
+
+def test_new_core_variants_build_with_reference_shapes():
+    m = quiet(tr.TTLSTM, 40, 64, 1, torch.device("cpu"), n_cores=2, tt_rank=2, new_core="last")
+    shapes = [tuple(p.shape) for p in m.cell0.input_weights.weight_t.tt_cores]
+    assert shapes == [(1, 8, 5, 2), (2, 8, 8, 2), (2, 4, 1, 1)]
+    m = quiet(tr.TTGRU, 40, 64, 1, torch.device("cpu"), n_cores=2, tt_rank=2, new_core="first")
+    assert tuple(m.cell0.hidden_weights.weight_t.tt_cores[0].shape) == (1, 3, 1, 2)
+
+
+def test_unsupported_options_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        quiet(tr.TTLSTM, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2, is_naive=True)
+    with pytest.raises(NotImplementedError):
+        quiet(tr.TTGRU, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2, log_grads=True)
+    with pytest.raises(AssertionError):
+        quiet(tr.TTGRU, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2, new_core="middle")
+
+
+def test_no_cpu_fallback():
+    m = quiet(tr.TTLSTM, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 3, 4))
+    lin = quiet(tr.TTLinear, in_features=16, out_features=8, d=2, tt_rank=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lin(torch.zeros(2, 16))
+    with pytest.raises(NameError):
+        m(torch.zeros(2, 0, 4))
+
+
+def test_ttlinear_prints_like_reference_and_matches_init():
+    buf = io.StringIO()
+    torch.manual_seed(2000)
+    with redirect_stdout(buf):
+        lin = tr.TTLinear(in_features=256, out_features=10, bias=True, auto_shapes=True, d=2, tt_rank=4)
+    assert "Created TTLinear layer with input shape: [16, 16]. output shape: [2, 5]" in buf.getvalue()
+    g = dict(np.load(os.path.join(ROOT, "tests", "golden", "ttlinear_0.npz")))
+    for k, v in lin.state_dict().items():
+        assert torch.equal(v, torch.from_numpy(g["param:" + k])), k
+
+
+def test_tensor_train_full_matches_oracle_dense():
+    from helpers import oracle
+    lin = quiet(tr.TTLinear, in_features=40, out_features=64, d=3, tt_rank=4)
+    w = lin.weight_t.full()
+    assert w.shape == (64, 40)
+    assert torch.allclose(w, oracle.tt_dense([c.detach() for c in lin.weight_t.tt_cores]), atol=1e-6)
+
+
+# ---- the C-ABI library: loads on a CPU-only box and exports what the header declares ----------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "ttrnn_b200.h")).read()
+    declared = set(re.findall(r"\b(ttrnn_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(_lib.lib_path())
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    assert declared == set(_lib.SYMBOLS), "python binding and header disagree: %s" % (declared ^ set(_lib.SYMBOLS))
+    assert _lib.load().ttrnn_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    # sizes implied by include/ttrnn_b200.h
+    assert ctypes.sizeof(_lib.TTShape) == 4 * (1 + 6 + 6 + 7)
+    assert ctypes.sizeof(_lib.RnnDesc) == 4 * 6 + 8 + 2 * 8 * ctypes.sizeof(_lib.TTShape)
+
+
+def test_descriptor_validation_without_gpu():
+    lib = _lib.load()
+    m = quiet(tr.TTLSTM, 40, 256, 3, torch.device("cpu"), n_cores=3, tt_rank=8)
+    d = m.spec().desc(8, 5)
+    assert lib.ttrnn_rnn_param_count(ctypes.byref(d)) == 35840
+    d2 = quiet(tr.TTGRU, 1, 256, 1, torch.device("cpu"), n_cores=2, tt_rank=4).spec().desc(4, 4)
+    assert lib.ttrnn_rnn_param_count(ctypes.byref(d2)) == 5344
+    bad = m.spec().desc(8, 5)
+    bad.hidden_size = 128
+    assert lib.ttrnn_rnn_param_count(ctypes.byref(bad)) == -1
+    assert b"expected" in lib.ttrnn_last_error()
+    bad.hidden_size = 256
