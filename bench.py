@@ -199,11 +199,15 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
+    ap.add_argument("--seq-len", type=int, default=0, help="override T (profiling only; not a bench number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.batch:
         cfg["B"] = args.batch
+    if args.seq_len:
+        cfg["T"] = args.seq_len
+        cfg["name"] += " [T overridden to %d: profiling run]" % args.seq_len
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

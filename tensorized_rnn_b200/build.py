@@ -15,13 +15,14 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libttrnn_b200.so")
-SOURCES = ["ttrnn_capi.cu"]
-HEADERS = ["tt_plan.h", "tt_stage.cuh", "tt_kernels.cuh", os.path.join("..", "..", "include", "ttrnn_b200.h")]
+SOURCES = ["ttrnn_capi.cu", "tt_static_inst.cu"]
+HEADERS = ["tt_plan.h", "tt_stage.cuh", "tt_kernels.cuh", "tt_static.cuh", "tt_static_api.h",
+           os.path.join("..", "..", "include", "ttrnn_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
 
@@ -44,12 +45,26 @@ def needs_build() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    # one nvcc per translation unit, in parallel; then link
+    procs, objs, log = [], [], ""
+    for src in SOURCES:
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for cmd, pr in procs:
+        out, _ = pr.communicate()
+        log += " ".join(cmd) + "\n" + out + "\n"
+        failed = failed or pr.returncode != 0
+    if not failed:
+        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += " ".join(cmd) + "\n" + res.stdout + res.stderr
+        failed = res.returncode != 0
     with open(os.path.join(CSRC, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        f.write(log)
+    if failed:
         raise RuntimeError("nvcc failed:\n" + log[-8000:])
     if verbose:
         print(log)

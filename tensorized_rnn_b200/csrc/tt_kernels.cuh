@@ -645,6 +645,11 @@ __global__ void k_reduce_partials(const float *__restrict__ partial, int nslots,
     out[e] = s;
 }
 
+__global__ void k_fill(float *dst, float v, int n) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) dst[e] = v;
+}
+
 // dst[e] (+)= src[e]
 __global__ void k_axpy1(const float *__restrict__ src, float *__restrict__ dst, long long n, int accumulate) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,0 +1,20 @@
+// Host-side registry of the statically specialised kernels (tt_static.cuh / tt_static_inst.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/ttrnn_b200.h"
+
+namespace tts {
+struct RnnFwdSArgs;
+}
+
+struct TtsRnnFwdEntry {
+    const char *name;
+    int cell, mode, R;
+    size_t smem;
+    bool (*match)(const ttrnn_tt_shape *hh);
+    int (*launch)(const tts::RnnFwdSArgs *args, int grid, cudaStream_t st);   // 0 = ok, else cudaError_t
+    int (*prepare)(int *max_blocks_per_sm);                                  // sets attributes; 0 = ok
+};
+
+// best registered forward kernel for (hh shape, cell, mode) at batch B on `sms` SMs, or nullptr
+const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms);

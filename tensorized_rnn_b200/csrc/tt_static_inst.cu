@@ -1,0 +1,78 @@
+// Instantiations of the static kernels for the benchmark shapes (BASELINE.json configs 1-5) and the
+// lookup used by the C ABI.  Adding a shape = one TTS_SHAPE line + one TTS_FWD line per variant.
+#include "tt_static.cuh"
+#include "tt_static_api.h"
+
+namespace {
+
+#define TTS_SHAPE(NAME, D_, G_, ...)                          \
+    struct NAME {                                             \
+        static constexpr int D = D_, G = G_;                  \
+        __VA_ARGS__                                           \
+    };
+#define ARR(name, ...) static constexpr int name[7] = {__VA_ARGS__};
+
+// hidden-to-hidden chains: J = in modes, I = out modes (gates folded into I[0]), RK = ranks r_0..r_d
+TTS_SHAPE(HH_H256_d2r4_lstm, 2, 4, ARR(J, 16, 16) ARR(I, 32, 32) ARR(RK, 1, 4, 1))
+TTS_SHAPE(HH_H256_d2r4_gru, 2, 3, ARR(J, 16, 16) ARR(I, 24, 32) ARR(RK, 1, 4, 1))
+TTS_SHAPE(HH_H256_d3r8_lstm, 3, 4, ARR(J, 4, 8, 8) ARR(I, 8, 8, 16) ARR(RK, 1, 8, 8, 1))
+TTS_SHAPE(HH_H256_d4r16_lstm, 4, 4, ARR(J, 4, 4, 4, 4) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
+TTS_SHAPE(HH_H1024_d4r8_lstm, 4, 4, ARR(J, 4, 4, 8, 8) ARR(I, 8, 8, 8, 8) ARR(RK, 1, 8, 8, 8, 1))
+
+template <class S>
+bool match_shape(const ttrnn_tt_shape *s) {
+    if (s->d != S::D) return false;
+    for (int k = 0; k < S::D; ++k)
+        if (s->in_modes[k] != S::J[k] || s->out_modes[k] != S::I[k] || s->ranks[k] != S::RK[k]) return false;
+    return s->ranks[S::D] == 1;
+}
+
+template <class S, int CELL, int R, int MODE>
+int launch_fwd(const tts::RnnFwdSArgs *a, int grid, cudaStream_t st) {
+    tts::k_rnn_fwd_s<S, CELL, R, MODE><<<grid, tts::NTHR, tts::FwdSmem<S, R>::BYTES, st>>>(*a);
+    return (int)cudaGetLastError();
+}
+template <class S, int CELL, int R, int MODE>
+int prepare_fwd(int *occ) {
+    auto k = tts::k_rnn_fwd_s<S, CELL, R, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::FwdSmem<S, R>::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::FwdSmem<S, R>::BYTES);
+}
+
+#define TTS_FWD(S, CELL, R, MODE)                                                                          \
+    {#S, CELL, MODE, R, tts::FwdSmem<S, R>::BYTES, &match_shape<S>, &launch_fwd<S, CELL, R, MODE>,          \
+     &prepare_fwd<S, CELL, R, MODE>}
+
+const TtsRnnFwdEntry kFwd[] = {
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG),
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG),
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG),
+    TTS_FWD(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG),
+    TTS_FWD(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG),
+};
+
+}  // namespace
+
+const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms) {
+    const TtsRnnFwdEntry *best = nullptr;
+    long long best_cost = 0;
+    for (const auto &e : kFwd) {
+        if (e.cell != cell || e.mode != mode || !e.match(hh)) continue;
+        const long long tiles = (B + e.R - 1) / e.R;
+        const long long waves = (tiles + sms - 1) / sms;
+        const long long cost = waves * e.R;               // rows processed back to back by the busiest SM
+        if (!best || cost < best_cost || (cost == best_cost && e.R > best->R)) {
+            best = &e;
+            best_cost = cost;
+        }
+    }
+    return best;
+}

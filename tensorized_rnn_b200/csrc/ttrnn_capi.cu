@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "tt_kernels.cuh"
+#include "tt_static.cuh"
+#include "tt_static_api.h"
 
 namespace {
 
@@ -18,6 +20,7 @@ std::atomic<long long> g_launches{0};
 std::atomic<long long> g_opt_rows{0};
 std::atomic<long long> g_opt_chunk{0};
 std::atomic<long long> g_opt_chunk_bytes{4LL << 30};
+std::atomic<long long> g_opt_static{1};
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
 struct TimedLaunch { int kind; cudaEvent_t a, b; };
@@ -253,7 +256,7 @@ struct RnnLayout {
     // saved (floats)
     long long sv_hs = 0, sv_cs = 0, sv_total = 0;
     // fwd scratch (floats)
-    long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_total = 0;
+    long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_aux = 0, f_total = 0;
     // bwd scratch (floats)
     long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
@@ -284,6 +287,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->f_sh = o; o += r4(lo->BH);
     lo->f_sc = o; o += r4(lo->BH);
     lo->f_hs = o; o += (L > 1 ? 2 * r4(lo->BTH) : 0);     // used only when nothing is saved
+    lo->f_aux = o; o += r4(GH) + 4;                       // rank-one input mode: dense W_ih column + a 1.0f
     lo->f_total = o;
     // backward scratch
     long long maxp = 0;
@@ -433,6 +437,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "rows_per_cta")) { g_opt_rows.store(value); return 0; }
     if (!strcmp(key, "chunk_steps")) { g_opt_chunk.store(value); return 0; }
     if (!strcmp(key, "chunk_bytes")) { g_opt_chunk_bytes.store(value > 0 ? value : (4LL << 30)); return 0; }
+    if (!strcmp(key, "static_kernels")) { g_opt_static.store(value); return 0; }
     return 1;
 }
 
@@ -488,6 +493,64 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
         float *csave = (sv && lstm) ? sv + lo.sv_cs + (long long)l * lo.BTH : nullptr;
         const float *b_ih = d->has_bias ? params + lp.off_ih_bias : nullptr;
         const float *b_hh = d->has_bias ? params + lp.off_hh_bias : nullptr;
+
+        // ---- statically specialised kernel for this hh shape, if one is registered -------------------
+        const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
+        const TtsRnnFwdEntry *se = g_opt_static.load() ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms) : nullptr;
+        if (se) {
+            int occ = 0;
+            int rc = se->prepare(&occ);
+            if (rc || occ < 1) return fail("static kernel %s cannot be configured (cuda error %d)", se->name, rc);
+            long long g = (long long)occ * dv.sms;
+            const long long tiles = (B + se->R - 1) / se->R;
+            if (g > tiles) g = tiles;
+            tts::RnnFwdSArgs sa;
+            memset(&sa, 0, sizeof sa);
+            sa.B = B;
+            sa.cores = params + lp.off_hh_cores;
+            float *aux = sc + lo.f_aux;
+            if (mode == tts::MODE_RANK1) {
+                // W_ih has a single column: densify it once (the TT chain applied to the scalar 1)
+                k_fill<<<1, 32, 0, st>>>(aux + r4(GH), 1.0f, 1);
+                ++g_launches;
+                if (launch_ttlinear_fwd(lp.ih, dv, 1, 1, aux + r4(GH), 0, params + lp.off_ih_cores, nullptr, nullptr,
+                                        aux, 0, st))
+                    return 1;
+                sa.w_eff = aux;
+                sa.bias_ih = b_ih;
+                sa.bias_hh = b_hh;
+            } else {
+                sa.bias_hh = lstm ? nullptr : b_hh;
+            }
+            const int chunk = (mode == tts::MODE_RANK1) ? T : lo.Tc;
+            for (int t0 = 0; t0 < T; t0 += chunk) {
+                const int tc = (T - t0 < chunk) ? T - t0 : chunk;
+                if (mode == tts::MODE_XG) {
+                    if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                            params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg,
+                                            (long long)tc * GH, st))
+                        return 1;
+                    sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
+                } else {
+                    sa.x1 = lin + t0; sa.x1_bstride = T;
+                }
+                const bool first = (t0 == 0), last = (t0 + tc == T);
+                sa.steps = tc;
+                sa.h_in = first ? h0 : st_h;
+                sa.c_in = first ? c0 : st_c;
+                sa.out = lout + (long long)t0 * H; sa.out_bstride = (long long)T * H;
+                sa.c_save = csave ? csave + (long long)t0 * H : nullptr;
+                sa.h_out = (last && l == L - 1 && hT) ? hT : st_h;
+                sa.c_out = (last && l == L - 1 && cT) ? cT : st_c;
+                {
+                    KernelTimer tm(TTRNN_K_RNN_FWD, st);
+                    rc = se->launch(&sa, (int)g, st);
+                }
+                ++g_launches;
+                if (rc) return fail("static kernel %s launch failed: %s", se->name, cudaGetErrorString((cudaError_t)rc));
+            }
+            continue;
+        }
 
         // recurrent kernel configuration for this layer
         RnnFwdArgs a;
