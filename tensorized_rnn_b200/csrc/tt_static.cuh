@@ -91,34 +91,61 @@ TTS_DEV void stage_weights_k(const float *__restrict__ cores, float *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Forward stage k >= 1:  X_{k-1}[(i,m,a)] = sum_kappa X_k[m][kappa] W_k[kappa][(i,a)]
-// thread tile = R batch rows x TMr rows x TN columns
+// Lane arrangement.  Measured on B200 (tools/lds_probe.cu): an LDS.128 costs 2 wavefronts when the
+// lanes that share an address are adjacent pairs (address = f(lane/2)) or when the address
+// depends only on lane%2 and on the high lane bits; period-4/8/16 interleaved duplicates cost 4.
+// So a warp is laid out as LX "x" positions (lane bits 1..lgLX) times LY = 32/LX "y" positions
+// (lane bit 0 and the top bits): the x operand is read pair-blocked, the y operand with period 2.
 // ---------------------------------------------------------------------------------------------
-template <class S, int k, int R>
-struct FwdMap {
-    using T = St<S, k>;
-    static constexpr int TN = (T::N % 8 == 0) ? 8 : 4;
-    static constexpr int NTl = T::N / TN;
-    static constexpr int TMr = p2div(T::Mrow, cmin(cmax(T::Mrow * NTl / NTHR, 1), cmax(64 / (R * TN), 1)));
-    static constexpr int MTl = T::Mrow / TMr;
-    static constexpr int TT = MTl * NTl;
-    static constexpr int ITER = (TT + NTHR - 1) / NTHR;
-    static_assert(T::K % 4 == 0 && T::N % 4 == 0 && T::r % 4 == 0, "static path needs K, N, r multiples of 4");
+template <int LX>
+struct Lanes {
+    static constexpr int LY = 32 / LX;
+    static constexpr int lg = (LX == 32) ? 5 : (LX == 16) ? 4 : (LX == 8) ? 3 : (LX == 4) ? 2 : (LX == 2) ? 1 : 0;
+    TTS_DEV static int x(int lane) { return (LX == 32) ? lane : ((lane >> 1) & (LX - 1)); }
+    TTS_DEV static int y(int lane) { return (LX == 32) ? 0 : ((lane & 1) | ((lane >> (1 + lg)) << 1)); }
 };
 
-template <class S, int k, int R>
+// ---------------------------------------------------------------------------------------------
+// Forward stage k >= 1:  X_{k-1}[(i,m,a)] = sum_kappa X_k[m][kappa] W_k[kappa][(i,a)]
+// thread tile = (R batch rows x TMr rows) x TN columns; TMr rows are MTl apart (lanes read
+// neighbouring rows), the TN = 8 columns are two float4 groups N/2 apart (lanes read neighbouring
+// float4s of W).  x = column tile, y = row tile.
+// ---------------------------------------------------------------------------------------------
+template <class S, int k, int R, int TMr_, int TN_>
+struct FwdMap {
+    using T = St<S, k>;
+    static constexpr int TN = TN_, TMr = TMr_;
+    static_assert(TN == 4 || TN == 8, "TN");
+    static_assert(T::K % 4 == 0 && T::N % TN == 0 && T::r % 4 == 0, "static path needs K, N, r multiples of 4");
+    static_assert(T::Mrow % TMr == 0, "TMr must divide Mrow");
+    static constexpr int NTl = T::N / TN;
+    static constexpr int MTl = T::Mrow / TMr;
+    static constexpr int LX = NTl >= 16 ? 16 : NTl;            // column tiles across a warp
+    static constexpr int LY = 32 / LX;
+    static_assert(NTl % LX == 0 && MTl % LY == 0, "tile grid must be a multiple of the lane grid");
+    static constexpr int WX = NTl / LX;                         // warps along columns
+    static constexpr int TT = MTl * NTl;
+    static constexpr int ITER = (TT + NTHR - 1) / NTHR;
+    static_assert(TT % NTHR == 0 || TT < NTHR, "tile count");
+};
+
+template <class S, int k, int R, int TMr, int TN>
 TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W, float *__restrict__ Y, int tid) {
     using T = St<S, k>;
     using To = St<S, k - 1>;
-    using M = FwdMap<S, k, R>;
-    constexpr int TN = M::TN, TMr = M::TMr;
+    using M = FwdMap<S, k, R, TMr, TN>;
+    using L = Lanes<M::LX>;
     constexpr int Jp = To::J, KSo = To::KS, BSo = To::BS;
     constexpr int ISo = (T::Mrow / Jp) * KSo;
+    constexpr int NG = TN / 4;                 // float4 column groups per thread
+    constexpr int GSTR = T::N / NG;            // distance between the groups (columns)
+    const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
     for (int it = 0; it < M::ITER; ++it) {
-        const int u = tid + it * NTHR;
-        if (M::TT % NTHR != 0 && u >= M::TT) break;
-        const int tn = u % M::NTl, mt = u / M::NTl;
+        const int wv = warp + it * (NTHR / 32);
+        const int tn = (wv % M::WX) * M::LX + L::x(lane);
+        const int mt = (wv / M::WX) * M::LY + L::y(lane);
+        if (M::TT < NTHR && mt >= M::MTl) break;
         float acc[R][TMr][TN];
 #pragma unroll
         for (int b = 0; b < R; ++b)
@@ -126,22 +153,22 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
             for (int q = 0; q < TMr; ++q)
 #pragma unroll
                 for (int j = 0; j < TN; ++j) acc[b][q][j] = 0.f;
-        const float *xb = X + mt * TMr * T::KS;
-        const float *wb = W + tn * TN;
-#pragma unroll 4
+        const float *xb = X + mt * T::KS;
+        const float *wb = W + tn * 4;
+#pragma unroll 2
         for (int k4 = 0; k4 < T::K; k4 += 4) {
             float4 a[R][TMr];
 #pragma unroll
             for (int b = 0; b < R; ++b)
 #pragma unroll
-                for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * T::KS + k4);
+                for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 float w[TN];
 #pragma unroll
-                for (int j = 0; j < TN; j += 4) {
-                    const float4 t = ld4(wb + (k4 + kk) * T::NS + j);
-                    w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
+                for (int g = 0; g < NG; ++g) {
+                    const float4 t = ld4(wb + (k4 + kk) * T::NS + g * GSTR);
+                    w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
                 }
 #pragma unroll
                 for (int b = 0; b < R; ++b)
@@ -155,54 +182,71 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
         }
 #pragma unroll
         for (int q = 0; q < TMr; ++q) {
-            const int mr = mt * TMr + q;
+            const int mr = q * M::MTl + mt;
             const int base = (mr / Jp) * KSo + (mr % Jp) * T::r;
 #pragma unroll
-            for (int j = 0; j < TN; j += 4) {
-                const int n = tn * TN + j;
+            for (int g = 0; g < NG; ++g) {
+                const int n = g * GSTR + tn * 4;
                 const int off = base + (n / T::r) * ISo + (n % T::r);
 #pragma unroll
                 for (int b = 0; b < R; ++b)
-                    st4(Y + b * BSo + off, make_float4(acc[b][q][j], acc[b][q][j + 1], acc[b][q][j + 2], acc[b][q][j + 3]));
+                    st4(Y + b * BSo + off,
+                        make_float4(acc[b][q][4 * g], acc[b][q][4 * g + 1], acc[b][q][4 * g + 2], acc[b][q][4 * g + 3]));
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Final stage (k = 0) with every gate of a hidden unit in one thread.
-// thread tile = R batch rows x TMr rows x TI first-mode slices x G gates; lanes: 8 row tiles x 4 slices
+// Final stage (k = 0): every gate of a hidden unit ends up in one thread.
+//   thread tile  = (R batch rows x TMr rows) x (TI first-mode slices x G gates), over 1/SK of K
+//   thread grid  = MTl row tiles x ITl slice tiles x SK k-splits = NTHR threads
+//   lanes        = 16 row tiles (x) x 2 slice tiles (y)   [ITl >= 2]   or 32 row tiles [ITl == 1]
+//   after the k-loop the SK partial tiles are reduce-scattered through shared memory: thread kh
+//   keeps the elements e = q*TI + i with e % SK == kh (NE = TMr*TI/SK of them).
 // hidden unit of (mr, i0') is  h = i0' * Mrow_0 + mr
 // ---------------------------------------------------------------------------------------------
-template <class S, int R>
+template <class S, int R, int TMr_, int TI_, int SK_>
 struct FinMap {
     using T = St<S, 0>;
     static_assert(T::r == 1 && T::I % S::G == 0, "gates must align with the first output mode");
+    static constexpr int TMr = TMr_, TI = TI_, SK = SK_;
     static constexpr int I0p = T::I / S::G;
-    // grow the tile until one tile per thread suffices
-    static constexpr int tiles1 = T::Mrow * I0p;                       // with TMr = TI = 1
-    static constexpr int need = (tiles1 + NTHR - 1) / NTHR;            // elements per thread
-    static constexpr int TI = cmin(p2div(I0p, need), I0p);
-    static constexpr int TMr = p2div(T::Mrow, cmax(need / TI, 1));
+    static_assert(I0p % TI == 0 && T::Mrow % TMr == 0 && (T::K / 4) % SK == 0, "final tile shape");
+    static_assert((TMr * TI) % SK == 0, "k-split must divide the tile elements");
     static constexpr int ITl = I0p / TI;
     static constexpr int MTl = T::Mrow / TMr;
-    static constexpr int TT = MTl * ITl;
-    static_assert(TT <= NTHR, "final stage does not fit one tile per thread");
-    static constexpr int LM = (MTl % 8 == 0) ? 8 : p2div(MTl, 8);      // row tiles that are lane-adjacent
-    TTS_DEV static void coords(int u, int &mt, int &it) {
-        const int lo = u % LM;
-        const int rest = u / LM;
-        it = rest % ITl;
-        mt = (rest / ITl) * LM + lo;
+    static constexpr int TT = MTl * ITl * SK;
+    static_assert(TT == NTHR, "final stage must use exactly one tile per thread");
+    static constexpr int NE = TMr * TI / SK;            // elements (hidden units per batch row) owned per thread
+    static constexpr int LX = (ITl >= 2) ? 16 : 32;
+    static constexpr int LYI = (ITl >= 2) ? 2 : 1;      // slice tiles per warp
+    static_assert(MTl % LX == 0 && ITl % LYI == 0, "lane grid");
+    static constexpr int WM = MTl / LX;                 // warps along rows
+    static constexpr int WI = ITl / LYI;                // warps along slices
+    static constexpr int KPART = T::K / SK;
+    static constexpr int XCH = (SK > 1) ? cr4((SK - 1) * NE * R * 4) : 0;   // exchange floats per thread
+    static constexpr int XCH_FLOATS = XCH * NTHR;
+    TTS_DEV static void coords(int tid, int &mt, int &itg, int &kh) {
+        const int lane = tid & 31, warp = tid >> 5;
+        using L = Lanes<LX>;
+        mt = (warp % WM) * LX + L::x(lane);
+        itg = ((warp / WM) % WI) * LYI + L::y(lane);
+        kh = warp / (WM * WI);
+    }
+    // element e = q*TI + i  ->  hidden unit
+    TTS_DEV static int hidden(int mt, int itg, int e) {
+        const int q = e / TI, i = e % TI;
+        return (itg * TI + i) * T::Mrow + q * MTl + mt;
     }
 };
 
-template <class S, int R>
-TTS_DEV void final_stage(const float *__restrict__ X, const float *__restrict__ W, int mt, int it,
-                         float (&acc)[R][FinMap<S, R>::TMr][FinMap<S, R>::TI][4]) {
+// accumulates the partial tile of this thread; acc[b][q][i][g]
+template <class S, int R, class FM>
+TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict__ W, int mt, int itg, int kh,
+                           float (&acc)[R][FM::TMr][FM::TI][4]) {
     using T = St<S, 0>;
-    using M = FinMap<S, R>;
-    constexpr int TMr = M::TMr, TI = M::TI;
+    constexpr int TMr = FM::TMr, TI = FM::TI;
 #pragma unroll
     for (int b = 0; b < R; ++b)
 #pragma unroll
@@ -211,15 +255,15 @@ TTS_DEV void final_stage(const float *__restrict__ X, const float *__restrict__ 
             for (int i = 0; i < TI; ++i)
 #pragma unroll
                 for (int g = 0; g < 4; ++g) acc[b][q][i][g] = 0.f;
-    const float *xb = X + mt * TMr * T::KS;
-    const float *wb = W + it * TI * 4;
-#pragma unroll 4
-    for (int k4 = 0; k4 < T::K; k4 += 4) {
+    const float *xb = X + mt * T::KS + kh * FM::KPART;
+    const float *wb = W + kh * FM::KPART * T::NS + itg * TI * 4;
+#pragma unroll 2
+    for (int k4 = 0; k4 < FM::KPART; k4 += 4) {
         float4 a[R][TMr];
 #pragma unroll
         for (int b = 0; b < R; ++b)
 #pragma unroll
-            for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * T::KS + k4);
+            for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * FM::MTl * T::KS + k4);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             float4 w[TI];
@@ -242,17 +286,82 @@ TTS_DEV void final_stage(const float *__restrict__ X, const float *__restrict__ 
     }
 }
 
+// reduce-scatter of the SK partial tiles: on return pre[b][n][g] holds the full sums of the NE
+// elements this thread owns (element index e = n*SK + kh).  xch: FM::XCH_FLOATS floats of shared
+// memory; contains two block barriers when SK > 1.
+template <class S, int R, class FM>
+TTS_DEV void final_reduce(float (&acc)[R][FM::TMr][FM::TI][4], float (&pre)[R][FM::NE][4], float *xch, int tid, int kh) {
+    constexpr int TI = FM::TI, SK = FM::SK, NE = FM::NE;
+    constexpr int PER = NTHR / SK;                       // threads per k-split group
+    if constexpr (SK > 1) {
+        // slot layout: [(d-1)][n][b] float4 per thread, thread-minor: xch4[slot * NTHR + owner_tid]
+        float4 *x4 = reinterpret_cast<float4 *>(xch);
+        const int tprime = tid % PER;
+#pragma unroll
+        for (int e = 0; e < FM::TMr * TI; ++e) {
+            const int owner = e % SK;                    // compile-time after unrolling
+            const int n = e / SK;
+            const int q = e / TI, i = e % TI;
+#pragma unroll
+            for (int dlt = 1; dlt < SK; ++dlt) {
+                // this thread is the dlt-th partner of `owner` iff (kh - owner) mod SK == dlt
+                if (((kh - owner + SK) % SK) == dlt) {
+#pragma unroll
+                    for (int b = 0; b < R; ++b)
+                        x4[((dlt - 1) * NE * R + n * R + b) * NTHR + owner * PER + tprime] =
+                            make_float4(acc[b][q][i][0], acc[b][q][i][1], acc[b][q][i][2], acc[b][q][i][3]);
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < FM::TMr * TI; ++e) {
+            const int owner = e % SK;
+            const int n = e / SK;
+            const int q = e / TI, i = e % TI;
+            if (owner == kh) {
+#pragma unroll
+                for (int b = 0; b < R; ++b) {
+                    float s0 = acc[b][q][i][0], s1 = acc[b][q][i][1], s2 = acc[b][q][i][2], s3 = acc[b][q][i][3];
+#pragma unroll
+                    for (int dlt = 1; dlt < SK; ++dlt) {
+                        const float4 v = x4[((dlt - 1) * NE * R + n * R + b) * NTHR + tid];
+                        s0 += v.x; s1 += v.y; s2 += v.z; s3 += v.w;
+                    }
+                    pre[b][n][0] = s0; pre[b][n][1] = s1; pre[b][n][2] = s2; pre[b][n][3] = s3;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < FM::TMr * TI; ++e) {
+            const int q = e / TI, i = e % TI;
+#pragma unroll
+            for (int b = 0; b < R; ++b)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) pre[b][e][g] = acc[b][q][i][g];
+        }
+    }
+}
+
 TTS_DEV float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// ---- per (shape, R) tuning table ----------------------------------------------------------------
+// TMr[k], TN[k] for the forward stages k >= 1; FTMr / FTI / FSK for the final stage
+template <int FTMr_, int FTI_, int FSK_, int TM1 = 1, int TN1 = 8, int TM2 = 1, int TN2 = 8, int TM3 = 1, int TN3 = 8>
+struct Tune {
+    static constexpr int FTMr = FTMr_, FTI = FTI_, FSK = FSK_;
+    static constexpr int TMr[4] = {0, TM1, TM2, TM3};
+    static constexpr int TN[4] = {0, TN1, TN2, TN3};
+};
+
 // shared-memory floats of the forward recurrent kernel
-template <class S, int R>
+template <class S, int R, class TU>
 struct FwdSmem {
     static constexpr int D = S::D;
+    using FM = FinMap<S, R, TU::FTMr, TU::FTI, TU::FSK>;
     static constexpr int W = w_floats<S>();
     static constexpr int HS = cr4(R * St<S, D - 1>::BS);
-    static constexpr int slot(int k) { return 0; }
-    // ping-pong slots P (X_{d-2}, X_{d-4}, ..) and Q (X_{d-3}, ..)
-    template <int k> static constexpr int bs() { return St<S, k>::BS; }
     static constexpr int pfloats() {
         int m = 0;
         if (D >= 2) m = cmax(m, St<S, (D >= 2 ? D - 2 : 0)>::BS);
@@ -267,7 +376,8 @@ struct FwdSmem {
         return cr4(R * m);
     }
     static constexpr int P = pfloats(), Q = qfloats();
-    static constexpr int TOTAL = W + HS + P + Q;
+    static constexpr int XCH = FM::XCH_FLOATS;
+    static constexpr int TOTAL = W + HS + P + Q + XCH;
     static constexpr size_t BYTES = (size_t)TOTAL * 4;
 };
 
@@ -292,28 +402,27 @@ struct RnnFwdSArgs {
 enum { MODE_XG = 0, MODE_RANK1 = 1 };
 
 // run stages D-1 .. 1 (each followed by a barrier); returns the slot holding X_0
-template <class S, int R, int k>
+template <class S, int R, class TU, int k>
 TTS_DEV const float *fwd_chain_pp(float *hs, float *P, float *Q, const float *wsm, int tid) {
     if constexpr (k == 0) {
         return (S::D == 1) ? hs : (((S::D - 2) % 2 == 0) ? P : Q);
     } else {
         const float *X = (k == S::D - 1) ? hs : (((S::D - 2 - k) % 2 == 0) ? P : Q);
         float *Y = ((S::D - 2 - (k - 1)) % 2 == 0) ? P : Q;
-        fwd_stage<S, k, R>(X, wsm + WOff<S, k>::v, Y, tid);
+        fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(X, wsm + WOff<S, k>::v, Y, tid);
         __syncthreads();
-        return fwd_chain_pp<S, R, k - 1>(hs, P, Q, wsm, tid);
+        return fwd_chain_pp<S, R, TU, k - 1>(hs, P, Q, wsm, tid);
     }
 }
 
-template <class S, int CELL, int R, int MODE>
+template <class S, int CELL, int R, int MODE, class TU>
 __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ RnnFwdSArgs a) {
     extern __shared__ __align__(16) float smem[];
-    using SM = FwdSmem<S, R>;
-    using FM = FinMap<S, R>;
+    using SM = FwdSmem<S, R, TU>;
+    using FM = typename SM::FM;
     using TL = St<S, S::D - 1>;
-    using T0 = St<S, 0>;
     constexpr int G = S::G, H = n_in<S>(), GH = G * H;
-    constexpr int TMr = FM::TMr, TI = FM::TI;
+    constexpr int NE = FM::NE;
     constexpr bool LSTM = (CELL == TTRNN_CELL_LSTM);
     static_assert(G == (LSTM ? 4 : 3), "gate count");
     const int tid = threadIdx.x;
@@ -321,25 +430,26 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ R
     float *hs = wsm + SM::W;
     float *P = hs + SM::HS;
     float *Q = P + SM::P;
+    float *xch = Q + SM::Q;
 
     stage_weights_k<S, 0>(a.cores, wsm, tid);
 
-    const bool active = tid < FM::TT;
-    int mt = 0, it = 0;
-    FM::coords(active ? tid : 0, mt, it);
-    // hidden units owned by this thread: h(q, i) = (it*TI + i) * Mrow_0 + mt*TMr + q
-    float bhh[TI][TMr][4], weff[TI][TMr][4], bih[TI][TMr][4];
+    int mt, itg, kh;
+    FM::coords(tid, mt, itg, kh);
+    // hidden units owned by this thread: element e = n*SK + kh
+    int hid[NE];
+    float bhh[NE][4], weff[NE][4], bih[NE][4];
 #pragma unroll
-    for (int i = 0; i < TI; ++i)
+    for (int n = 0; n < NE; ++n) {
+        hid[n] = FM::hidden(mt, itg, n * FM::SK + kh);
 #pragma unroll
-        for (int q = 0; q < TMr; ++q)
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                const int col = g * H + (it * TI + i) * T0::Mrow + mt * TMr + q;
-                bhh[i][q][g] = a.bias_hh ? __ldg(a.bias_hh + col) : 0.f;
-                weff[i][q][g] = (MODE == MODE_RANK1) ? __ldg(a.w_eff + col) : 0.f;
-                bih[i][q][g] = (MODE == MODE_RANK1 && a.bias_ih) ? __ldg(a.bias_ih + col) : 0.f;
-            }
+        for (int g = 0; g < G; ++g) {
+            const int col = g * H + hid[n];
+            bhh[n][g] = a.bias_hh ? __ldg(a.bias_hh + col) : 0.f;
+            weff[n][g] = (MODE == MODE_RANK1) ? __ldg(a.w_eff + col) : 0.f;
+            bih[n][g] = (MODE == MODE_RANK1 && a.bias_ih) ? __ldg(a.bias_ih + col) : 0.f;
+        }
+    }
 
     const long long ntiles = (a.B + R - 1) / R;
     for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
@@ -352,98 +462,85 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ R
             if (row0 + b < a.B && a.h_in) hv = __ldg(a.h_in + (row0 + b) * H + h);
             hs[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hv;
         }
-        float cst[R][TMr][TI], hpr[R][TMr][TI];
+        float cst[R][NE], hpr[R][NE];
 #pragma unroll
         for (int b = 0; b < R; ++b)
 #pragma unroll
-            for (int q = 0; q < TMr; ++q)
-#pragma unroll
-                for (int i = 0; i < TI; ++i) {
-                    const int h = (it * TI + i) * T0::Mrow + mt * TMr + q;
-                    const bool ok = active && (row0 + b < a.B);
-                    cst[b][q][i] = (LSTM && ok && a.c_in) ? __ldg(a.c_in + (row0 + b) * H + h) : 0.f;
-                    hpr[b][q][i] = (ok && a.h_in) ? __ldg(a.h_in + (row0 + b) * H + h) : 0.f;
-                }
+            for (int n = 0; n < NE; ++n) {
+                const bool ok = (row0 + b < a.B);
+                cst[b][n] = (LSTM && ok && a.c_in) ? __ldg(a.c_in + (row0 + b) * H + hid[n]) : 0.f;
+                hpr[b][n] = (ok && a.h_in) ? __ldg(a.h_in + (row0 + b) * H + hid[n]) : 0.f;
+            }
         __syncthreads();
 
         for (int t = 0; t < a.steps; ++t) {
             // ---- operands of the gate phase, requested before the chain so their latency hides
-            float xin[R][TMr][TI][4];
+            float xin[R][NE][4];
             float x1[R];
             if (MODE == MODE_XG) {
 #pragma unroll
                 for (int b = 0; b < R; ++b)
 #pragma unroll
-                    for (int q = 0; q < TMr; ++q)
+                    for (int n = 0; n < NE; ++n)
 #pragma unroll
-                        for (int i = 0; i < TI; ++i)
-#pragma unroll
-                            for (int g = 0; g < G; ++g) {
-                                const int col = g * H + (it * TI + i) * T0::Mrow + mt * TMr + q;
-                                xin[b][q][i][g] = (active && row0 + b < a.B)
-                                    ? __ldg(a.xg + (row0 + b) * a.xg_bstride + (long long)t * GH + col) : 0.f;
-                            }
+                        for (int g = 0; g < G; ++g)
+                            xin[b][n][g] = (row0 + b < a.B)
+                                ? __ldg(a.xg + (row0 + b) * a.xg_bstride + (long long)t * GH + g * H + hid[n]) : 0.f;
             } else {
 #pragma unroll
                 for (int b = 0; b < R; ++b)
                     x1[b] = (row0 + b < a.B) ? __ldg(a.x1 + (row0 + b) * a.x1_bstride + t) : 0.f;
             }
             // ---- stages d-1 .. 1
-            const float *X0 = fwd_chain_pp<S, R, S::D - 1>(hs, P, Q, wsm, tid);
-            // ---- stage 0 fused with the gate math and the state update
-            if (active) {
-                float acc[R][TMr][TI][4];
-                final_stage<S, R>(X0, wsm + WOff<S, 0>::v, mt, it, acc);
-#pragma unroll
-                for (int b = 0; b < R; ++b)
-#pragma unroll
-                    for (int q = 0; q < TMr; ++q)
-#pragma unroll
-                        for (int i = 0; i < TI; ++i) {
-                            const int h = (it * TI + i) * T0::Mrow + mt * TMr + q;
-                            float ain[4];
-#pragma unroll
-                            for (int g = 0; g < G; ++g)
-                                ain[g] = (MODE == MODE_XG) ? xin[b][q][i][g] : fmaf(x1[b], weff[i][q][g], bih[i][q][g]);
-                            float hnew;
-                            if (LSTM) {
-                                const float ig = sigmoidf_acc(acc[b][q][i][0] + bhh[i][q][0] + ain[0]);
-                                const float fg = sigmoidf_acc(acc[b][q][i][1] + bhh[i][q][1] + ain[1]);
-                                const float gg = tanhf(acc[b][q][i][2] + bhh[i][q][2] + ain[2]);
-                                const float og = sigmoidf_acc(acc[b][q][i][3] + bhh[i][q][3] + ain[3]);
-                                const float cn = fg * cst[b][q][i] + ig * gg;
-                                cst[b][q][i] = cn;
-                                hnew = og * tanhf(cn);
-                            } else {
-                                const float rg = sigmoidf_acc(ain[0] + (acc[b][q][i][0] + bhh[i][q][0]));
-                                const float zg = sigmoidf_acc(ain[1] + (acc[b][q][i][1] + bhh[i][q][1]));
-                                const float ng = tanhf(ain[2] + rg * (acc[b][q][i][2] + bhh[i][q][2]));
-                                hnew = (1.0f - zg) * ng + zg * hpr[b][q][i];
-                            }
-                            hpr[b][q][i] = hnew;
-                            hs[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hnew;
-                            if (row0 + b < a.B) {
-                                a.out[(row0 + b) * a.out_bstride + (long long)t * H + h] = hnew;
-                                if (LSTM && a.c_save) a.c_save[(row0 + b) * a.out_bstride + (long long)t * H + h] = cst[b][q][i];
-                            }
-                        }
+            const float *X0 = fwd_chain_pp<S, R, TU, S::D - 1>(hs, P, Q, wsm, tid);
+            // ---- stage 0 (split over K) + reduce-scatter + gate math + state update
+            float pre[R][NE][4];
+            {
+                float acc[R][FM::TMr][FM::TI][4];
+                final_partial<S, R, FM>(X0, wsm + WOff<S, 0>::v, mt, itg, kh, acc);
+                final_reduce<S, R, FM>(acc, pre, xch, tid, kh);
             }
-            __syncthreads();
-        }
-        if (active) {
 #pragma unroll
             for (int b = 0; b < R; ++b)
 #pragma unroll
-                for (int q = 0; q < TMr; ++q)
+                for (int n = 0; n < NE; ++n) {
+                    const int h = hid[n];
+                    float ain[4];
 #pragma unroll
-                    for (int i = 0; i < TI; ++i) {
-                        const int h = (it * TI + i) * T0::Mrow + mt * TMr + q;
-                        if (row0 + b < a.B) {
-                            if (a.h_out) a.h_out[(row0 + b) * H + h] = hpr[b][q][i];
-                            if (LSTM && a.c_out) a.c_out[(row0 + b) * H + h] = cst[b][q][i];
-                        }
+                    for (int g = 0; g < G; ++g)
+                        ain[g] = (MODE == MODE_XG) ? xin[b][n][g] : fmaf(x1[b], weff[n][g], bih[n][g]);
+                    float hnew;
+                    if (LSTM) {
+                        const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
+                        const float fg = sigmoidf_acc(pre[b][n][1] + bhh[n][1] + ain[1]);
+                        const float gg = tanhf(pre[b][n][2] + bhh[n][2] + ain[2]);
+                        const float og = sigmoidf_acc(pre[b][n][3] + bhh[n][3] + ain[3]);
+                        const float cn = fg * cst[b][n] + ig * gg;
+                        cst[b][n] = cn;
+                        hnew = og * tanhf(cn);
+                    } else {
+                        const float rg = sigmoidf_acc(ain[0] + (pre[b][n][0] + bhh[n][0]));
+                        const float zg = sigmoidf_acc(ain[1] + (pre[b][n][1] + bhh[n][1]));
+                        const float ng = tanhf(ain[2] + rg * (pre[b][n][2] + bhh[n][2]));
+                        hnew = (1.0f - zg) * ng + zg * hpr[b][n];
                     }
+                    hpr[b][n] = hnew;
+                    hs[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hnew;
+                    if (row0 + b < a.B) {
+                        a.out[(row0 + b) * a.out_bstride + (long long)t * H + h] = hnew;
+                        if (LSTM && a.c_save) a.c_save[(row0 + b) * a.out_bstride + (long long)t * H + h] = cst[b][n];
+                    }
+                }
+            __syncthreads();
         }
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+#pragma unroll
+            for (int n = 0; n < NE; ++n)
+                if (row0 + b < a.B) {
+                    if (a.h_out) a.h_out[(row0 + b) * H + hid[n]] = hpr[b][n];
+                    if (LSTM && a.c_out) a.c_out[(row0 + b) * H + hid[n]] = cst[b][n];
+                }
     }
 }
 

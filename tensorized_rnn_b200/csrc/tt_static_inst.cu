@@ -27,36 +27,39 @@ bool match_shape(const ttrnn_tt_shape *s) {
     return s->ranks[S::D] == 1;
 }
 
-template <class S, int CELL, int R, int MODE>
+template <class S, int CELL, int R, int MODE, class TU>
 int launch_fwd(const tts::RnnFwdSArgs *a, int grid, cudaStream_t st) {
-    tts::k_rnn_fwd_s<S, CELL, R, MODE><<<grid, tts::NTHR, tts::FwdSmem<S, R>::BYTES, st>>>(*a);
+    tts::k_rnn_fwd_s<S, CELL, R, MODE, TU><<<grid, tts::NTHR, tts::FwdSmem<S, R, TU>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
-template <class S, int CELL, int R, int MODE>
+template <class S, int CELL, int R, int MODE, class TU>
 int prepare_fwd(int *occ) {
-    auto k = tts::k_rnn_fwd_s<S, CELL, R, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::FwdSmem<S, R>::BYTES);
+    auto k = tts::k_rnn_fwd_s<S, CELL, R, MODE, TU>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::FwdSmem<S, R, TU>::BYTES);
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::FwdSmem<S, R>::BYTES);
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::FwdSmem<S, R, TU>::BYTES);
 }
 
-#define TTS_FWD(S, CELL, R, MODE)                                                                          \
-    {#S, CELL, MODE, R, tts::FwdSmem<S, R>::BYTES, &match_shape<S>, &launch_fwd<S, CELL, R, MODE>,          \
-     &prepare_fwd<S, CELL, R, MODE>}
+#define TTS_FWD(S, CELL, R, MODE, ...)                                                                     \
+    {#S, CELL, MODE, R, tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>,                            \
+     &launch_fwd<S, CELL, R, MODE, __VA_ARGS__>, &prepare_fwd<S, CELL, R, MODE, __VA_ARGS__>}
 
+// Tune<FTMr, FTI, FSK, TM1, TN1, TM2, TN2, TM3, TN3>: final-stage tile (rows, first-mode slices, k-split)
+// and (rows, columns) of the thread tile of stages 1..3
+using tts::Tune;
 const TtsRnnFwdEntry kFwd[] = {
-    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1),
-    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1),
-    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG),
-    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG),
-    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1),
-    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1),
-    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG),
-    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG),
-    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG),
-    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG),
-    TTS_FWD(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG),
-    TTS_FWD(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 1, 1, 2, 8, 2, 8>),
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
+    TTS_FWD(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<4, 1, 4, 8, 8, 8, 8, 4, 8>),
+    TTS_FWD(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<8, 1, 2, 8, 8, 4, 8, 4, 8>),
 };
 
 }  // namespace
