@@ -544,4 +544,616 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ R
     }
 }
 
+// =============================================================================================
+// Backward (BPTT) -- static path
+// =============================================================================================
+
+// ---- transposed weights  WT_k[n][kappa]  (row stride cpad(K)); k == 0 rows are n = i0'*4 + gate ----
+template <class S, int k>
+struct StT {
+    using T = St<S, k>;
+    static constexpr int ROWS = T::NW;                 // n (k >= 1) or i0'*4+g (k == 0)
+    static constexpr int KST = cpad(T::K);
+    static constexpr int FLOATS = cr4(ROWS * KST);
+};
+template <class S, int k> struct WTOff { static constexpr int v = WTOff<S, k - 1>::v + StT<S, k - 1>::FLOATS; };
+template <class S> struct WTOff<S, 0> { static constexpr int v = 0; };
+template <class S> constexpr int wt_floats() { return WTOff<S, S::D - 1>::v + StT<S, S::D - 1>::FLOATS; }
+
+template <class S, int k>
+TTS_DEV void stage_weights_t(const float *__restrict__ cores, float *__restrict__ wt, int tid) {
+    using T = St<S, k>;
+    using TT_ = StT<S, k>;
+    constexpr int I0p = T::I / S::G;
+    if (k == 0 && S::G == 3)
+        for (int e = tid; e < TT_::FLOATS; e += NTHR) wt[WTOff<S, 0>::v + e] = 0.f;
+    if (k == 0 && S::G == 3) __syncthreads();
+    for (int e = tid; e < T::CORE; e += NTHR) {
+        const int ap = e % T::rn;
+        int t = e / T::rn;
+        const int j = t % T::J;
+        t /= T::J;
+        const int i = t % T::I;
+        const int a = t / T::I;
+        const int row = (k == 0) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
+        wt[WTOff<S, k>::v + row * TT_::KST + j * T::rn + ap] = __ldg(cores + COff<S, k>::v + e);
+    }
+    if constexpr (k + 1 < S::D) stage_weights_t<S, k + 1>(cores, wt, tid);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward-data stage:  dX_k[m][kappa] = sum_n dY_k[m][n] WT_k[n][kappa]
+// Same register-tile structure as fwd_stage (rows x 8 columns, columns = kappa in two float4 groups
+// K/2 apart, or one group when K < 8); the reduction runs over n in groups of four.
+// SPLIT > 1 divides the reduction between SPLIT groups of warps; the partial tiles are
+// reduce-scattered through shared memory (owner s keeps columns [s*CW, (s+1)*CW) of the tile).
+//   k >= 1 : dY_k sits in the X_{k-1}-shaped buffer the forward stage wrote to
+//   k == 0 : dY_0 is the gate-gradient buffer [b][mr][i0'*4+g], row stride DS0
+// ---------------------------------------------------------------------------------------------
+template <class S> struct DY0 {
+    using T = St<S, 0>;
+    static constexpr int DS = cpad((T::I / S::G) * 4);       // row stride
+    static constexpr int BS = T::Mrow * DS;                  // per batch row
+};
+
+template <class S, int k, int R, int TMr_, int SPLIT_>
+struct BdMap {
+    using T = St<S, k>;
+    static constexpr int TMr = TMr_, SPLIT = SPLIT_;
+    static constexpr int TN = (T::K % 8 == 0) ? 8 : 4;         // kappa columns per thread
+    static constexpr int NG = TN / 4;
+    static constexpr int GSTR = T::K / NG;
+    static constexpr int CTl = T::K / TN;
+    static constexpr int MTl = T::Mrow / TMr;
+    static constexpr int RED = (k == 0) ? (T::I / S::G) * 4 : T::N;    // reduction length (incl. padded gate)
+    static_assert(T::Mrow % TMr == 0 && (RED / 4) % SPLIT == 0, "bwd-data tile shape");
+    static constexpr int LX = CTl >= 16 ? 16 : CTl;
+    static constexpr int LY = 32 / LX;
+    static_assert(CTl % LX == 0 && MTl % LY == 0, "bwd-data lane grid");
+    static constexpr int WX = CTl / LX;
+    static constexpr int TT = MTl * CTl;                        // tiles per split
+    static constexpr int PER = NTHR / SPLIT;                    // threads per split
+    static constexpr int ITER = (TT + PER - 1) / PER;
+    static_assert(TT % PER == 0 || TT < PER, "bwd-data tile count");
+    static_assert(SPLIT == 1 || TT <= PER, "split stages use one tile per thread");
+    static constexpr int CW = TN / SPLIT > 0 ? TN / SPLIT : 1;  // columns kept per thread after the reduce-scatter
+    static_assert(SPLIT == 1 || TN % SPLIT == 0, "split must divide the tile columns");
+    static constexpr int XCH_FLOATS = (SPLIT > 1) ? (SPLIT - 1) * R * TMr * CW * NTHR : 0;
+    static constexpr int REDP = RED / SPLIT;
+};
+
+template <class S, int k, int R, int TMr, int SPLIT>
+TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restrict__ WT, float *__restrict__ dX,
+                            float *__restrict__ xch, int tid) {
+    using T = St<S, k>;
+    using M = BdMap<S, k, R, TMr, SPLIT>;
+    using L = Lanes<M::LX>;
+    constexpr int TN = M::TN, NG = M::NG, GSTR = M::GSTR;
+    constexpr int KST = StT<S, k>::KST;
+    // geometry of the dY buffer
+    constexpr int Jp = (k == 0) ? 1 : St<S, (k == 0 ? 0 : k - 1)>::J;
+    constexpr int KSo = (k == 0) ? DY0<S>::DS : St<S, (k == 0 ? 0 : k - 1)>::KS;
+    constexpr int BSo = (k == 0) ? DY0<S>::BS : St<S, (k == 0 ? 0 : k - 1)>::BS;
+    constexpr int ISo = (k == 0) ? 0 : (T::Mrow / Jp) * KSo;
+    const int lane = tid & 31;
+    const int sp = tid / M::PER;                 // split index (whole warps)
+    const int wloc = (tid % M::PER) >> 5;
+#pragma unroll 1
+    for (int it = 0; it < M::ITER; ++it) {
+        const int wv = wloc + it * (M::PER / 32);
+        const int tn = (wv % M::WX) * M::LX + L::x(lane);
+        const int mt = (wv / M::WX) * M::LY + L::y(lane);
+        const bool live = !(M::TT < M::PER && mt >= M::MTl);
+        float acc[R][TMr][TN];
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+#pragma unroll
+            for (int q = 0; q < TMr; ++q)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[b][q][j] = 0.f;
+        if (live) {
+            int rbase[TMr];
+#pragma unroll
+            for (int q = 0; q < TMr; ++q) {
+                const int mr = q * M::MTl + mt;
+                rbase[q] = (k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r;
+            }
+            const float *wb = WT + tn * 4;
+#pragma unroll 2
+            for (int n4 = 0; n4 < M::REDP; n4 += 4) {
+                const int n = sp * M::REDP + n4;                      // first reduction index of the group
+                const int aoff = (k == 0) ? n : (n / T::r) * ISo + (n % T::r);
+                float4 a[R][TMr];
+#pragma unroll
+                for (int b = 0; b < R; ++b)
+#pragma unroll
+                    for (int q = 0; q < TMr; ++q) a[b][q] = ld4(dY + b * BSo + rbase[q] + aoff);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (k == 0 && kk >= S::G) continue;               // padded gate column
+                    float w[TN];
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const float4 t = ld4(wb + (n + kk) * KST + g * GSTR);
+                        w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int b = 0; b < R; ++b)
+#pragma unroll
+                        for (int q = 0; q < TMr; ++q) {
+                            const float av = kk == 0 ? a[b][q].x : (kk == 1 ? a[b][q].y : (kk == 2 ? a[b][q].z : a[b][q].w));
+#pragma unroll
+                            for (int j = 0; j < TN; ++j) acc[b][q][j] = fmaf(av, w[j], acc[b][q][j]);
+                        }
+                }
+            }
+        }
+        if constexpr (SPLIT == 1) {
+            if (live) {
+#pragma unroll
+                for (int q = 0; q < TMr; ++q) {
+                    const int mr = q * M::MTl + mt;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g)
+#pragma unroll
+                        for (int b = 0; b < R; ++b)
+                            st4(dX + b * T::BS + mr * T::KS + g * GSTR + tn * 4,
+                                make_float4(acc[b][q][4 * g], acc[b][q][4 * g + 1], acc[b][q][4 * g + 2], acc[b][q][4 * g + 3]));
+                }
+            }
+        } else {
+            // reduce-scatter over the SPLIT groups: owner s keeps columns j in [s*CW, (s+1)*CW)
+            constexpr int CW = M::CW;
+            const int tprime = tid % M::PER;
+#pragma unroll
+            for (int j = 0; j < TN; ++j) {
+                const int owner = j / CW, c = j % CW;
+#pragma unroll
+                for (int dlt = 1; dlt < SPLIT; ++dlt)
+                    if (((sp - owner + SPLIT) % SPLIT) == dlt) {
+#pragma unroll
+                        for (int b = 0; b < R; ++b)
+#pragma unroll
+                            for (int q = 0; q < TMr; ++q)
+                                xch[(((dlt - 1) * R + b) * TMr + q) * CW * NTHR + c * NTHR + owner * M::PER + tprime] = acc[b][q][j];
+                    }
+            }
+            __syncthreads();
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < TN; ++j) {
+                    const int owner = j / CW, c = j % CW;
+                    if (owner == sp) {
+                        const int col = (j / 4) * GSTR + tn * 4 + (j % 4);
+#pragma unroll
+                        for (int b = 0; b < R; ++b)
+#pragma unroll
+                            for (int q = 0; q < TMr; ++q) {
+                                float sum = acc[b][q][j];
+#pragma unroll
+                                for (int dlt = 1; dlt < SPLIT; ++dlt)
+                                    sum += xch[(((dlt - 1) * R + b) * TMr + q) * CW * NTHR + c * NTHR + tid];
+                                dX[b * T::BS + (q * M::MTl + mt) * T::KS + col] = sum;
+                            }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward-weight stage:  dW_k[kappa][n] += sum_m X_k[m][kappa] dY_k[m][n]
+// Thread = (kappa tile of TK=8 | 4, n tile of 4, row group mg of MG); rows m = it*MG + mg.
+// The TK x 4 tile stays in registers for the whole launch (no per-step reduction); the MG row
+// groups are summed once at the end of the launch (flush_dw).
+//   k == 0: n tile = the 4 (3 used) gates of one i0'
+// ---------------------------------------------------------------------------------------------
+template <class S, int k, int R, int TK_>
+struct BwMap {
+    using T = St<S, k>;
+    static constexpr int TK = TK_;
+    static_assert(TK == 4 || TK == 8, "TK");
+    static constexpr int KT = T::K / TK;
+    static constexpr int NT4 = (k == 0) ? (T::I / S::G) : T::N / 4;      // n tiles
+    static constexpr int TILES = KT * NT4;
+    static_assert(TILES <= NTHR && NTHR % TILES == 0, "bwd-weight tiles must divide the thread count");
+    static constexpr int MG = NTHR / TILES;
+    static constexpr int M = R * T::Mrow;
+    static constexpr int ROWS = (M + MG - 1) / MG;                        // row iterations per thread
+};
+
+template <class S, int k, int R, int TK>
+TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restrict__ dY, float (&acc)[TK][4], int tid) {
+    using T = St<S, k>;
+    using M = BwMap<S, k, R, TK>;
+    constexpr int Jp = (k == 0) ? 1 : St<S, (k == 0 ? 0 : k - 1)>::J;
+    constexpr int KSo = (k == 0) ? DY0<S>::DS : St<S, (k == 0 ? 0 : k - 1)>::KS;
+    constexpr int BSo = (k == 0) ? DY0<S>::BS : St<S, (k == 0 ? 0 : k - 1)>::BS;
+    constexpr int ISo = (k == 0) ? 0 : (T::Mrow / Jp) * KSo;
+    // tile coordinates: n tile fastest, then kappa tile, then the row group
+    const int nt = tid % M::NT4;
+    const int kt = (tid / M::NT4) % M::KT;
+    const int mg = tid / M::TILES;
+    const int n0 = nt * 4;
+    const int yoff = (k == 0) ? n0 : (n0 / T::r) * ISo + (n0 % T::r);
+#pragma unroll 2
+    for (int it = 0; it < M::ROWS; ++it) {
+        const int m = it * M::MG + mg;
+        if (M::M % M::MG != 0 && m >= M::M) break;
+        const int b = m / T::Mrow, mr = m % T::Mrow;
+        const float *xp = X + b * T::BS + mr * T::KS + kt * TK;
+        const float *yp = dY + b * BSo + ((k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r) + yoff;
+        const float4 y = ld4(yp);
+        float x[TK];
+#pragma unroll
+        for (int g = 0; g < TK / 4; ++g) {
+            const float4 t = ld4(xp + 4 * g);
+            x[4 * g] = t.x; x[4 * g + 1] = t.y; x[4 * g + 2] = t.z; x[4 * g + 3] = t.w;
+        }
+#pragma unroll
+        for (int a = 0; a < TK; ++a) {
+            acc[a][0] = fmaf(x[a], y.x, acc[a][0]);
+            acc[a][1] = fmaf(x[a], y.y, acc[a][1]);
+            acc[a][2] = fmaf(x[a], y.z, acc[a][2]);
+            if (!(k == 0 && S::G == 3)) acc[a][3] = fmaf(x[a], y.w, acc[a][3]);
+        }
+    }
+}
+
+// end of launch: sum the MG row groups of stage k and add the result to the gradient slot
+// (blob layout r,i,j,r').  stg: shared staging of K*NS floats (reuses the activation slots).
+template <class S, int k, int R, int TK>
+TTS_DEV void flush_dw(float (&acc)[TK][4], float *__restrict__ stg, float *__restrict__ slot, int tid) {
+    using T = St<S, k>;
+    using M = BwMap<S, k, R, TK>;
+    constexpr int I0p = T::I / S::G;
+    const int nt = tid % M::NT4;
+    const int kt = (tid / M::NT4) % M::KT;
+    const int mg = tid / M::TILES;
+    __syncthreads();
+    for (int g = 0; g < M::MG; ++g) {
+        if (mg == g) {
+#pragma unroll
+            for (int a = 0; a < TK; ++a)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float *p = stg + (kt * TK + a) * T::NS + nt * 4 + c;
+                    *p = (g == 0) ? acc[a][c] : *p + acc[a][c];
+                }
+        }
+        __syncthreads();
+    }
+    // staged layout = W_k shared layout [kappa][NS]; scatter-add to the blob
+    for (int e = tid; e < T::CORE; e += NTHR) {
+        const int ap = e % T::rn;
+        int t = e / T::rn;
+        const int j = t % T::J;
+        t /= T::J;
+        const int i = t % T::I;
+        const int a = t / T::I;
+        const int col = (k == 0) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
+        slot[COff<S, k>::v + e] += stg[(j * T::rn + ap) * T::NS + col];
+    }
+    __syncthreads();
+}
+
+// ---- backward tuning: forward tiles (recompute) + bwd-data tiles + bwd-weight tiles -------------
+// BTM[k] rows per thread of the bwd-data stage k, BSP = split of the last bwd-data stage, WTK[k] = TK
+template <class FT, int BTM0, int BTM1, int BTM2, int BTM3, int BSP_, int WTK0, int WTK1, int WTK2, int WTK3>
+struct TuneB {
+    using F = FT;
+    static constexpr int BTM[4] = {BTM0, BTM1, BTM2, BTM3};
+    static constexpr int BSP = BSP_;
+    static constexpr int WTK[4] = {WTK0, WTK1, WTK2, WTK3};
+};
+
+template <class S, int R, class TB>
+struct BwdSmem {
+    static constexpr int D = S::D;
+    using TU = typename TB::F;
+    using FM = FinMap<S, R, TU::FTMr, TU::FTI, TU::FSK>;
+    static constexpr int W = w_floats<S>();
+    static constexpr int WT = wt_floats<S>();
+    // every X_k kept: offsets from the start of the slot area (X_{d-1} first)
+    static constexpr int stage_bs(int k) {
+        int m = 1;
+        for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
+        for (int q = 0; q < k; ++q) m *= S::J[q];
+        return m * cpad(S::J[k] * S::RK[k + 1]);
+    }
+    static constexpr int xoff(int k) {
+        int v = 0;
+        for (int q = S::D - 1; q > k; --q) v += cr4(R * stage_bs(q));
+        return v;
+    }
+    template <int k> struct XOff { static constexpr int v = xoff(k); };
+    static constexpr int XALL = xoff(0) + cr4(R * stage_bs(0));
+    static constexpr int DY = cr4(R * DY0<S>::BS);
+    static constexpr int DHC = cr4(R * St<S, D - 1>::BS);
+    static constexpr int XCH = cmax(FM::XCH_FLOATS, BdMap<S, D - 1, R, TB::BTM[D - 1], TB::BSP>::XCH_FLOATS);
+    static constexpr int TOTAL = W + WT + XALL + DY + DHC + XCH;
+    static constexpr size_t BYTES = (size_t)TOTAL * 4;
+};
+
+struct RnnBwdSArgs {
+    int t0, steps, T;
+    long long B;
+    float *xg;               // MODE_XG: chunk buffer (B, steps, G*H): ih projection in, delta_ih out
+    long long xg_bstride;
+    const float *x1;         // MODE_RANK1: x (B, T) (not offset), row stride x1_bstride
+    long long x1_bstride;
+    const float *w_eff, *bias_ih;
+    const float *cores, *bias_hh;
+    const float *hs, *cs;    // (B,T,H) outputs / cell states of this layer
+    const float *h0, *c0;
+    const float *dhs;        // (B,T,H) or null
+    const float *dh_in, *dc_in;
+    float *dh_out, *dc_out;
+    float *partial;          // [gridDim.x][core_floats + 3*G*H]: cores, db_hh, d_weff, db_ih  (+= at the end)
+};
+
+template <class S, int R, class TB, int k>
+TTS_DEV void fwd_chain_keep(float *xs, const float *wsm, int tid) {
+    if constexpr (k >= 1) {
+        using SM = BwdSmem<S, R, TB>;
+        using TU = typename TB::F;
+        fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(xs + SM::template XOff<k>::v, wsm + WOff<S, k>::v,
+                                                   xs + SM::template XOff<k - 1>::v, tid);
+        __syncthreads();
+        fwd_chain_keep<S, R, TB, k - 1>(xs, wsm, tid);
+    }
+}
+
+// persistent dW register tiles of every stage
+template <class S, int R, class TB>
+struct DwRegs {
+    float a0[TB::WTK[0]][4];
+    float a1[S::D > 1 ? TB::WTK[S::D > 1 ? 1 : 0] : 1][4];
+    float a2[S::D > 2 ? TB::WTK[S::D > 2 ? 2 : 0] : 1][4];
+    float a3[S::D > 3 ? TB::WTK[S::D > 3 ? 3 : 0] : 1][4];
+};
+
+template <class S, int R, class TB, int k>
+TTS_DEV void bwd_chain(float *xs, float *dy0, float *dhc, const float *wt, float *xch, DwRegs<S, R, TB> &dw, int tid) {
+    using SM = BwdSmem<S, R, TB>;
+    float *X = xs + SM::template XOff<k>::v;
+    const float *dY = (k == 0) ? dy0 : xs + SM::template XOff<(k == 0 ? 0 : k - 1)>::v;
+    if constexpr (k == 0) bwd_weight_stage<S, 0, R, TB::WTK[0]>(X, dY, dw.a0, tid);
+    if constexpr (k == 1) bwd_weight_stage<S, 1, R, TB::WTK[1]>(X, dY, dw.a1, tid);
+    if constexpr (k == 2) bwd_weight_stage<S, 2, R, TB::WTK[2]>(X, dY, dw.a2, tid);
+    if constexpr (k == 3) bwd_weight_stage<S, 3, R, TB::WTK[3]>(X, dY, dw.a3, tid);
+    if constexpr (k == S::D - 1) {
+        // last stage: dX goes to the dh slot (no aliasing with X_k); split reduction
+        bwd_data_stage<S, k, R, TB::BTM[k], TB::BSP>(dY, wt + WTOff<S, k>::v, dhc, xch, tid);
+        __syncthreads();
+    } else {
+        __syncthreads();                                  // X_k is overwritten in place by dX_k
+        bwd_data_stage<S, k, R, TB::BTM[k], 1>(dY, wt + WTOff<S, k>::v, X, xch, tid);
+        __syncthreads();
+        bwd_chain<S, R, TB, k + 1>(xs, dy0, dhc, wt, xch, dw, tid);
+    }
+}
+
+template <class S, int R, class TB, int k>
+TTS_DEV void flush_all(DwRegs<S, R, TB> &dw, float *stg, float *slot, int tid) {
+    if constexpr (k == 0) flush_dw<S, 0, R, TB::WTK[0]>(dw.a0, stg, slot, tid);
+    if constexpr (k == 1) flush_dw<S, 1, R, TB::WTK[1]>(dw.a1, stg, slot, tid);
+    if constexpr (k == 2) flush_dw<S, 2, R, TB::WTK[2]>(dw.a2, stg, slot, tid);
+    if constexpr (k == 3) flush_dw<S, 3, R, TB::WTK[3]>(dw.a3, stg, slot, tid);
+    if constexpr (k + 1 < S::D) flush_all<S, R, TB, k + 1>(dw, stg, slot, tid);
+}
+
+template <class S, int CELL, int R, int MODE, class TB>
+__global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    using SM = BwdSmem<S, R, TB>;
+    using FM = typename SM::FM;
+    using TL = St<S, S::D - 1>;
+    using T0 = St<S, 0>;
+    constexpr int G = S::G, H = n_in<S>(), GH = G * H;
+    constexpr int NE = FM::NE;
+    constexpr bool LSTM = (CELL == TTRNN_CELL_LSTM);
+    const int tid = threadIdx.x;
+    float *wsm = smem;
+    float *wt = wsm + SM::W;
+    float *xs = wt + SM::WT;
+    float *dy0 = xs + SM::XALL;
+    float *dhc = dy0 + SM::DY;
+    float *xch = dhc + SM::DHC;
+    float *hslot = xs + SM::template XOff<S::D - 1>::v;
+
+    stage_weights_k<S, 0>(a.cores, wsm, tid);
+    stage_weights_t<S, 0>(a.cores, wt, tid);
+    for (int e = tid; e < SM::DY; e += NTHR) dy0[e] = 0.f;       // padded gate column stays zero
+
+    int mt, itg, kh;
+    FM::coords(tid, mt, itg, kh);
+    int hid[NE];
+    float bhh[NE][4], weff[NE][4], bih[NE][4];
+    float g_bhh[NE][4], g_weff[NE][4], g_bih[NE][4];             // gradient accumulators (whole launch)
+#pragma unroll
+    for (int n = 0; n < NE; ++n) {
+        hid[n] = FM::hidden(mt, itg, n * FM::SK + kh);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int col = g * H + hid[n];
+            const bool ok = g < G;
+            bhh[n][g] = (ok && a.bias_hh) ? __ldg(a.bias_hh + col) : 0.f;
+            weff[n][g] = (ok && MODE == MODE_RANK1) ? __ldg(a.w_eff + col) : 0.f;
+            bih[n][g] = (ok && MODE == MODE_RANK1 && a.bias_ih) ? __ldg(a.bias_ih + col) : 0.f;
+            g_bhh[n][g] = 0.f; g_weff[n][g] = 0.f; g_bih[n][g] = 0.f;
+        }
+    }
+    DwRegs<S, R, TB> dw;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a0) / 16); ++q) dw.a0[q][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a1) / 16); ++q) dw.a1[q][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a2) / 16); ++q) dw.a2[q][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a3) / 16); ++q) dw.a3[q][c] = 0.f;
+    }
+
+    const long long ntiles = (a.B + R - 1) / R;
+    for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const long long row0 = tile_i * R;
+        __syncthreads();
+        for (int e = tid; e < SM::DHC; e += NTHR) dhc[e] = 0.f;
+        float dhd[R][NE], dcs[R][NE];                            // direct dh term (GRU) and dc, per owned unit
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+#pragma unroll
+            for (int n = 0; n < NE; ++n) {
+                const bool ok = row0 + b < a.B;
+                dhd[b][n] = (ok && a.dh_in) ? __ldg(a.dh_in + (row0 + b) * H + hid[n]) : 0.f;
+                dcs[b][n] = (LSTM && ok && a.dc_in) ? __ldg(a.dc_in + (row0 + b) * H + hid[n]) : 0.f;
+            }
+        for (int t = a.steps - 1; t >= 0; --t) {
+            const int tg = a.t0 + t;
+            __syncthreads();
+            // ---- h_{t-1} -> X_{d-1} slot
+            for (int e = tid; e < R * H; e += NTHR) {
+                const int b = e / H, h = e % H;
+                const long long row = row0 + b;
+                float hv = 0.f;
+                if (row < a.B) {
+                    if (tg > 0) hv = __ldg(a.hs + (row * a.T + (tg - 1)) * H + h);
+                    else if (a.h0) hv = __ldg(a.h0 + row * H + h);
+                }
+                hslot[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hv;
+            }
+            // ---- per-unit operands of the gate phase (owner thread)
+            float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE];
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                const long long row = row0 + b;
+                const bool ok = row < a.B;
+                x1[b] = (MODE == MODE_RANK1 && ok) ? __ldg(a.x1 + row * a.x1_bstride + tg) : 0.f;
+#pragma unroll
+                for (int n = 0; n < NE; ++n) {
+                    if (MODE == MODE_XG) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            xin[b][n][g] = ok ? a.xg[row * a.xg_bstride + (long long)t * GH + g * H + hid[n]] : 0.f;
+                    }
+                    float hv = 0.f, cv = 0.f;
+                    if (ok) {
+                        if (tg > 0) {
+                            hv = __ldg(a.hs + (row * a.T + (tg - 1)) * H + hid[n]);
+                            if (LSTM) cv = __ldg(a.cs + (row * a.T + (tg - 1)) * H + hid[n]);
+                        } else {
+                            if (a.h0) hv = __ldg(a.h0 + row * H + hid[n]);
+                            if (LSTM && a.c0) cv = __ldg(a.c0 + row * H + hid[n]);
+                        }
+                    }
+                    hprev[b][n] = hv;
+                    cprev[b][n] = cv;
+                    dho[b][n] = (ok && a.dhs) ? __ldg(a.dhs + (row * a.T + tg) * H + hid[n]) : 0.f;
+                }
+            }
+            __syncthreads();
+            // ---- recompute the hh chain keeping every X_k
+            fwd_chain_keep<S, R, TB, S::D - 1>(xs, wsm, tid);
+            float pre[R][NE][4];
+            {
+                float acc[R][FM::TMr][FM::TI][4];
+                final_partial<S, R, FM>(xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg, kh, acc);
+                final_reduce<S, R, FM>(acc, pre, xch, tid, kh);
+            }
+            // ---- gates and their gradients
+#pragma unroll
+            for (int b = 0; b < R; ++b)
+#pragma unroll
+                for (int n = 0; n < NE; ++n) {
+                    const int h = hid[n];
+                    const long long row = row0 + b;
+                    const bool ok = row < a.B;
+                    float ain[4];
+#pragma unroll
+                    for (int g = 0; g < G; ++g)
+                        ain[g] = (MODE == MODE_XG) ? xin[b][n][g] : fmaf(x1[b], weff[n][g], bih[n][g]);
+                    const float dh = dhd[b][n] + dhc[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] + dho[b][n];
+                    float d_ih[4], d_hh[4];
+                    d_ih[3] = 0.f; d_hh[3] = 0.f;
+                    if (LSTM) {
+                        const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
+                        const float fg = sigmoidf_acc(pre[b][n][1] + bhh[n][1] + ain[1]);
+                        const float gg = tanhf(pre[b][n][2] + bhh[n][2] + ain[2]);
+                        const float og = sigmoidf_acc(pre[b][n][3] + bhh[n][3] + ain[3]);
+                        const float cn = fg * cprev[b][n] + ig * gg;
+                        const float tc = tanhf(cn);
+                        const float dc = dcs[b][n] + dh * og * (1.0f - tc * tc);
+                        d_hh[0] = dc * gg * ig * (1.0f - ig);
+                        d_hh[1] = dc * cprev[b][n] * fg * (1.0f - fg);
+                        d_hh[2] = dc * ig * (1.0f - gg * gg);
+                        d_hh[3] = dh * tc * og * (1.0f - og);
+                        dcs[b][n] = dc * fg;
+                        dhd[b][n] = 0.f;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) d_ih[g] = d_hh[g];
+                    } else {
+                        const float ur = pre[b][n][0] + bhh[n][0];
+                        const float uz = pre[b][n][1] + bhh[n][1];
+                        const float un = pre[b][n][2] + bhh[n][2];
+                        const float rg = sigmoidf_acc(ain[0] + ur);
+                        const float zg = sigmoidf_acc(ain[1] + uz);
+                        const float ng = tanhf(ain[2] + rg * un);
+                        const float d_n = dh * (1.0f - zg) * (1.0f - ng * ng);
+                        const float d_z = dh * (hprev[b][n] - ng) * zg * (1.0f - zg);
+                        const float d_r = d_n * un * rg * (1.0f - rg);
+                        d_ih[0] = d_r; d_ih[1] = d_z; d_ih[2] = d_n;
+                        d_hh[0] = d_r; d_hh[1] = d_z; d_hh[2] = d_n * rg;
+                        dhd[b][n] = dh * zg;
+                    }
+                    if (!ok) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) { d_ih[g] = 0.f; d_hh[g] = 0.f; }
+                    }
+                    // delta_hh -> dY_0 [b][mr][i0'*4 + g]
+                    const int mr = h % T0::Mrow, i0p = h / T0::Mrow;
+                    st4(dy0 + b * DY0<S>::BS + mr * DY0<S>::DS + i0p * 4, make_float4(d_hh[0], d_hh[1], d_hh[2], d_hh[3]));
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        if (MODE == MODE_RANK1) {
+                            g_weff[n][g] = fmaf(d_ih[g], x1[b], g_weff[n][g]);
+                            g_bih[n][g] += d_ih[g];
+                        } else if (ok) {
+                            a.xg[row * a.xg_bstride + (long long)t * GH + g * H + h] = d_ih[g];
+                        }
+                        g_bhh[n][g] += d_hh[g];
+                    }
+                }
+            __syncthreads();
+            // ---- backward chain: core gradients (register tiles) and dh_{t-1}
+            bwd_chain<S, R, TB, 0>(xs, dy0, dhc, wt, xch, dw, tid);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+#pragma unroll
+            for (int n = 0; n < NE; ++n)
+                if (row0 + b < a.B) {
+                    const int h = hid[n];
+                    a.dh_out[(row0 + b) * H + h] = dhd[b][n] + dhc[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)];
+                    if (LSTM) a.dc_out[(row0 + b) * H + h] = dcs[b][n];
+                }
+    }
+    // ---- flush gradients of this CTA into its slot
+    float *slot = a.partial + (long long)blockIdx.x * (core_floats<S>() + 3 * GH);
+    flush_all<S, R, TB, 0>(dw, xs, slot, tid);
+#pragma unroll
+    for (int n = 0; n < NE; ++n)
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const int col = g * H + hid[n];
+            slot[core_floats<S>() + col] += g_bhh[n][g];
+            slot[core_floats<S>() + GH + col] += g_weff[n][g];
+            slot[core_floats<S>() + 2 * GH + col] += g_bih[n][g];
+        }
+}
+
 }  // namespace tts

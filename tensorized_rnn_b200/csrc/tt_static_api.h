@@ -5,6 +5,7 @@
 
 namespace tts {
 struct RnnFwdSArgs;
+struct RnnBwdSArgs;
 }
 
 struct TtsRnnFwdEntry {
@@ -18,3 +19,14 @@ struct TtsRnnFwdEntry {
 
 // best registered forward kernel for (hh shape, cell, mode) at batch B on `sms` SMs, or nullptr
 const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms);
+
+struct TtsRnnBwdEntry {
+    const char *name;
+    int cell, mode, R;
+    size_t smem;
+    long long slot_floats;                                                   // floats per gradient slot
+    bool (*match)(const ttrnn_tt_shape *hh);
+    int (*launch)(const tts::RnnBwdSArgs *args, int grid, cudaStream_t st);
+    int (*prepare)(int *max_blocks_per_sm);
+};
+const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms);

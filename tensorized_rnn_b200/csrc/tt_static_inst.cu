@@ -62,7 +62,62 @@ const TtsRnnFwdEntry kFwd[] = {
     TTS_FWD(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<8, 1, 2, 8, 8, 4, 8, 4, 8>),
 };
 
+
+template <class S, int CELL, int R, int MODE, class TB>
+int launch_bwd(const tts::RnnBwdSArgs *a, int grid, cudaStream_t st) {
+    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB>::BYTES, st>>>(*a);
+    return (int)cudaGetLastError();
+}
+template <class S, int CELL, int R, int MODE, class TB>
+int prepare_bwd(int *occ) {
+    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB>::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB>::BYTES);
+}
+template <class S>
+constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * tts::n_in<S>(); }
+
+#define TTS_BWD(S, CELL, R, MODE, ...)                                                                      \
+    {#S, CELL, MODE, R, tts::BwdSmem<S, R, __VA_ARGS__>::BYTES, slot_floats<S>(), &match_shape<S>,           \
+     &launch_bwd<S, CELL, R, MODE, __VA_ARGS__>, &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__>}
+
+// TuneB<forward Tune, BTM0..3 (rows per thread of bwd-data stage k), BSP (split of the last bwd-data
+// stage), WTK0..3 (kappa rows of the register tile of bwd-weight stage k)>
+using tts::TuneB;
+using TB_d2 = TuneB<Tune<1, 2, 2, 1, 8>, 1, 1, 1, 1, 8, 8, 8, 8, 8>;
+using TB_d3_R5 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+using TB_d3_R2 = TuneB<Tune<1, 1, 1, 2, 8, 2, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+const TtsRnnBwdEntry kBwd[] = {
+    TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
+    TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d2),
+    TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, TB_d2),
+    TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
+    TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, TB_d2),
+    TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, TB_d2),
+    TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
+    TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG, TB_d3_R5),
+};
+
 }  // namespace
+
+const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms) {
+    const TtsRnnBwdEntry *best = nullptr;
+    long long best_cost = 0;
+    for (const auto &e : kBwd) {
+        if (e.cell != cell || e.mode != mode || !e.match(hh)) continue;
+        const long long tiles = (B + e.R - 1) / e.R;
+        const long long waves = (tiles + sms - 1) / sms;
+        const long long cost = waves * e.R;
+        if (!best || cost < best_cost || (cost == best_cost && e.R > best->R)) {
+            best = &e;
+            best_cost = cost;
+        }
+    }
+    return best;
+}
 
 const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms) {
     const TtsRnnFwdEntry *best = nullptr;

@@ -258,7 +258,7 @@ struct RnnLayout {
     // fwd scratch (floats)
     long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_aux = 0, f_total = 0;
     // bwd scratch (floats)
-    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_total = 0;
+    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
     int nslots = 0;
 };
@@ -292,7 +292,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     // backward scratch
     long long maxp = 0;
     for (int l = 0; l < L; ++l) {
-        long long a = rp.layer[l].ih.core_floats + GH, b = rp.layer[l].hh.core_floats + GH;
+        long long a = rp.layer[l].ih.core_floats + GH, b = rp.layer[l].hh.core_floats + 3 * GH;
         if (a > maxp) maxp = a;
         if (b > maxp) maxp = b;
     }
@@ -317,6 +317,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
         if (c.spill > spill) spill = c.spill;
     }
     lo->b_spill = o; o += r4(spill) * lo->nslots;
+    lo->b_aux = o; o += 2 * r4(GH) + 4;                   // rank-one input mode: W_ih column, its gradient, a 1.0f
     lo->b_total = o;
     return 0;
 }
@@ -630,6 +631,108 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
         float *dlin = (l == 0) ? d_x : sc + lo.b_dhs + (l & 1) * r4(lo.BTH);
         const float *b_ih = d->has_bias ? params + lp.off_ih_bias : nullptr;
         const float *b_hh = d->has_bias ? params + lp.off_hh_bias : nullptr;
+
+        // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
+        const int mode = (l == 0 && d->input_size == 1 && !d_x) ? tts::MODE_RANK1 : tts::MODE_XG;
+        const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms) : nullptr;
+        if (be) {
+            int occ = 0;
+            int rc = be->prepare(&occ);
+            if (rc || occ < 1) return fail("static kernel %s cannot be configured (cuda error %d)", be->name, rc);
+            long long g = (long long)occ * dv.sms;
+            const long long tiles = (B + be->R - 1) / be->R;
+            if (g > tiles) g = tiles;
+            if (g > lo.nslots) g = lo.nslots;
+            const int sgrid = (int)g;
+            const long long slot = be->slot_floats;
+            if (slot > lo.part_stride) return fail("internal: gradient slot too small");
+            const long long ih_slot = lp.ih.core_floats + GH;
+            CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)slot * sgrid * 4, st));
+            CU_CHECK(cudaMemsetAsync(part_ih, 0, (size_t)ih_slot * lo.nslots * 4, st));
+            tts::RnnBwdSArgs sa;
+            memset(&sa, 0, sizeof sa);
+            sa.B = B; sa.T = T;
+            sa.cores = params + lp.off_hh_cores;
+            sa.hs = lout; sa.cs = lcs; sa.h0 = h0; sa.c0 = c0; sa.dhs = dhs;
+            sa.partial = part_hh;
+            float *aux = sc + lo.b_aux;
+            float *aux_g = aux + r4(GH);
+            float *one = aux_g + r4(GH);
+            int ih_used = 0;
+            if (mode == tts::MODE_RANK1) {
+                k_fill<<<1, 32, 0, st>>>(one, 1.0f, 1);
+                ++g_launches;
+                if (launch_ttlinear_fwd(lp.ih, dv, 1, 1, one, 0, params + lp.off_ih_cores, nullptr, nullptr, aux, 0, st))
+                    return 1;
+                sa.w_eff = aux; sa.bias_ih = b_ih; sa.bias_hh = b_hh;
+                sa.x1 = lin; sa.x1_bstride = T;
+                sa.t0 = 0; sa.steps = T;
+                sa.dh_in = (l == L - 1) ? d_hT : nullptr;
+                sa.dc_in = (l == L - 1) ? d_cT : nullptr;
+                sa.dh_out = sdh; sa.dc_out = sdc;
+                {
+                    KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                    rc = be->launch(&sa, sgrid, st);
+                }
+                ++g_launches;
+                if (rc) return fail("static kernel %s launch failed: %s", be->name, cudaGetErrorString((cudaError_t)rc));
+            } else {
+                sa.bias_hh = lstm ? nullptr : b_hh;
+                const int nchunks = (T + lo.Tc - 1) / lo.Tc;
+                for (int ci = nchunks - 1; ci >= 0; --ci) {
+                    const int t0 = ci * lo.Tc;
+                    const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
+                    const bool last = (t0 + tc == T);
+                    if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                            params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st))
+                        return 1;
+                    sa.t0 = t0; sa.steps = tc;
+                    sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
+                    sa.dh_in = last ? (l == L - 1 ? d_hT : nullptr) : sdh;
+                    sa.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
+                    sa.dh_out = sdh; sa.dc_out = sdc;
+                    {
+                        KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                        rc = be->launch(&sa, sgrid, st);
+                    }
+                    ++g_launches;
+                    if (rc) return fail("static kernel %s launch failed: %s", be->name, cudaGetErrorString((cudaError_t)rc));
+                    if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                            params + lp.off_ih_cores, xg, (long long)tc * GH,
+                                            dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
+                                            lo.nslots, sc + lo.b_spill, 1, st, &ih_used))
+                        return 1;
+                }
+            }
+            // fold the per-CTA slots into the gradient blob
+            const long long cf = lp.hh.core_floats;
+            if (reduce_partials(part_hh, sgrid, slot, 0, (int)cf, d_params + lp.off_hh_cores, st)) return 1;
+            if (mode == tts::MODE_RANK1) {
+                if (d->has_bias) {
+                    if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, st)) return 1;
+                    if (reduce_partials(part_hh, sgrid, slot, cf + 2 * GH, GH, d_params + lp.off_ih_bias, st)) return 1;
+                }
+                // gradient of the dense W_ih column -> TT cores of W_ih (one-row TT-matvec backward)
+                if (reduce_partials(part_hh, sgrid, slot, cf + GH, GH, aux_g, st)) return 1;
+                if (launch_ttlinear_bwd(lp.ih, dv, 1, 1, one, 0, params + lp.off_ih_cores, aux_g, 0, nullptr, 0, part_ih,
+                                        lo.nslots, sc + lo.b_spill, 0, st, &ih_used))
+                    return 1;
+                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
+            } else {
+                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
+                if (d->has_bias) {
+                    if (reduce_partials(part_ih, ih_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) return 1;
+                    if (lstm) {
+                        if (axpy1(d_params + lp.off_ih_bias, d_params + lp.off_hh_bias, GH, 0, st)) return 1;
+                    } else {
+                        if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, st)) return 1;
+                    }
+                }
+            }
+            if (d_h0 && axpy1(sdh, d_h0, lo.BH, l != L - 1, st)) return 1;
+            if (lstm && d_c0 && axpy1(sdc, d_c0, lo.BH, l != L - 1, st)) return 1;
+            continue;
+        }
 
         RnnBwdArgs a;
         memset(&a, 0, sizeof a);

@@ -19,21 +19,22 @@ __device__ __forceinline__ float lds(unsigned addr) {
 }
 
 __device__ int pattern(int p, int lane) {
+    const int l = lane;
     switch (p) {
-    case 0: return (lane / 2) % 8;                    // 8 uniq pair-blocked, dup across halves
-    case 1: return (lane % 2) + 2 * (lane / 16);      // 4 uniq, period 2 inside each half
-    case 2: return (lane / 2) * 17;                   // 16 rows pair-blocked
-    case 3: return ((lane / 2) % 8) * 17;             // 8 rows pair-blocked dup across halves
-    case 4: return (lane % 2) * 17 + (lane / 16) * 34;// 4 rows period 2 inside halves
-    case 5: return (lane / 4) % 4;                    // 4 uniq quad-blocked dup across halves
-    case 6: return (lane % 2) + 2 * (lane / 8);       // 8 uniq period 2 inside quarters
-    case 7: return (lane / 2) % 4;                    // 4 uniq pair-blocked, dup across quarters
-    case 8: return (lane % 2) + 2 * ((lane / 4) % 2); // period 2 in quads
-    case 9: return lane / 2 + 16 * (lane % 2);        // 32 uniq: pairs far apart
-    case 10: return (lane % 16) / 2;                  // = case 0
-    case 11: return (lane / 16) + 2 * (lane % 2);     // 4 uniq
-    case 12: return (lane / 8) * 17 + (lane % 8) / 2; // 16 uniq: 4 per quarter pair-blocked
-    case 13: return (lane % 2);                       // 2 uniq period 2
+    case 0: return (l % 2) + 2 * (l / 4);                  // 16 uniq: b0 + bits 2..4
+    case 1: return (l >> 2) * 17 + ((l >> 1) & 1) * 2;     // X-type: mg rows (stride 17) x kt
+    case 2: return (l >> 2) * 9 + (l & 1) * 2;             // dY0-type
+    case 3: return (l >> 2) + (l & 1) * 34;                // dYk-type
+    case 4: return (l >> 1) * 17;                          // 16 rows pair-blocked
+    case 5: return (l & 1) * 8 + (l >> 4) * 16;            // 4 uniq: b0 and b4
+    case 6: return ((l >> 1) & 7) * 17 + (l >> 4) * 2;     // 16 uniq: bits1-3 rows, bit4 col : pair-blocked
+    case 7: return (l & 1) * 17 + ((l >> 4) & 1) * 34 + 0; // y-type 4 uniq rows
+    case 8: return (l >> 1) + (l & 1) * 64;                // 32 uniq, pair far apart (float4 units)
+    case 9: return l * 9;                                  // 32 rows stride 9 float4
+    case 10: return (l >> 3) * 17 + (l & 7);               // 32 uniq: 8 consecutive per quarter
+    case 11: return (l & 15) * 17 + (l >> 4) * 4;          // 32 uniq
+    case 12: return (l >> 1) * 9;                          // 16 rows stride 9
+    case 13: return (l >> 2) * 17;                         // 8 rows quad-blocked
     default: return lane;
     }
 }
@@ -41,7 +42,7 @@ __device__ int pattern(int p, int lane) {
 template <int W>
 __global__ void probe(int p, int iters, float *out, long long *cyc) {
     extern __shared__ float sm[];
-    for (int i = threadIdx.x; i < 12288; i += blockDim.x) sm[i] = (float)i;
+    for (int i = threadIdx.x; i < 16384; i += blockDim.x) sm[i] = (float)i;
     __syncthreads();
     const int lane = threadIdx.x & 31;
     unsigned base = (unsigned)__cvta_generic_to_shared(sm) + pattern(p, lane) * (W * 4);
@@ -68,14 +69,14 @@ int main() {
     float *out; long long *cyc;
     cudaMalloc(&out, 4); cudaMalloc(&cyc, 8);
     const int iters = 2000;
-    const char *names[] = {"(l/2)%8","(l%2)+2*(l/16)","(l/2)*17","((l/2)%8)*17","(l%2)*17+(l/16)*34","(l/4)%4","(l%2)+2*(l/8)","(l/2)%4","(l%2)+2*((l/4)%2)","l/2+16*(l%2)","(l%16)/2","(l/16)+2*(l%2)","(l/8)*17+(l%8)/2","l%2"};
-    for (int w = 4; w >= 2; w /= 2) {
+    const char *names[] = {"(l%2)+2*(l/4)","X: (l>>2)*17+((l>>1)&1)*2","dY0: (l>>2)*9+(l&1)*2","dYk: (l>>2)+(l&1)*34","(l>>1)*17","(l&1)*8+(l>>4)*16","((l>>1)&7)*17+(l>>4)*2","(l&1)*17+((l>>4)&1)*34","(l>>1)+(l&1)*64","l*9","(l>>3)*17+(l&7)","(l&15)*17+(l>>4)*4","(l>>1)*9","(l>>2)*17"};
+    for (int w = 4; w >= 4; w /= 2) {
         for (int p = 0; p < 14; ++p) {
             for (int warps = 16; warps <= 16; warps *= 2) {
                 long long c = 0;
-                if (w == 4) probe<4><<<148, warps * 32, 49152>>>(p, iters, out, cyc);
-                else if (w == 2) probe<2><<<148, warps * 32, 49152>>>(p, iters, out, cyc);
-                else probe<1><<<148, warps * 32, 49152>>>(p, iters, out, cyc);
+                cudaFuncSetAttribute(probe<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); if (w == 4) probe<4><<<148, warps * 32, 65536>>>(p, iters, out, cyc);
+                else if (w == 2) probe<2><<<148, warps * 32, 65536>>>(p, iters, out, cyc);
+                else probe<1><<<148, warps * 32, 65536>>>(p, iters, out, cyc);
                 cudaDeviceSynchronize();
                 cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
                 double per = (double)c / (iters * 16.0 * warps);
