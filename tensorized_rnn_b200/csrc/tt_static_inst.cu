@@ -19,6 +19,8 @@ TTS_SHAPE(HH_H256_d3r8_lstm, 3, 4, ARR(J, 4, 8, 8) ARR(I, 8, 8, 16) ARR(RK, 1, 8
 TTS_SHAPE(HH_H256_d4r16_lstm, 4, 4, ARR(J, 4, 4, 4, 4) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
 TTS_SHAPE(HH_H1024_d4r8_lstm, 4, 4, ARR(J, 4, 4, 8, 8) ARR(I, 8, 8, 8, 8) ARR(RK, 1, 8, 8, 8, 1))
 
+constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
+
 template <class S>
 bool match_shape(const ttrnn_tt_shape *s) {
     if (s->d != S::D) return false;
@@ -88,6 +90,7 @@ using tts::TuneB;
 using TB_d2 = TuneB<Tune<1, 2, 2, 1, 8>, 1, 1, 1, 1, 8, 8, 8, 8, 8>;
 using TB_d3_R5 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
 using TB_d3_R2 = TuneB<Tune<1, 1, 1, 2, 8, 2, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+using TB_d3_R3 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
 const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
     TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
@@ -98,7 +101,7 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, TB_d2),
     TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, TB_d2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
-    TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG, TB_d3_R5),
+    TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
 };
 
 }  // namespace
@@ -107,7 +110,7 @@ const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int m
     const TtsRnnBwdEntry *best = nullptr;
     long long best_cost = 0;
     for (const auto &e : kBwd) {
-        if (e.cell != cell || e.mode != mode || !e.match(hh)) continue;
+        if (e.cell != cell || e.mode != mode || !e.match(hh) || e.smem > kMaxSmem) continue;
         const long long tiles = (B + e.R - 1) / e.R;
         const long long waves = (tiles + sms - 1) / sms;
         const long long cost = waves * e.R;
@@ -123,7 +126,7 @@ const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int m
     const TtsRnnFwdEntry *best = nullptr;
     long long best_cost = 0;
     for (const auto &e : kFwd) {
-        if (e.cell != cell || e.mode != mode || !e.match(hh)) continue;
+        if (e.cell != cell || e.mode != mode || !e.match(hh) || e.smem > kMaxSmem) continue;
         const long long tiles = (B + e.R - 1) / e.R;
         const long long waves = (tiles + sms - 1) / sms;
         const long long cost = waves * e.R;               // rows processed back to back by the busiest SM
