@@ -29,6 +29,12 @@ constexpr int p2div(int n, int want) {
 
 #define TTS_DEV __device__ __forceinline__
 
+TTS_DEV void cp_async16(float *smem_dst, const float *gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+TTS_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 TTS_DEV float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 TTS_DEV void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
@@ -155,21 +161,33 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
                 for (int j = 0; j < TN; ++j) acc[b][q][j] = 0.f;
         const float *xb = X + mt * T::KS;
         const float *wb = W + tn * 4;
+        // software pipeline: the A fragment of the next 4 kappas and the W fragment of the next kappa
+        // are requested before the FMAs of the current ones
+        float4 a[R][TMr], an[R][TMr];
+        float4 wc[NG], wn[NG];
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+#pragma unroll
+            for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) wc[g] = ld4(wb + g * GSTR);
 #pragma unroll 2
         for (int k4 = 0; k4 < T::K; k4 += 4) {
-            float4 a[R][TMr];
+            if (k4 + 4 < T::K) {
 #pragma unroll
-            for (int b = 0; b < R; ++b)
+                for (int b = 0; b < R; ++b)
 #pragma unroll
-                for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS + k4);
+                    for (int q = 0; q < TMr; ++q) an[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS + k4 + 4);
+            }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
+                if (k4 + kk + 1 < T::K) {
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) wn[g] = ld4(wb + (k4 + kk + 1) * T::NS + g * GSTR);
+                }
                 float w[TN];
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const float4 t = ld4(wb + (k4 + kk) * T::NS + g * GSTR);
-                    w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
-                }
+                for (int g = 0; g < NG; ++g) { w[4 * g] = wc[g].x; w[4 * g + 1] = wc[g].y; w[4 * g + 2] = wc[g].z; w[4 * g + 3] = wc[g].w; }
 #pragma unroll
                 for (int b = 0; b < R; ++b)
 #pragma unroll
@@ -178,7 +196,13 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
 #pragma unroll
                         for (int j = 0; j < TN; ++j) acc[b][q][j] = fmaf(av, w[j], acc[b][q][j]);
                     }
+#pragma unroll
+                for (int g = 0; g < NG; ++g) wc[g] = wn[g];
             }
+#pragma unroll
+            for (int b = 0; b < R; ++b)
+#pragma unroll
+                for (int q = 0; q < TMr; ++q) a[b][q] = an[b][q];
         }
 #pragma unroll
         for (int q = 0; q < TMr; ++q) {
@@ -344,7 +368,12 @@ TTS_DEV void final_reduce(float (&acc)[R][FM::TMr][FM::TI][4], float (&pre)[R][F
     }
 }
 
+#ifdef TTS_FAST_GATES
+// MUFU-based logistic: ex2.approx + rcp.approx, ~3e-7 relative error (validated against the 1e-5 bar)
+TTS_DEV float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+#else
 TTS_DEV float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+#endif
 
 // ---- per (shape, R) tuning table ----------------------------------------------------------------
 // TMr[k], TN[k] for the forward stages k >= 1; FTMr / FTI / FSK for the final stage
@@ -872,7 +901,8 @@ struct BwdSmem {
     static constexpr int DY = cr4(R * DY0<S>::BS);
     static constexpr int DHC = cr4(R * St<S, D - 1>::BS);
     static constexpr int XCH = cmax(FM::XCH_FLOATS, BdMap<S, D - 1, R, TB::BTM[D - 1], TB::BSP>::XCH_FLOATS);
-    static constexpr int TOTAL = W + WT + XALL + DY + DHC + XCH;
+    static constexpr int H2 = cr4(R * St<S, D - 1>::BS);          // second h_{t-1} slot (cp.async double buffer)
+    static constexpr int TOTAL = W + WT + XALL + DY + DHC + XCH + H2;
     static constexpr size_t BYTES = (size_t)TOTAL * 4;
 };
 
@@ -894,14 +924,14 @@ struct RnnBwdSArgs {
 };
 
 template <class S, int R, class TB, int k>
-TTS_DEV void fwd_chain_keep(float *xs, const float *wsm, int tid) {
+TTS_DEV void fwd_chain_keep(float *xs, const float *hcur, const float *wsm, int tid) {
     if constexpr (k >= 1) {
         using SM = BwdSmem<S, R, TB>;
         using TU = typename TB::F;
-        fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(xs + SM::template XOff<k>::v, wsm + WOff<S, k>::v,
-                                                   xs + SM::template XOff<k - 1>::v, tid);
+        const float *X = (k == S::D - 1) ? hcur : xs + SM::template XOff<k>::v;
+        fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(X, wsm + WOff<S, k>::v, xs + SM::template XOff<k - 1>::v, tid);
         __syncthreads();
-        fwd_chain_keep<S, R, TB, k - 1>(xs, wsm, tid);
+        fwd_chain_keep<S, R, TB, k - 1>(xs, hcur, wsm, tid);
     }
 }
 
@@ -915,9 +945,10 @@ struct DwRegs {
 };
 
 template <class S, int R, class TB, int k>
-TTS_DEV void bwd_chain(float *xs, float *dy0, float *dhc, const float *wt, float *xch, DwRegs<S, R, TB> &dw, int tid) {
+TTS_DEV void bwd_chain(float *xs, float *hcur, float *dy0, float *dhc, const float *wt, float *xch,
+                       DwRegs<S, R, TB> &dw, int tid) {
     using SM = BwdSmem<S, R, TB>;
-    float *X = xs + SM::template XOff<k>::v;
+    float *X = (k == S::D - 1) ? hcur : xs + SM::template XOff<k>::v;
     const float *dY = (k == 0) ? dy0 : xs + SM::template XOff<(k == 0 ? 0 : k - 1)>::v;
     if constexpr (k == 0) bwd_weight_stage<S, 0, R, TB::WTK[0]>(X, dY, dw.a0, tid);
     if constexpr (k == 1) bwd_weight_stage<S, 1, R, TB::WTK[1]>(X, dY, dw.a1, tid);
@@ -931,7 +962,7 @@ TTS_DEV void bwd_chain(float *xs, float *dy0, float *dhc, const float *wt, float
         __syncthreads();                                  // X_k is overwritten in place by dX_k
         bwd_data_stage<S, k, R, TB::BTM[k], 1>(dY, wt + WTOff<S, k>::v, X, xch, tid);
         __syncthreads();
-        bwd_chain<S, R, TB, k + 1>(xs, dy0, dhc, wt, xch, dw, tid);
+        bwd_chain<S, R, TB, k + 1>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
     }
 }
 
@@ -961,7 +992,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
     float *dy0 = xs + SM::XALL;
     float *dhc = dy0 + SM::DY;
     float *xch = dhc + SM::DHC;
-    float *hslot = xs + SM::template XOff<S::D - 1>::v;
+    float *hbuf[2] = {xs + SM::template XOff<S::D - 1>::v, xch + SM::XCH};
 
     stage_weights_k<S, 0>(a.cores, wsm, tid);
     stage_weights_t<S, 0>(a.cores, wt, tid);
@@ -1012,56 +1043,80 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 dhd[b][n] = (ok && a.dh_in) ? __ldg(a.dh_in + (row0 + b) * H + hid[n]) : 0.f;
                 dcs[b][n] = (LSTM && ok && a.dc_in) ? __ldg(a.dc_in + (row0 + b) * H + hid[n]) : 0.f;
             }
-        for (int t = a.steps - 1; t >= 0; --t) {
-            const int tg = a.t0 + t;
-            __syncthreads();
-            // ---- h_{t-1} -> X_{d-1} slot
-            for (int e = tid; e < R * H; e += NTHR) {
+        // h_{t-1} tiles are double-buffered with cp.async one step ahead; per-unit operands of the gate
+        // phase are fetched into registers one step ahead as well
+        auto fetch_h = [&](float *dst, int tgl) {          // h_{tgl-1} -> dst (X_{d-1} layout)
+            for (int e = tid * 4; e < R * H; e += NTHR * 4) {
                 const int b = e / H, h = e % H;
                 const long long row = row0 + b;
-                float hv = 0.f;
+                float *d4 = dst + b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K);
+                const float *src = nullptr;
                 if (row < a.B) {
-                    if (tg > 0) hv = __ldg(a.hs + (row * a.T + (tg - 1)) * H + h);
-                    else if (a.h0) hv = __ldg(a.h0 + row * H + h);
+                    if (tgl > 0) src = a.hs + (row * a.T + (tgl - 1)) * H + h;
+                    else if (a.h0) src = a.h0 + row * H + h;
                 }
-                hslot[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hv;
+                if (src) cp_async16(d4, src);
+                else st4(d4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
-            // ---- per-unit operands of the gate phase (owner thread)
-            float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE];
+        };
+        float xin_n[R][NE][4], x1_n[R], cprev_n[R][NE], dho_n[R][NE];
+        auto fetch_regs = [&](int tl) {                   // operands of local step tl
+            const int tgl = a.t0 + tl;
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 const long long row = row0 + b;
                 const bool ok = row < a.B;
-                x1[b] = (MODE == MODE_RANK1 && ok) ? __ldg(a.x1 + row * a.x1_bstride + tg) : 0.f;
+                x1_n[b] = (MODE == MODE_RANK1 && ok) ? __ldg(a.x1 + row * a.x1_bstride + tgl) : 0.f;
 #pragma unroll
                 for (int n = 0; n < NE; ++n) {
                     if (MODE == MODE_XG) {
 #pragma unroll
                         for (int g = 0; g < G; ++g)
-                            xin[b][n][g] = ok ? a.xg[row * a.xg_bstride + (long long)t * GH + g * H + hid[n]] : 0.f;
+                            xin_n[b][n][g] = ok ? a.xg[row * a.xg_bstride + (long long)tl * GH + g * H + hid[n]] : 0.f;
                     }
-                    float hv = 0.f, cv = 0.f;
-                    if (ok) {
-                        if (tg > 0) {
-                            hv = __ldg(a.hs + (row * a.T + (tg - 1)) * H + hid[n]);
-                            if (LSTM) cv = __ldg(a.cs + (row * a.T + (tg - 1)) * H + hid[n]);
-                        } else {
-                            if (a.h0) hv = __ldg(a.h0 + row * H + hid[n]);
-                            if (LSTM && a.c0) cv = __ldg(a.c0 + row * H + hid[n]);
-                        }
+                    float cv = 0.f;
+                    if (LSTM && ok) {
+                        if (tgl > 0) cv = __ldg(a.cs + (row * a.T + (tgl - 1)) * H + hid[n]);
+                        else if (a.c0) cv = __ldg(a.c0 + row * H + hid[n]);
                     }
-                    hprev[b][n] = hv;
-                    cprev[b][n] = cv;
-                    dho[b][n] = (ok && a.dhs) ? __ldg(a.dhs + (row * a.T + tg) * H + hid[n]) : 0.f;
+                    cprev_n[b][n] = cv;
+                    dho_n[b][n] = (ok && a.dhs) ? __ldg(a.dhs + (row * a.T + tgl) * H + hid[n]) : 0.f;
                 }
             }
+        };
+        fetch_h(hbuf[(a.steps - 1) & 1], a.t0 + a.steps - 1);
+        fetch_regs(a.steps - 1);
+        cp_async_wait_all();
+        for (int t = a.steps - 1; t >= 0; --t) {
+            const int tg = a.t0 + t;
+            float *hcur = hbuf[t & 1];
             __syncthreads();
+            // operands of this step (fetched during the previous one)
+            float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE];
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                x1[b] = x1_n[b];
+#pragma unroll
+                for (int n = 0; n < NE; ++n) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) xin[b][n][g] = xin_n[b][n][g];
+                    cprev[b][n] = cprev_n[b][n];
+                    dho[b][n] = dho_n[b][n];
+                    hprev[b][n] = hcur[b * TL::BS + (hid[n] / TL::K) * TL::KS + (hid[n] % TL::K)];
+                }
+            }
+            // request the operands of step t-1 now; they land while this step computes
+            if (t > 0) {
+                fetch_h(hbuf[(t - 1) & 1], tg - 1);
+                fetch_regs(t - 1);
+            }
             // ---- recompute the hh chain keeping every X_k
-            fwd_chain_keep<S, R, TB, S::D - 1>(xs, wsm, tid);
+            fwd_chain_keep<S, R, TB, S::D - 1>(xs, hcur, wsm, tid);
             float pre[R][NE][4];
             {
                 float acc[R][FM::TMr][FM::TI][4];
-                final_partial<S, R, FM>(xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg, kh, acc);
+                final_partial<S, R, FM>((S::D == 1) ? hcur : xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg,
+                                        kh, acc);
                 final_reduce<S, R, FM>(acc, pre, xch, tid, kh);
             }
             // ---- gates and their gradients
@@ -1129,7 +1184,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 }
             __syncthreads();
             // ---- backward chain: core gradients (register tiles) and dh_{t-1}
-            bwd_chain<S, R, TB, 0>(xs, dy0, dhc, wt, xch, dw, tid);
+            bwd_chain<S, R, TB, 0>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
+            cp_async_wait_all();
         }
         __syncthreads();
 #pragma unroll
