@@ -45,8 +45,10 @@ template <class S, int k>
 struct St {
     static_assert(k >= 0 && k < S::D, "stage index");
     static constexpr int J = S::J[k], I = S::I[k], r = S::RK[k], rn = S::RK[k + 1];
-    static constexpr int K = J * rn;
+    static constexpr int Kraw = J * rn;               // contraction length in the blob
+    static constexpr int K = cr4(Kraw);               // compute length (zero-padded; only a last stage with odd j needs it)
     static constexpr int N = I * r;
+    static constexpr bool PACK = (S::G > 0);          // gate-interleaved layout of stage 0 (recurrent hh chains)
     static constexpr int mrow() {
         int m = 1;
         for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
@@ -57,7 +59,7 @@ struct St {
     static constexpr int KS = cpad(K);
     static constexpr int BS = Mrow * KS;              // floats per batch row of X_k
     // shared-memory weight layout: k >= 1: [kappa][n] stride NS;  k == 0: [kappa][i0'][4 gates]
-    static constexpr int NW = (k == 0) ? (I / S::G) * 4 : N;
+    static constexpr int NW = (k == 0 && PACK) ? (I / (PACK ? S::G : 1)) * 4 : N;
     static constexpr int NS = cpad(NW);
     static constexpr int WFLOATS = cr4(K * NS);
     static constexpr int CORE = r * I * J * rn;       // floats of core k in the blob
@@ -77,7 +79,9 @@ template <class S> constexpr int core_floats() { return COff<S, S::D - 1>::v + S
 template <class S, int k>
 TTS_DEV void stage_weights_k(const float *__restrict__ cores, float *__restrict__ wsm, int tid) {
     using T = St<S, k>;
-    constexpr int I0p = T::I / S::G;
+    constexpr int I0p = T::PACK ? T::I / (T::PACK ? S::G : 1) : 1;
+    if (T::K != T::Kraw)         // zero rows of a padded contraction
+        for (int e = tid; e < (T::K - T::Kraw) * T::NS; e += NTHR) wsm[WOff<S, k>::v + T::Kraw * T::NS + e] = 0.f;
     for (int e = tid; e < T::CORE; e += NTHR) {
         const int ap = e % T::rn;
         int t = e / T::rn;
@@ -86,7 +90,7 @@ TTS_DEV void stage_weights_k(const float *__restrict__ cores, float *__restrict_
         const int i = t % T::I;
         const int a = t / T::I;
         int col;
-        if (k == 0) col = (i % I0p) * 4 + (i / I0p);      // gate index = i / I0p (gates are the high part of i_0)
+        if (k == 0 && T::PACK) col = (i % I0p) * 4 + (i / I0p);   // gate index = i / I0p (gates are the high part of i_0)
         else col = i * T::r + a;
         wsm[WOff<S, k>::v + (j * T::rn + ap) * T::NS + col] = __ldg(cores + COff<S, k>::v + e);
     }
@@ -368,8 +372,9 @@ TTS_DEV void final_reduce(float (&acc)[R][FM::TMr][FM::TI][4], float (&pre)[R][F
     }
 }
 
-#ifdef TTS_FAST_GATES
-// MUFU-based logistic: ex2.approx + rcp.approx, ~3e-7 relative error (validated against the 1e-5 bar)
+#ifndef TTS_ACCURATE_GATES
+// MUFU-based logistic (ex2.approx + rcp.approx): measured parity error stays at 1-4e-7 forward and
+// <= 7e-7 on gradients (tools/parity_report.py), bars are 1e-5 / 1e-4.  -DTTS_ACCURATE_GATES restores expf + IEEE division.
 TTS_DEV float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 #else
 TTS_DEV float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -382,6 +387,26 @@ struct Tune {
     static constexpr int FTMr = FTMr_, FTI = FTI_, FSK = FSK_;
     static constexpr int TMr[4] = {0, TM1, TM2, TM3};
     static constexpr int TN[4] = {0, TN1, TN2, TN3};
+};
+
+// ping-pong slots of a forward-only chain: P holds X_{d-2}, X_{d-4}, ..; Q holds X_{d-3}, ..
+template <class S, int R>
+struct PPSlots {
+    static constexpr int D = S::D;
+    static constexpr int pfloats() {
+        int m = 0;
+        if (D >= 2) m = cmax(m, St<S, (D >= 2 ? D - 2 : 0)>::BS);
+        if (D >= 4) m = cmax(m, St<S, (D >= 4 ? D - 4 : 0)>::BS);
+        if (D >= 6) m = cmax(m, St<S, (D >= 6 ? D - 6 : 0)>::BS);
+        return cr4(R * m);
+    }
+    static constexpr int qfloats() {
+        int m = 0;
+        if (D >= 3) m = cmax(m, St<S, (D >= 3 ? D - 3 : 0)>::BS);
+        if (D >= 5) m = cmax(m, St<S, (D >= 5 ? D - 5 : 0)>::BS);
+        return cr4(R * m);
+    }
+    static constexpr int P = pfloats(), Q = qfloats();
 };
 
 // shared-memory floats of the forward recurrent kernel
@@ -593,10 +618,11 @@ template <class S, int k>
 TTS_DEV void stage_weights_t(const float *__restrict__ cores, float *__restrict__ wt, int tid) {
     using T = St<S, k>;
     using TT_ = StT<S, k>;
-    constexpr int I0p = T::I / S::G;
-    if (k == 0 && S::G == 3)
-        for (int e = tid; e < TT_::FLOATS; e += NTHR) wt[WTOff<S, 0>::v + e] = 0.f;
-    if (k == 0 && S::G == 3) __syncthreads();
+    constexpr int I0p = T::PACK ? T::I / (T::PACK ? S::G : 1) : 1;
+    constexpr bool ZERO = (k == 0 && S::G == 3) || (T::K != T::Kraw);
+    if (ZERO)
+        for (int e = tid; e < TT_::FLOATS; e += NTHR) wt[WTOff<S, k>::v + e] = 0.f;
+    if (ZERO) __syncthreads();
     for (int e = tid; e < T::CORE; e += NTHR) {
         const int ap = e % T::rn;
         int t = e / T::rn;
@@ -604,7 +630,7 @@ TTS_DEV void stage_weights_t(const float *__restrict__ cores, float *__restrict_
         t /= T::J;
         const int i = t % T::I;
         const int a = t / T::I;
-        const int row = (k == 0) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
+        const int row = (k == 0 && T::PACK) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
         wt[WTOff<S, k>::v + row * TT_::KST + j * T::rn + ap] = __ldg(cores + COff<S, k>::v + e);
     }
     if constexpr (k + 1 < S::D) stage_weights_t<S, k + 1>(cores, wt, tid);
@@ -621,7 +647,7 @@ TTS_DEV void stage_weights_t(const float *__restrict__ cores, float *__restrict_
 // ---------------------------------------------------------------------------------------------
 template <class S> struct DY0 {
     using T = St<S, 0>;
-    static constexpr int DS = cpad((T::I / S::G) * 4);       // row stride
+    static constexpr int DS = cpad(T::NW);                   // row stride
     static constexpr int BS = T::Mrow * DS;                  // per batch row
 };
 
@@ -634,7 +660,7 @@ struct BdMap {
     static constexpr int GSTR = T::K / NG;
     static constexpr int CTl = T::K / TN;
     static constexpr int MTl = T::Mrow / TMr;
-    static constexpr int RED = (k == 0) ? (T::I / S::G) * 4 : T::N;    // reduction length (incl. padded gate)
+    static constexpr int RED = T::NW;                           // reduction length (incl. the padded gate of stage 0)
     static_assert(T::Mrow % TMr == 0 && (RED / 4) % SPLIT == 0, "bwd-data tile shape");
     static constexpr int LX = CTl >= 16 ? 16 : CTl;
     static constexpr int LY = 32 / LX;
@@ -699,7 +725,7 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
                     for (int q = 0; q < TMr; ++q) a[b][q] = ld4(dY + b * BSo + rbase[q] + aoff);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    if (k == 0 && kk >= S::G) continue;               // padded gate column
+                    if (k == 0 && T::PACK && kk >= S::G) continue;    // padded gate column
                     float w[TN];
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
@@ -784,7 +810,7 @@ struct BwMap {
     static constexpr int TK = TK_;
     static_assert(TK == 4 || TK == 8, "TK");
     static constexpr int KT = T::K / TK;
-    static constexpr int NT4 = (k == 0) ? (T::I / S::G) : T::N / 4;      // n tiles
+    static constexpr int NT4 = T::NW / 4;                                 // n tiles (stage 0 of a gate chain: one i0')
     static constexpr int TILES = KT * NT4;
     static_assert(TILES <= NTHR && NTHR % TILES == 0, "bwd-weight tiles must divide the thread count");
     static constexpr int MG = NTHR / TILES;
@@ -825,7 +851,7 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
             acc[a][0] = fmaf(x[a], y.x, acc[a][0]);
             acc[a][1] = fmaf(x[a], y.y, acc[a][1]);
             acc[a][2] = fmaf(x[a], y.z, acc[a][2]);
-            if (!(k == 0 && S::G == 3)) acc[a][3] = fmaf(x[a], y.w, acc[a][3]);
+            if (!(k == 0 && T::PACK && S::G == 3)) acc[a][3] = fmaf(x[a], y.w, acc[a][3]);
         }
     }
 }
@@ -836,7 +862,7 @@ template <class S, int k, int R, int TK>
 TTS_DEV void flush_dw(float (&acc)[TK][4], float *__restrict__ stg, float *__restrict__ slot, int tid) {
     using T = St<S, k>;
     using M = BwMap<S, k, R, TK>;
-    constexpr int I0p = T::I / S::G;
+    constexpr int I0p = T::PACK ? T::I / (T::PACK ? S::G : 1) : 1;
     const int nt = tid % M::NT4;
     const int kt = (tid / M::NT4) % M::KT;
     const int mg = tid / M::TILES;
@@ -861,7 +887,7 @@ TTS_DEV void flush_dw(float (&acc)[TK][4], float *__restrict__ stg, float *__res
         t /= T::J;
         const int i = t % T::I;
         const int a = t / T::I;
-        const int col = (k == 0) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
+        const int col = (k == 0 && T::PACK) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
         slot[COff<S, k>::v + e] += stg[(j * T::rn + ap) * T::NS + col];
     }
     __syncthreads();
@@ -944,7 +970,7 @@ struct DwRegs {
     float a3[S::D > 3 ? TB::WTK[S::D > 3 ? 3 : 0] : 1][4];
 };
 
-template <class S, int R, class TB, int k>
+template <class S, int R, class TB, int k, bool WANT_DX = true>
 TTS_DEV void bwd_chain(float *xs, float *hcur, float *dy0, float *dhc, const float *wt, float *xch,
                        DwRegs<S, R, TB> &dw, int tid) {
     using SM = BwdSmem<S, R, TB>;
@@ -956,13 +982,13 @@ TTS_DEV void bwd_chain(float *xs, float *hcur, float *dy0, float *dhc, const flo
     if constexpr (k == 3) bwd_weight_stage<S, 3, R, TB::WTK[3]>(X, dY, dw.a3, tid);
     if constexpr (k == S::D - 1) {
         // last stage: dX goes to the dh slot (no aliasing with X_k); split reduction
-        bwd_data_stage<S, k, R, TB::BTM[k], TB::BSP>(dY, wt + WTOff<S, k>::v, dhc, xch, tid);
+        if constexpr (WANT_DX) bwd_data_stage<S, k, R, TB::BTM[k], TB::BSP>(dY, wt + WTOff<S, k>::v, dhc, xch, tid);
         __syncthreads();
     } else {
         __syncthreads();                                  // X_k is overwritten in place by dX_k
         bwd_data_stage<S, k, R, TB::BTM[k], 1>(dY, wt + WTOff<S, k>::v, X, xch, tid);
         __syncthreads();
-        bwd_chain<S, R, TB, k + 1>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
+        bwd_chain<S, R, TB, k + 1, WANT_DX>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
     }
 }
 
@@ -1210,6 +1236,290 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             slot[core_floats<S>() + GH + col] += g_weff[n][g];
             slot[core_floats<S>() + 2 * GH + col] += g_bih[n][g];
         }
+}
+
+// =============================================================================================
+// Batched TT matvec (ih projection of a time chunk, stand-alone TTLinear) -- static path
+// Shapes have G = 0 (plain stage-0 layout).  Rows are processed in tiles of R; CTAs are persistent.
+// =============================================================================================
+template <class S, int R, int TMr_>
+struct OutMap {
+    using T = St<S, 0>;
+    static_assert(T::r == 1 && (T::N == 4 || T::N == 8), "output stage handles a first mode of 4 or 8");
+    static constexpr int TMr = TMr_, TN = T::N;
+    static constexpr int MTl = T::Mrow / TMr;
+    static_assert(T::Mrow % TMr == 0 && NTHR % MTl == 0 && MTl % 32 == 0, "output stage tile grid");
+    static constexpr int RB = NTHR / MTl;                // groups of threads that split the R batch rows
+    static constexpr int RPT = (R + RB - 1) / RB;        // batch rows per thread
+};
+
+struct TtlFwdSArgs {
+    long long rows;
+    int rows_per_b;
+    long long x_bstride, y_bstride;
+    const float *x, *cores, *bias, *bias2;
+    float *y;
+};
+
+template <class S, int R, class TU>
+struct TtlFwdSmem {
+    static constexpr int W = w_floats<S>();
+    static constexpr int HS = cr4(R * St<S, S::D - 1>::BS);
+    static constexpr int P = PPSlots<S, R>::P, Q = PPSlots<S, R>::Q;
+    static constexpr int TOTAL = W + HS + P + Q;
+    static constexpr size_t BYTES = (size_t)TOTAL * 4;
+};
+
+// rows (global) -> X_{d-1} slot; pad columns of the slot are zeroed once by the caller
+template <class S, int R>
+TTS_DEV void load_rows(const float *__restrict__ x, long long row0, long long rows, int rows_per_b, long long bstride,
+                       float *__restrict__ slot, int tid) {
+    using TL = St<S, S::D - 1>;
+    constexpr int NIN = n_in<S>();
+    for (int e = tid; e < R * NIN; e += NTHR) {
+        const int b = e / NIN, c = e % NIN;
+        const long long row = row0 + b;
+        float v = 0.f;
+        if (row < rows) {
+            const long long bb = row / rows_per_b, tt = row - bb * rows_per_b;
+            v = __ldg(x + bb * bstride + tt * NIN + c);
+        }
+        slot[b * TL::BS + (c / TL::Kraw) * TL::KS + (c % TL::Kraw)] = v;
+    }
+}
+
+template <class S, int R, class TU>
+__global__ void __launch_bounds__(NTHR, 1) k_ttlin_fwd_s(const __grid_constant__ TtlFwdSArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    using SM = TtlFwdSmem<S, R, TU>;
+    using T0 = St<S, 0>;
+    using OM = OutMap<S, R, TU::FTMr>;
+    constexpr int NOUT = n_out<S>();
+    const int tid = threadIdx.x;
+    float *wsm = smem;
+    float *hs = wsm + SM::W;
+    float *P = hs + SM::HS;
+    float *Q = P + SM::P;
+    stage_weights_k<S, 0>(a.cores, wsm, tid);
+    for (int e = tid; e < SM::HS; e += NTHR) hs[e] = 0.f;
+    const int mt = tid % OM::MTl, rb = tid / OM::MTl;
+    // bias of the columns this thread writes: col(j, q) = j*Mrow_0 + q*MTl + mt
+    float bias[OM::TMr][OM::TN];
+#pragma unroll
+    for (int q = 0; q < OM::TMr; ++q)
+#pragma unroll
+        for (int j = 0; j < OM::TN; ++j) {
+            const int col = j * T0::Mrow + q * OM::MTl + mt;
+            bias[q][j] = (a.bias ? __ldg(a.bias + col) : 0.f) + (a.bias2 ? __ldg(a.bias2 + col) : 0.f);
+        }
+    const long long ntiles = (a.rows + R - 1) / R;
+    for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const long long row0 = tile_i * R;
+        __syncthreads();
+        load_rows<S, R>(a.x, row0, a.rows, a.rows_per_b, a.x_bstride, hs, tid);
+        __syncthreads();
+        const float *X0 = fwd_chain_pp<S, R, TU, S::D - 1>(hs, P, Q, wsm, tid);
+        // ---- output stage: thread = (row tile mt, batch-row group rb); lanes run along rows, so every
+        // global store of a warp covers 32 consecutive floats
+        float acc[OM::RPT][OM::TMr][OM::TN];
+#pragma unroll
+        for (int i = 0; i < OM::RPT; ++i)
+#pragma unroll
+            for (int q = 0; q < OM::TMr; ++q)
+#pragma unroll
+                for (int j = 0; j < OM::TN; ++j) acc[i][q][j] = 0.f;
+        const float *xb = X0 + mt * T0::KS;
+        const float *wb = wsm + WOff<S, 0>::v;
+#pragma unroll 2
+        for (int k4 = 0; k4 < T0::K; k4 += 4) {
+            float4 av[OM::RPT][OM::TMr];
+#pragma unroll
+            for (int i = 0; i < OM::RPT; ++i)
+#pragma unroll
+                for (int q = 0; q < OM::TMr; ++q) {
+                    const int b = rb * OM::RPT + i;
+                    av[i][q] = ld4(xb + (b < R ? b : 0) * T0::BS + q * OM::MTl * T0::KS + k4);
+                }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                float w[OM::TN];
+#pragma unroll
+                for (int g = 0; g < OM::TN / 4; ++g) {
+                    const float4 t = ld4(wb + (k4 + kk) * T0::NS + 4 * g);
+                    w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
+                }
+#pragma unroll
+                for (int i = 0; i < OM::RPT; ++i)
+#pragma unroll
+                    for (int q = 0; q < OM::TMr; ++q) {
+                        const float x = kk == 0 ? av[i][q].x : (kk == 1 ? av[i][q].y : (kk == 2 ? av[i][q].z : av[i][q].w));
+#pragma unroll
+                        for (int j = 0; j < OM::TN; ++j) acc[i][q][j] = fmaf(x, w[j], acc[i][q][j]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < OM::RPT; ++i) {
+            const int b = rb * OM::RPT + i;
+            const long long row = row0 + b;
+            if (b < R && row < a.rows) {
+                const long long bb = row / a.rows_per_b, tt = row - bb * a.rows_per_b;
+                float *yr = a.y + bb * a.y_bstride + tt * NOUT;
+#pragma unroll
+                for (int q = 0; q < OM::TMr; ++q)
+#pragma unroll
+                    for (int j = 0; j < OM::TN; ++j) yr[j * T0::Mrow + q * OM::MTl + mt] = acc[i][q][j] + bias[q][j];
+            }
+        }
+    }
+}
+
+// ---- backward of the batched TT matvec ---------------------------------------------------------
+template <bool W, class S, int k, int R, int TM, int SP> struct XchSel { static constexpr int v = 0; };
+template <class S, int k, int R, int TM, int SP> struct XchSel<true, S, k, R, TM, SP> {
+    static constexpr int v = BdMap<S, k, R, TM, SP>::XCH_FLOATS;
+};
+
+struct TtlBwdSArgs {
+    long long rows;
+    int rows_per_b;
+    long long x_bstride, dy_bstride, dx_bstride;
+    const float *x, *cores, *dy;
+    float *dx;               // used only by the WANT_DX instantiation
+    float *partial;          // [gridDim.x][core_floats + n_out]
+    int want_dbias;
+};
+
+template <class S, int R, class TB, bool WANT_DX>
+struct TtlBwdSmem {
+    static constexpr int W = w_floats<S>();
+    static constexpr int WT = wt_floats<S>();
+    static constexpr int stage_bs(int k) {
+        int m = 1;
+        for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
+        for (int q = 0; q < k; ++q) m *= S::J[q];
+        return m * cpad(cr4(S::J[k] * S::RK[k + 1]));
+    }
+    static constexpr int xoff(int k) {
+        int v = 0;
+        for (int q = S::D - 1; q > k; --q) v += cr4(R * stage_bs(q));
+        return v;
+    }
+    template <int k> struct XOff { static constexpr int v = xoff(k); };
+    static constexpr int XALL = xoff(0) + cr4(R * stage_bs(0));
+    static constexpr int DY = cr4(R * DY0<S>::BS);
+    static constexpr int DXS = WANT_DX ? cr4(R * St<S, S::D - 1>::BS) : 0;
+    static constexpr int XCH = XchSel<WANT_DX, S, S::D - 1, R, TB::BTM[S::D - 1], TB::BSP>::v;
+    static constexpr int TOTAL = W + WT + XALL + DY + DXS + XCH;
+    static constexpr size_t BYTES = (size_t)TOTAL * 4;
+};
+
+template <class S, int R, class TB, int k, class SM>
+TTS_DEV void ttl_fwd_keep(float *xs, const float *wsm, int tid) {
+    if constexpr (k >= 1) {
+        using TU = typename TB::F;
+        fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(xs + SM::template XOff<k>::v, wsm + WOff<S, k>::v,
+                                                   xs + SM::template XOff<k - 1>::v, tid);
+        __syncthreads();
+        ttl_fwd_keep<S, R, TB, k - 1, SM>(xs, wsm, tid);
+    }
+}
+
+template <class S, int R, class TB, int k, bool WANT_DX, class SM>
+TTS_DEV void ttl_bwd_chain(float *xs, float *dy0, float *dxs, const float *wt, float *xch, DwRegs<S, R, TB> &dw, int tid) {
+    float *X = xs + SM::template XOff<k>::v;
+    const float *dY = (k == 0) ? dy0 : xs + SM::template XOff<(k == 0 ? 0 : k - 1)>::v;
+    if constexpr (k == 0) bwd_weight_stage<S, 0, R, TB::WTK[0]>(X, dY, dw.a0, tid);
+    if constexpr (k == 1) bwd_weight_stage<S, 1, R, TB::WTK[1]>(X, dY, dw.a1, tid);
+    if constexpr (k == 2) bwd_weight_stage<S, 2, R, TB::WTK[2]>(X, dY, dw.a2, tid);
+    if constexpr (k == 3) bwd_weight_stage<S, 3, R, TB::WTK[3]>(X, dY, dw.a3, tid);
+    if constexpr (k == S::D - 1) {
+        if constexpr (WANT_DX) bwd_data_stage<S, k, R, TB::BTM[k], TB::BSP>(dY, wt + WTOff<S, k>::v, dxs, xch, tid);
+        __syncthreads();
+    } else {
+        __syncthreads();
+        bwd_data_stage<S, k, R, TB::BTM[k], 1>(dY, wt + WTOff<S, k>::v, X, xch, tid);
+        __syncthreads();
+        ttl_bwd_chain<S, R, TB, k + 1, WANT_DX, SM>(xs, dy0, dxs, wt, xch, dw, tid);
+    }
+}
+
+template <class S, int R, class TB, bool WANT_DX>
+__global__ void __launch_bounds__(NTHR, 1) k_ttlin_bwd_s(const __grid_constant__ TtlBwdSArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    using SM = TtlBwdSmem<S, R, TB, WANT_DX>;
+    using T0 = St<S, 0>;
+    using TL = St<S, S::D - 1>;
+    constexpr int NOUT = n_out<S>(), NIN = n_in<S>();
+    static_assert(NOUT % NTHR == 0, "bias-gradient ownership needs n_out to be a multiple of the block size");
+    constexpr int CPT = NOUT / NTHR;                      // output columns owned per thread (bias gradient)
+    const int tid = threadIdx.x;
+    float *wsm = smem;
+    float *wt = wsm + SM::W;
+    float *xs = wt + SM::WT;
+    float *dy0 = xs + SM::XALL;
+    float *dxs = dy0 + SM::DY;
+    float *xch = dxs + SM::DXS;
+    stage_weights_k<S, 0>(a.cores, wsm, tid);
+    stage_weights_t<S, 0>(a.cores, wt, tid);
+    for (int e = tid; e < cr4(R * TL::BS); e += NTHR) xs[SM::template XOff<S::D - 1>::v + e] = 0.f;
+    float dbias[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) dbias[j] = 0.f;
+    DwRegs<S, R, TB> dw;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a0) / 16); ++q) dw.a0[q][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a1) / 16); ++q) dw.a1[q][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a2) / 16); ++q) dw.a2[q][c] = 0.f;
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(dw.a3) / 16); ++q) dw.a3[q][c] = 0.f;
+    }
+    const long long ntiles = (a.rows + R - 1) / R;
+    for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
+        const long long row0 = tile_i * R;
+        __syncthreads();
+        load_rows<S, R>(a.x, row0, a.rows, a.rows_per_b, a.x_bstride, xs + SM::template XOff<S::D - 1>::v, tid);
+        // dy rows -> dY_0 [b][mr][i0]; the thread that reads column c also owns its bias gradient
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const int c = tid + j * NTHR;
+            const int i0 = c / T0::Mrow, mr = c % T0::Mrow;
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                const long long row = row0 + b;
+                float v = 0.f;
+                if (row < a.rows) {
+                    const long long bb = row / a.rows_per_b, tt = row - bb * a.rows_per_b;
+                    v = __ldg(a.dy + bb * a.dy_bstride + tt * NOUT + c);
+                }
+                dy0[b * DY0<S>::BS + mr * DY0<S>::DS + i0] = v;
+                dbias[j] += v;
+            }
+        }
+        __syncthreads();
+        ttl_fwd_keep<S, R, TB, S::D - 1, SM>(xs, wsm, tid);
+        ttl_bwd_chain<S, R, TB, 0, WANT_DX, SM>(xs, dy0, dxs, wt, xch, dw, tid);
+        if constexpr (WANT_DX) {
+            for (int e = tid; e < R * NIN; e += NTHR) {
+                const int b = e / NIN, c = e % NIN;
+                const long long row = row0 + b;
+                if (row < a.rows) {
+                    const long long bb = row / a.rows_per_b, tt = row - bb * a.rows_per_b;
+                    a.dx[bb * a.dx_bstride + tt * NIN + c] = dxs[b * TL::BS + (c / TL::Kraw) * TL::KS + (c % TL::Kraw)];
+                }
+            }
+        }
+    }
+    float *slot = a.partial + (long long)blockIdx.x * (core_floats<S>() + NOUT);
+    flush_all<S, R, TB, 0>(dw, xs, slot, tid);
+    if (a.want_dbias) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) slot[core_floats<S>() + tid + j * NTHR] += dbias[j];
+    }
 }
 
 }  // namespace tts

@@ -6,6 +6,8 @@
 namespace tts {
 struct RnnFwdSArgs;
 struct RnnBwdSArgs;
+struct TtlFwdSArgs;
+struct TtlBwdSArgs;
 }
 
 struct TtsRnnFwdEntry {
@@ -30,3 +32,22 @@ struct TtsRnnBwdEntry {
     int (*prepare)(int *max_blocks_per_sm);
 };
 const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms);
+
+struct TtsTtlFwdEntry {
+    const char *name;
+    int R;
+    size_t smem;
+    bool (*match)(const ttrnn_tt_shape *s);
+    int (*launch)(const tts::TtlFwdSArgs *args, int grid, cudaStream_t st);
+    int (*prepare)(int *max_blocks_per_sm);
+};
+struct TtsTtlBwdEntry {
+    const char *name;
+    int R, want_dx;
+    size_t smem;
+    bool (*match)(const ttrnn_tt_shape *s);
+    int (*launch)(const tts::TtlBwdSArgs *args, int grid, cudaStream_t st);
+    int (*prepare)(int *max_blocks_per_sm);
+};
+const TtsTtlFwdEntry *tts_find_ttl_fwd(const ttrnn_tt_shape *s, long long rows);
+const TtsTtlBwdEntry *tts_find_ttl_bwd(const ttrnn_tt_shape *s, long long rows, int want_dx);

@@ -21,6 +21,13 @@ TTS_SHAPE(HH_H1024_d4r8_lstm, 4, 4, ARR(J, 4, 4, 8, 8) ARR(I, 8, 8, 8, 8) ARR(RK
 
 constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
 
+// input-to-hidden chains (G = 0: plain stage-0 layout); a last in-mode of 5 is zero-padded to 8
+TTS_SHAPE(IH_40_H256_d3r8, 3, 0, ARR(J, 2, 4, 5) ARR(I, 8, 8, 16) ARR(RK, 1, 8, 8, 1))
+TTS_SHAPE(IH_256_H256_d3r8, 3, 0, ARR(J, 4, 8, 8) ARR(I, 8, 8, 16) ARR(RK, 1, 8, 8, 1))
+TTS_SHAPE(IH_256_H1024_d4r8, 4, 0, ARR(J, 4, 4, 4, 4) ARR(I, 8, 8, 8, 8) ARR(RK, 1, 8, 8, 8, 1))
+TTS_SHAPE(IH_40_H256_d4r16, 4, 0, ARR(J, 2, 2, 2, 5) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
+TTS_SHAPE(IH_256_H256_d4r16, 4, 0, ARR(J, 4, 4, 4, 4) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
+
 template <class S>
 bool match_shape(const ttrnn_tt_shape *s) {
     if (s->d != S::D) return false;
@@ -104,7 +111,72 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
 };
 
+
+// ---- batched TT matvec ---------------------------------------------------------------------------
+template <class S, int R, class TU>
+int launch_tf(const tts::TtlFwdSArgs *a, int grid, cudaStream_t st) {
+    tts::k_ttlin_fwd_s<S, R, TU><<<grid, tts::NTHR, tts::TtlFwdSmem<S, R, TU>::BYTES, st>>>(*a);
+    return (int)cudaGetLastError();
+}
+template <class S, int R, class TU>
+int prepare_tf(int *occ) {
+    auto k = tts::k_ttlin_fwd_s<S, R, TU>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::TtlFwdSmem<S, R, TU>::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::TtlFwdSmem<S, R, TU>::BYTES);
+}
+template <class S, int R, class TB, bool DX>
+int launch_tb(const tts::TtlBwdSArgs *a, int grid, cudaStream_t st) {
+    tts::k_ttlin_bwd_s<S, R, TB, DX><<<grid, tts::NTHR, tts::TtlBwdSmem<S, R, TB, DX>::BYTES, st>>>(*a);
+    return (int)cudaGetLastError();
+}
+template <class S, int R, class TB, bool DX>
+int prepare_tb(int *occ) {
+    auto k = tts::k_ttlin_bwd_s<S, R, TB, DX>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::TtlBwdSmem<S, R, TB, DX>::BYTES);
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::TtlBwdSmem<S, R, TB, DX>::BYTES);
+}
+#define TTS_TF(S, R, ...) \
+    {#S, R, tts::TtlFwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>, &launch_tf<S, R, __VA_ARGS__>, &prepare_tf<S, R, __VA_ARGS__>}
+#define TTS_TB(S, R, DX, ...) \
+    {#S, R, DX, tts::TtlBwdSmem<S, R, __VA_ARGS__, DX>::BYTES, &match_shape<S>, &launch_tb<S, R, __VA_ARGS__, DX>, &prepare_tb<S, R, __VA_ARGS__, DX>}
+
+using TU_ih40_d3 = Tune<1, 1, 1, 1, 8, 1, 4>;
+using TU_ih256_d3 = Tune<1, 1, 1, 1, 8, 1, 8>;
+using TU_ih256_d4r8 = Tune<2, 1, 1, 8, 8, 4, 8, 2, 8>;
+using TU_ih40_d4r16 = Tune<1, 1, 1, 4, 8, 2, 8, 1, 4>;
+using TU_ih256_d4r16 = Tune<1, 1, 1, 8, 8, 8, 8, 4, 8>;
+const TtsTtlFwdEntry kTtlFwd[] = {
+    TTS_TF(IH_40_H256_d3r8, 8, TU_ih40_d3),
+    TTS_TF(IH_256_H256_d3r8, 8, TU_ih256_d3),
+    TTS_TF(IH_256_H1024_d4r8, 1, TU_ih256_d4r8),
+    TTS_TF(IH_40_H256_d4r16, 2, TU_ih40_d4r16),
+    TTS_TF(IH_256_H256_d4r16, 1, TU_ih256_d4r16),
+};
+using TBI_ih40_d3 = TuneB<TU_ih40_d3, 1, 1, 1, 1, 8, 4, 8, 8, 4>;
+using TBI_ih256_d3 = TuneB<TU_ih256_d3, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+using TBI_ih256_d4r8 = TuneB<TU_ih256_d4r8, 8, 4, 2, 1, 4, 4, 8, 8, 4>;
+const TtsTtlBwdEntry kTtlBwd[] = {
+    TTS_TB(IH_40_H256_d3r8, 4, false, TBI_ih40_d3),
+    TTS_TB(IH_256_H256_d3r8, 3, true, TBI_ih256_d3),
+    TTS_TB(IH_256_H1024_d4r8, 1, false, TBI_ih256_d4r8),
+};
+
 }  // namespace
+
+const TtsTtlFwdEntry *tts_find_ttl_fwd(const ttrnn_tt_shape *s, long long rows) {
+    if (rows < 64) return nullptr;                  // tiny calls (rank-one helper rows) stay on the generic kernel
+    for (const auto &e : kTtlFwd)
+        if (e.match(s) && e.smem <= kMaxSmem) return &e;
+    return nullptr;
+}
+const TtsTtlBwdEntry *tts_find_ttl_bwd(const ttrnn_tt_shape *s, long long rows, int want_dx) {
+    if (rows < 64) return nullptr;
+    for (const auto &e : kTtlBwd)
+        if (e.match(s) && e.smem <= kMaxSmem && e.want_dx == (want_dx ? 1 : 0)) return &e;
+    return nullptr;
+}
 
 const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms) {
     const TtsRnnBwdEntry *best = nullptr;

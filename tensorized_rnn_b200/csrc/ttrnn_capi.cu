@@ -325,7 +325,28 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
 // ---- launch helpers ------------------------------------------------------------------------
 int launch_ttlinear_fwd(const ChainPlan &p, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
                         long long x_bstride, const float *cores, const float *bias, const float *bias2, float *y,
-                        long long y_bstride, cudaStream_t st) {
+                        long long y_bstride, cudaStream_t st, const ttrnn_tt_shape *shape = nullptr) {
+    if (shape && g_opt_static.load()) {
+        if (const TtsTtlFwdEntry *e = tts_find_ttl_fwd(shape, rows)) {
+            int occ = 0;
+            int rc = e->prepare(&occ);
+            if (rc || occ < 1) return fail("static kernel %s cannot be configured (cuda error %d)", e->name, rc);
+            long long g = (long long)occ * dv.sms;
+            const long long tiles = (rows + e->R - 1) / e->R;
+            if (g > tiles) g = tiles;
+            tts::TtlFwdSArgs sa;
+            memset(&sa, 0, sizeof sa);
+            sa.rows = rows; sa.rows_per_b = rows_per_b; sa.x_bstride = x_bstride; sa.y_bstride = y_bstride;
+            sa.x = x; sa.cores = cores; sa.bias = bias; sa.bias2 = bias2; sa.y = y;
+            {
+                KernelTimer tm(TTRNN_K_TTLINEAR_FWD, st);
+                rc = e->launch(&sa, (int)g, st);
+            }
+            ++g_launches;
+            if (rc) return fail("static kernel %s launch failed: %s", e->name, cudaGetErrorString((cudaError_t)rc));
+            return 0;
+        }
+    }
     TTLinFwdArgs a;
     memset(&a, 0, sizeof a);
     a.p = p;
@@ -352,7 +373,31 @@ int launch_ttlinear_fwd(const ChainPlan &p, const DevInfo &dv, long long rows, i
 int launch_ttlinear_bwd(const ChainPlan &p0, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
                         long long x_bstride, const float *cores, const float *dy, long long dy_bstride, float *dx,
                         long long dx_bstride, float *partial, int nslots, float *spill, int want_dbias,
-                        cudaStream_t st, int *slots_used) {
+                        cudaStream_t st, int *slots_used, const ttrnn_tt_shape *shape = nullptr) {
+    if (shape && g_opt_static.load()) {
+        if (const TtsTtlBwdEntry *e = tts_find_ttl_bwd(shape, rows, dx != nullptr)) {
+            int occ = 0;
+            int rc = e->prepare(&occ);
+            if (rc || occ < 1) return fail("static kernel %s cannot be configured (cuda error %d)", e->name, rc);
+            long long g = (long long)occ * dv.sms;
+            const long long tiles = (rows + e->R - 1) / e->R;
+            if (g > tiles) g = tiles;
+            if (g > nslots) g = nslots;
+            tts::TtlBwdSArgs sa;
+            memset(&sa, 0, sizeof sa);
+            sa.rows = rows; sa.rows_per_b = rows_per_b;
+            sa.x_bstride = x_bstride; sa.dy_bstride = dy_bstride; sa.dx_bstride = dx_bstride;
+            sa.x = x; sa.cores = cores; sa.dy = dy; sa.dx = dx; sa.partial = partial; sa.want_dbias = want_dbias;
+            {
+                KernelTimer tm(TTRNN_K_TTLINEAR_BWD, st);
+                rc = e->launch(&sa, (int)g, st);
+            }
+            ++g_launches;
+            if (rc) return fail("static kernel %s launch failed: %s", e->name, cudaGetErrorString((cudaError_t)rc));
+            if (slots_used && (int)g > *slots_used) *slots_used = (int)g;
+            return 0;
+        }
+    }
     BwdCfg c;
     if (plan_bwd(p0, [&](int r) { return smem_ttlin_bwd_fixed(p0, r); }, dv, rows, &c, "TT matvec backward")) return 1;
     TTLinBwdArgs a;
@@ -529,7 +574,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
                 if (mode == tts::MODE_XG) {
                     if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                             params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg,
-                                            (long long)tc * GH, st))
+                                            (long long)tc * GH, st, &d->ih[l]))
                         return 1;
                     sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
                 } else {
@@ -574,7 +619,8 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
             const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
             // (1) batched ih projection of the chunk: xg[b, t, :] = W_ih x[b, t0+t, :] + b_ih (+ b_hh for LSTM)
             if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st))
+                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
+                                    &d->ih[l]))
                 return 1;
             // (2) persistent recurrence over the chunk
             const bool first = (t0 == 0), last = (t0 + tc == T);
@@ -684,7 +730,8 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
                     const bool last = (t0 + tc == T);
                     if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                            params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st))
+                                            params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
+                                            &d->ih[l]))
                         return 1;
                     sa.t0 = t0; sa.steps = tc;
                     sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
@@ -700,7 +747,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                             params + lp.off_ih_cores, xg, (long long)tc * GH,
                                             dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
-                                            lo.nslots, sc + lo.b_spill, 1, st, &ih_used))
+                                            lo.nslots, sc + lo.b_spill, 1, st, &ih_used, &d->ih[l]))
                         return 1;
                 }
             }
@@ -765,7 +812,8 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             const bool last = (t0 + tc == T);
             // (1) recompute the ih projection of the chunk
             if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st))
+                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
+                                    &d->ih[l]))
                 return 1;
             // (2) reverse-time recurrence: xg <- delta_ih, hh core grads, dh/dc carried across chunks
             a.t0 = t0; a.steps = tc;
@@ -783,7 +831,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                     params + lp.off_ih_cores, xg, (long long)tc * GH,
                                     dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
-                                    lo.nslots, sc + lo.b_spill, 1, st, &ih_slots_used))
+                                    lo.nslots, sc + lo.b_spill, 1, st, &ih_slots_used, &d->ih[l]))
                 return 1;
         }
         // (4) fold the per-CTA partials into the gradient blob
@@ -832,7 +880,7 @@ int ttrnn_ttlinear_forward(const ttrnn_tt_shape *shape, int64_t rows, const floa
     DevInfo dv;
     if (get_dev(&dv)) return 1;
     if (rows > 0x7fffffffLL) return fail("rows too large");
-    return launch_ttlinear_fwd(p, dv, rows, (int)rows, x, 0, cores, bias, nullptr, y, 0, (cudaStream_t)stream);
+    return launch_ttlinear_fwd(p, dv, rows, (int)rows, x, 0, cores, bias, nullptr, y, 0, (cudaStream_t)stream, shape);
 }
 
 int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const float *x, const float *cores,
@@ -851,7 +899,7 @@ int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const flo
     int used = 0;
     float *spill = part + r4(slot) * nslots;
     if (launch_ttlinear_bwd(p, dv, rows, (int)rows, x, 0, cores, dy, 0, d_x, 0, part, nslots, spill,
-                            d_bias != nullptr, st, &used))
+                            d_bias != nullptr, st, &used, shape))
         return 1;
     if (reduce_partials(part, used, slot, 0, p.core_floats, d_cores, st)) return 1;
     if (d_bias && reduce_partials(part, used, slot, p.core_floats, p.n_out, d_bias, st)) return 1;
