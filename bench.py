@@ -239,6 +239,7 @@ def main():
     # ---------------- our arm -----------------------------------------------------------------
     import tensorized_rnn_b200 as tr
     from tensorized_rnn_b200 import _lib
+    from tensorized_rnn_b200.dist import allreduce_gradients
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
@@ -283,13 +284,7 @@ def main():
             loss.backward()
             result = loss
         if dist is not None:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)                       # one flat NCCL all-reduce of every TT-core / bias gradient
-            off = 0
-            for p in params:
-                n = p.numel()
-                p.grad.copy_(flat[off:off + n].view_as(p.grad))
-                off += n
+            allreduce_gradients(params)                 # one flat NCCL all-reduce of every TT-core / bias gradient
         return result
 
     def barrier():
