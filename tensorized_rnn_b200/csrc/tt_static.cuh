@@ -647,7 +647,7 @@ TTS_DEV void stage_weights_t(const float *__restrict__ cores, float *__restrict_
 // ---------------------------------------------------------------------------------------------
 template <class S> struct DY0 {
     using T = St<S, 0>;
-    static constexpr int DS = cpad(T::NW);                   // row stride
+    static constexpr int DS = T::PACK ? cpad(T::NW) : T::NW; // row stride (plain chains: unpadded, saves shared memory)
     static constexpr int BS = T::Mrow * DS;                  // per batch row
 };
 
@@ -903,27 +903,35 @@ struct TuneB {
     static constexpr int WTK[4] = {WTK0, WTK1, WTK2, WTK3};
 };
 
-template <class S, int R, class TB>
+// DWI = true : every X_k kept, core gradients accumulated in the recurrent kernel ("fused" backward)
+// DWI = false: X_k slots ping-pong like the forward kernel; the kernel only propagates dh/dc and writes
+//              delta; the core gradients come from a batched TT-matvec backward over (h_{t-1}, delta)
+//              ("split" backward, for chains whose kept slots exceed shared memory)
+template <class S, int R, class TB, bool DWI = true>
 struct BwdSmem {
     static constexpr int D = S::D;
     using TU = typename TB::F;
     using FM = FinMap<S, R, TU::FTMr, TU::FTI, TU::FSK>;
     static constexpr int W = w_floats<S>();
     static constexpr int WT = wt_floats<S>();
-    // every X_k kept: offsets from the start of the slot area (X_{d-1} first)
     static constexpr int stage_bs(int k) {
         int m = 1;
         for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
         for (int q = 0; q < k; ++q) m *= S::J[q];
-        return m * cpad(S::J[k] * S::RK[k + 1]);
+        return m * cpad(cr4(S::J[k] * S::RK[k + 1]));
     }
+    static constexpr int HS0 = cr4(R * stage_bs(S::D - 1));
     static constexpr int xoff(int k) {
-        int v = 0;
-        for (int q = S::D - 1; q > k; --q) v += cr4(R * stage_bs(q));
-        return v;
+        if (DWI) {
+            int v = 0;
+            for (int q = S::D - 1; q > k; --q) v += cr4(R * stage_bs(q));
+            return v;
+        }
+        if (k == S::D - 1) return 0;
+        return HS0 + (((S::D - 2 - k) % 2 == 0) ? 0 : PPSlots<S, R>::P);
     }
     template <int k> struct XOff { static constexpr int v = xoff(k); };
-    static constexpr int XALL = xoff(0) + cr4(R * stage_bs(0));
+    static constexpr int XALL = DWI ? xoff(0) + cr4(R * stage_bs(0)) : HS0 + PPSlots<S, R>::P + PPSlots<S, R>::Q;
     static constexpr int DY = cr4(R * DY0<S>::BS);
     static constexpr int DHC = cr4(R * St<S, D - 1>::BS);
     static constexpr int XCH = cmax(FM::XCH_FLOATS, BdMap<S, D - 1, R, TB::BTM[D - 1], TB::BSP>::XCH_FLOATS);
@@ -949,15 +957,15 @@ struct RnnBwdSArgs {
     float *partial;          // [gridDim.x][core_floats + 3*G*H]: cores, db_hh, d_weff, db_ih  (+= at the end)
 };
 
-template <class S, int R, class TB, int k>
+template <class S, int R, class TB, int k, bool DWI = true>
 TTS_DEV void fwd_chain_keep(float *xs, const float *hcur, const float *wsm, int tid) {
     if constexpr (k >= 1) {
-        using SM = BwdSmem<S, R, TB>;
+        using SM = BwdSmem<S, R, TB, DWI>;
         using TU = typename TB::F;
         const float *X = (k == S::D - 1) ? hcur : xs + SM::template XOff<k>::v;
         fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(X, wsm + WOff<S, k>::v, xs + SM::template XOff<k - 1>::v, tid);
         __syncthreads();
-        fwd_chain_keep<S, R, TB, k - 1>(xs, hcur, wsm, tid);
+        fwd_chain_keep<S, R, TB, k - 1, DWI>(xs, hcur, wsm, tid);
     }
 }
 
@@ -970,25 +978,25 @@ struct DwRegs {
     float a3[S::D > 3 ? TB::WTK[S::D > 3 ? 3 : 0] : 1][4];
 };
 
-template <class S, int R, class TB, int k, bool WANT_DX = true>
+template <class S, int R, class TB, int k, bool WANT_DX = true, bool DWI = true>
 TTS_DEV void bwd_chain(float *xs, float *hcur, float *dy0, float *dhc, const float *wt, float *xch,
                        DwRegs<S, R, TB> &dw, int tid) {
-    using SM = BwdSmem<S, R, TB>;
+    using SM = BwdSmem<S, R, TB, DWI>;
     float *X = (k == S::D - 1) ? hcur : xs + SM::template XOff<k>::v;
     const float *dY = (k == 0) ? dy0 : xs + SM::template XOff<(k == 0 ? 0 : k - 1)>::v;
-    if constexpr (k == 0) bwd_weight_stage<S, 0, R, TB::WTK[0]>(X, dY, dw.a0, tid);
-    if constexpr (k == 1) bwd_weight_stage<S, 1, R, TB::WTK[1]>(X, dY, dw.a1, tid);
-    if constexpr (k == 2) bwd_weight_stage<S, 2, R, TB::WTK[2]>(X, dY, dw.a2, tid);
-    if constexpr (k == 3) bwd_weight_stage<S, 3, R, TB::WTK[3]>(X, dY, dw.a3, tid);
+    if constexpr (DWI && k == 0) bwd_weight_stage<S, 0, R, TB::WTK[0]>(X, dY, dw.a0, tid);
+    if constexpr (DWI && k == 1) bwd_weight_stage<S, 1, R, TB::WTK[1]>(X, dY, dw.a1, tid);
+    if constexpr (DWI && k == 2) bwd_weight_stage<S, 2, R, TB::WTK[2]>(X, dY, dw.a2, tid);
+    if constexpr (DWI && k == 3) bwd_weight_stage<S, 3, R, TB::WTK[3]>(X, dY, dw.a3, tid);
     if constexpr (k == S::D - 1) {
         // last stage: dX goes to the dh slot (no aliasing with X_k); split reduction
         if constexpr (WANT_DX) bwd_data_stage<S, k, R, TB::BTM[k], TB::BSP>(dY, wt + WTOff<S, k>::v, dhc, xch, tid);
         __syncthreads();
     } else {
-        __syncthreads();                                  // X_k is overwritten in place by dX_k
+        if constexpr (DWI) __syncthreads();               // X_k is overwritten in place by dX_k
         bwd_data_stage<S, k, R, TB::BTM[k], 1>(dY, wt + WTOff<S, k>::v, X, xch, tid);
         __syncthreads();
-        bwd_chain<S, R, TB, k + 1, WANT_DX>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
+        bwd_chain<S, R, TB, k + 1, WANT_DX, DWI>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
     }
 }
 
@@ -1001,10 +1009,12 @@ TTS_DEV void flush_all(DwRegs<S, R, TB> &dw, float *stg, float *slot, int tid) {
     if constexpr (k + 1 < S::D) flush_all<S, R, TB, k + 1>(dw, stg, slot, tid);
 }
 
-template <class S, int CELL, int R, int MODE, class TB>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI = true>
 __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
     extern __shared__ __align__(16) float smem[];
-    using SM = BwdSmem<S, R, TB>;
+    using SM = BwdSmem<S, R, TB, DWI>;
+    static_assert(DWI || (CELL == TTRNN_CELL_LSTM && MODE == MODE_XG),
+                  "split backward: delta_hh must equal delta_ih (LSTM) and be written to the xg buffer");
     using FM = typename SM::FM;
     using TL = St<S, S::D - 1>;
     using T0 = St<S, 0>;
@@ -1137,7 +1147,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 fetch_regs(t - 1);
             }
             // ---- recompute the hh chain keeping every X_k
-            fwd_chain_keep<S, R, TB, S::D - 1>(xs, hcur, wsm, tid);
+            fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
             float pre[R][NE][4];
             {
                 float acc[R][FM::TMr][FM::TI][4];
@@ -1210,7 +1220,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 }
             __syncthreads();
             // ---- backward chain: core gradients (register tiles) and dh_{t-1}
-            bwd_chain<S, R, TB, 0>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
+            bwd_chain<S, R, TB, 0, true, DWI>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
             cp_async_wait_all();
         }
         __syncthreads();
@@ -1225,8 +1235,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 }
     }
     // ---- flush gradients of this CTA into its slot
+    if (!a.partial) return;
     float *slot = a.partial + (long long)blockIdx.x * (core_floats<S>() + 3 * GH);
-    flush_all<S, R, TB, 0>(dw, xs, slot, tid);
+    if constexpr (DWI) flush_all<S, R, TB, 0>(dw, xs, slot, tid);
 #pragma unroll
     for (int n = 0; n < NE; ++n)
 #pragma unroll

@@ -25,6 +25,7 @@ const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int m
 struct TtsRnnBwdEntry {
     const char *name;
     int cell, mode, R;
+    int split;                                                               // 1: core gradients come from a batched kernel
     size_t smem;
     long long slot_floats;                                                   // floats per gradient slot
     bool (*match)(const ttrnn_tt_shape *hh);

@@ -25,6 +25,7 @@ constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
 TTS_SHAPE(IH_40_H256_d3r8, 3, 0, ARR(J, 2, 4, 5) ARR(I, 8, 8, 16) ARR(RK, 1, 8, 8, 1))
 TTS_SHAPE(IH_256_H256_d3r8, 3, 0, ARR(J, 4, 8, 8) ARR(I, 8, 8, 16) ARR(RK, 1, 8, 8, 1))
 TTS_SHAPE(IH_256_H1024_d4r8, 4, 0, ARR(J, 4, 4, 4, 4) ARR(I, 8, 8, 8, 8) ARR(RK, 1, 8, 8, 8, 1))
+TTS_SHAPE(HHW_H1024_d4r8, 4, 0, ARR(J, 4, 4, 8, 8) ARR(I, 8, 8, 8, 8) ARR(RK, 1, 8, 8, 8, 1))
 TTS_SHAPE(IH_40_H256_d4r16, 4, 0, ARR(J, 2, 2, 2, 5) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
 TTS_SHAPE(IH_256_H256_d4r16, 4, 0, ARR(J, 4, 4, 4, 4) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
 
@@ -72,24 +73,28 @@ const TtsRnnFwdEntry kFwd[] = {
 };
 
 
-template <class S, int CELL, int R, int MODE, class TB>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI>
 int launch_bwd(const tts::RnnBwdSArgs *a, int grid, cudaStream_t st) {
-    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB>::BYTES, st>>>(*a);
+    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
-template <class S, int CELL, int R, int MODE, class TB>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI>
 int prepare_bwd(int *occ) {
-    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB>::BYTES);
+    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB, DWI>::BYTES);
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB>::BYTES);
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES);
 }
 template <class S>
 constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * tts::n_in<S>(); }
 
 #define TTS_BWD(S, CELL, R, MODE, ...)                                                                      \
-    {#S, CELL, MODE, R, tts::BwdSmem<S, R, __VA_ARGS__>::BYTES, slot_floats<S>(), &match_shape<S>,           \
-     &launch_bwd<S, CELL, R, MODE, __VA_ARGS__>, &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__>}
+    {#S, CELL, MODE, R, 0, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(), &match_shape<S>,  \
+     &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true>, &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true>}
+#define TTS_BWD_SPLIT(S, CELL, R, MODE, ...)                                                                \
+    {#S "(split)", CELL, MODE, R, 1, tts::BwdSmem<S, R, __VA_ARGS__, false>::BYTES, slot_floats<S>(),        \
+     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false>,                                     \
+     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, false>}
 
 // TuneB<forward Tune, BTM0..3 (rows per thread of bwd-data stage k), BSP (split of the last bwd-data
 // stage), WTK0..3 (kappa rows of the register tile of bwd-weight stage k)>
@@ -97,6 +102,8 @@ using tts::TuneB;
 using TB_d2 = TuneB<Tune<1, 2, 2, 1, 8>, 1, 1, 1, 1, 8, 8, 8, 8, 8>;
 using TB_d3_R5 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
 using TB_d3_R2 = TuneB<Tune<1, 1, 1, 2, 8, 2, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+// cfg5: split backward (recurrent kernel propagates dh/dc only); last bwd-data stage split 4 ways
+using TB_h1024_split = TuneB<Tune<8, 1, 2, 8, 8, 4, 8, 4, 8>, 8, 4, 4, 2, 4, 4, 4, 4, 4>;
 using TB_d3_R3 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
 const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
@@ -109,6 +116,7 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, TB_d2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
+    TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),
 };
 
 
@@ -144,23 +152,26 @@ int prepare_tb(int *occ) {
 
 using TU_ih40_d3 = Tune<1, 1, 1, 1, 8, 1, 4>;
 using TU_ih256_d3 = Tune<1, 1, 1, 1, 8, 1, 8>;
+using TU_ih256_d3_R4 = Tune<1, 1, 1, 2, 8, 2, 8>;
 using TU_ih256_d4r8 = Tune<2, 1, 1, 8, 8, 4, 8, 2, 8>;
 using TU_ih40_d4r16 = Tune<1, 1, 1, 4, 8, 2, 8, 1, 4>;
 using TU_ih256_d4r16 = Tune<1, 1, 1, 8, 8, 8, 8, 4, 8>;
 const TtsTtlFwdEntry kTtlFwd[] = {
     TTS_TF(IH_40_H256_d3r8, 8, TU_ih40_d3),
-    TTS_TF(IH_256_H256_d3r8, 8, TU_ih256_d3),
+    TTS_TF(IH_256_H256_d3r8, 4, TU_ih256_d3_R4),
     TTS_TF(IH_256_H1024_d4r8, 1, TU_ih256_d4r8),
     TTS_TF(IH_40_H256_d4r16, 2, TU_ih40_d4r16),
     TTS_TF(IH_256_H256_d4r16, 1, TU_ih256_d4r16),
 };
 using TBI_ih40_d3 = TuneB<TU_ih40_d3, 1, 1, 1, 1, 8, 4, 8, 8, 4>;
 using TBI_ih256_d3 = TuneB<TU_ih256_d3, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+using TBI_hhw_h1024 = TuneB<Tune<1, 1, 1, 8, 8, 4, 8, 4, 8>, 8, 4, 4, 1, 4, 4, 4, 8, 4>;
 using TBI_ih256_d4r8 = TuneB<TU_ih256_d4r8, 8, 4, 2, 1, 4, 4, 8, 8, 4>;
 const TtsTtlBwdEntry kTtlBwd[] = {
     TTS_TB(IH_40_H256_d3r8, 4, false, TBI_ih40_d3),
     TTS_TB(IH_256_H256_d3r8, 3, true, TBI_ih256_d3),
     TTS_TB(IH_256_H1024_d4r8, 1, false, TBI_ih256_d4r8),
+    TTS_TB(HHW_H1024_d4r8, 1, false, TBI_hhw_h1024),
 };
 
 }  // namespace

@@ -693,14 +693,16 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             const long long slot = be->slot_floats;
             if (slot > lo.part_stride) return fail("internal: gradient slot too small");
             const long long ih_slot = lp.ih.core_floats + GH;
-            CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)slot * sgrid * 4, st));
+            const long long hhw_slot = lp.hh.core_floats + GH;       // slot layout of the batched hh-dW kernel (split mode)
+            int hh_used = 0;
+            CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)(be->split ? hhw_slot * lo.nslots : slot * sgrid) * 4, st));
             CU_CHECK(cudaMemsetAsync(part_ih, 0, (size_t)ih_slot * lo.nslots * 4, st));
             tts::RnnBwdSArgs sa;
             memset(&sa, 0, sizeof sa);
             sa.B = B; sa.T = T;
             sa.cores = params + lp.off_hh_cores;
             sa.hs = lout; sa.cs = lcs; sa.h0 = h0; sa.c0 = c0; sa.dhs = dhs;
-            sa.partial = part_hh;
+            sa.partial = be->split ? nullptr : part_hh;
             float *aux = sc + lo.b_aux;
             float *aux_g = aux + r4(GH);
             float *one = aux_g + r4(GH);
@@ -744,6 +746,20 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     }
                     ++g_launches;
                     if (rc) return fail("static kernel %s launch failed: %s", be->name, cudaGetErrorString((cudaError_t)rc));
+                    if (be->split) {
+                        // hh core gradients: batched TT-matvec backward over rows (h_{t-1}, delta_t) of this chunk
+                        auto hh_dw = [&](const float *xp, long long xbs, const float *dyp, long long rows, int rpb) {
+                            return launch_ttlinear_bwd(lp.hh, dv, rows, rpb, xp, xbs, params + lp.off_hh_cores, dyp,
+                                                       (long long)tc * GH, nullptr, 0, part_hh, lo.nslots,
+                                                       sc + lo.b_spill, 0, st, &hh_used, &d->hh[l]);
+                        };
+                        if (t0 > 0) {
+                            if (hh_dw(lout + (long long)(t0 - 1) * H, (long long)T * H, xg, B * tc, tc)) return 1;
+                        } else {
+                            if (tc > 1 && hh_dw(lout, (long long)T * H, xg + GH, B * (tc - 1), tc - 1)) return 1;
+                            if (h0 && hh_dw(h0, H, xg, B, 1)) return 1;
+                        }
+                    }
                     if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                             params + lp.off_ih_cores, xg, (long long)tc * GH,
                                             dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
@@ -753,7 +769,11 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             }
             // fold the per-CTA slots into the gradient blob
             const long long cf = lp.hh.core_floats;
-            if (reduce_partials(part_hh, sgrid, slot, 0, (int)cf, d_params + lp.off_hh_cores, st)) return 1;
+            if (be->split) {
+                if (reduce_partials(part_hh, hh_used, hhw_slot, 0, (int)cf, d_params + lp.off_hh_cores, st)) return 1;
+            } else if (reduce_partials(part_hh, sgrid, slot, 0, (int)cf, d_params + lp.off_hh_cores, st)) {
+                return 1;
+            }
             if (mode == tts::MODE_RANK1) {
                 if (d->has_bias) {
                     if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, st)) return 1;
