@@ -35,6 +35,22 @@ TTS_DEV void cp_async16(float *smem_dst, const float *gsrc) {
 }
 TTS_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// Packed FP32x2 FMA (Blackwell FFMA2): c.lo += a*w.lo, c.hi += a*w.hi with a scalar `a` operand.  Same FLOP
+// rate as FFMA (measured 74.1 vs 72.5 TFLOP/s, tools/ffma2_probe.cu) for half the issue slots, which is what
+// these LDS-fed register-tile loops are short of.
+typedef unsigned long long f32x2;
+TTS_DEV f32x2 pk2(float lo, float hi) {
+    f32x2 v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+TTS_DEV void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+TTS_DEV void ffma2(f32x2 &c, float a, f32x2 w) {
+    f32x2 aa;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(aa), "l"(w));
+}
+
 TTS_DEV float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 TTS_DEV void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
@@ -156,57 +172,40 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
         const int tn = (wv % M::WX) * M::LX + L::x(lane);
         const int mt = (wv / M::WX) * M::LY + L::y(lane);
         if (M::TT < NTHR && mt >= M::MTl) break;
-        float acc[R][TMr][TN];
+        f32x2 acc2[R][TMr][TN / 2];
 #pragma unroll
         for (int b = 0; b < R; ++b)
 #pragma unroll
             for (int q = 0; q < TMr; ++q)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[b][q][j] = 0.f;
+                for (int j = 0; j < TN / 2; ++j) acc2[b][q][j] = 0ull;
         const float *xb = X + mt * T::KS;
         const float *wb = W + tn * 4;
-        // software pipeline: the A fragment of the next 4 kappas and the W fragment of the next kappa
-        // are requested before the FMAs of the current ones
-        float4 a[R][TMr], an[R][TMr];
-        float4 wc[NG], wn[NG];
-#pragma unroll
-        for (int b = 0; b < R; ++b)
-#pragma unroll
-            for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS);
-#pragma unroll
-        for (int g = 0; g < NG; ++g) wc[g] = ld4(wb + g * GSTR);
 #pragma unroll 2
         for (int k4 = 0; k4 < T::K; k4 += 4) {
-            if (k4 + 4 < T::K) {
+            float4 a[R][TMr];
 #pragma unroll
-                for (int b = 0; b < R; ++b)
+            for (int b = 0; b < R; ++b)
 #pragma unroll
-                    for (int q = 0; q < TMr; ++q) an[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS + k4 + 4);
-            }
+                for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                if (k4 + kk + 1 < T::K) {
+                f32x2 w2[TN / 2];
 #pragma unroll
-                    for (int g = 0; g < NG; ++g) wn[g] = ld4(wb + (k4 + kk + 1) * T::NS + g * GSTR);
+                for (int g = 0; g < NG; ++g) {
+                    const float4 t = ld4(wb + (k4 + kk) * T::NS + g * GSTR);
+                    w2[2 * g] = pk2(t.x, t.y);
+                    w2[2 * g + 1] = pk2(t.z, t.w);
                 }
-                float w[TN];
-#pragma unroll
-                for (int g = 0; g < NG; ++g) { w[4 * g] = wc[g].x; w[4 * g + 1] = wc[g].y; w[4 * g + 2] = wc[g].z; w[4 * g + 3] = wc[g].w; }
 #pragma unroll
                 for (int b = 0; b < R; ++b)
 #pragma unroll
                     for (int q = 0; q < TMr; ++q) {
                         const float av = kk == 0 ? a[b][q].x : (kk == 1 ? a[b][q].y : (kk == 2 ? a[b][q].z : a[b][q].w));
 #pragma unroll
-                        for (int j = 0; j < TN; ++j) acc[b][q][j] = fmaf(av, w[j], acc[b][q][j]);
+                        for (int j = 0; j < TN / 2; ++j) ffma2(acc2[b][q][j], av, w2[j]);
                     }
-#pragma unroll
-                for (int g = 0; g < NG; ++g) wc[g] = wn[g];
             }
-#pragma unroll
-            for (int b = 0; b < R; ++b)
-#pragma unroll
-                for (int q = 0; q < TMr; ++q) a[b][q] = an[b][q];
         }
 #pragma unroll
         for (int q = 0; q < TMr; ++q) {
@@ -217,9 +216,12 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
                 const int n = g * GSTR + tn * 4;
                 const int off = base + (n / T::r) * ISo + (n % T::r);
 #pragma unroll
-                for (int b = 0; b < R; ++b)
-                    st4(Y + b * BSo + off,
-                        make_float4(acc[b][q][4 * g], acc[b][q][4 * g + 1], acc[b][q][4 * g + 2], acc[b][q][4 * g + 3]));
+                for (int b = 0; b < R; ++b) {
+                    float4 v;
+                    upk2(acc2[b][q][2 * g], v.x, v.y);
+                    upk2(acc2[b][q][2 * g + 1], v.z, v.w);
+                    st4(Y + b * BSo + off, v);
+                }
             }
         }
     }
@@ -275,16 +277,15 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
                            float (&acc)[R][FM::TMr][FM::TI][4]) {
     using T = St<S, 0>;
     constexpr int TMr = FM::TMr, TI = FM::TI;
+    const float *xb = X + mt * T::KS + kh * FM::KPART;
+    const float *wb = W + kh * FM::KPART * T::NS + itg * TI * 4;
+    f32x2 acc2[R][TMr][TI][2];
 #pragma unroll
     for (int b = 0; b < R; ++b)
 #pragma unroll
         for (int q = 0; q < TMr; ++q)
 #pragma unroll
-            for (int i = 0; i < TI; ++i)
-#pragma unroll
-                for (int g = 0; g < 4; ++g) acc[b][q][i][g] = 0.f;
-    const float *xb = X + mt * T::KS + kh * FM::KPART;
-    const float *wb = W + kh * FM::KPART * T::NS + itg * TI * 4;
+            for (int i = 0; i < TI; ++i) { acc2[b][q][i][0] = 0ull; acc2[b][q][i][1] = 0ull; }
 #pragma unroll 2
     for (int k4 = 0; k4 < FM::KPART; k4 += 4) {
         float4 a[R][TMr];
@@ -294,9 +295,13 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
             for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * FM::MTl * T::KS + k4);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-            float4 w[TI];
+            f32x2 w2[TI][2];
 #pragma unroll
-            for (int i = 0; i < TI; ++i) w[i] = ld4(wb + (k4 + kk) * T::NS + i * 4);
+            for (int i = 0; i < TI; ++i) {
+                const float4 t = ld4(wb + (k4 + kk) * T::NS + i * 4);
+                w2[i][0] = pk2(t.x, t.y);
+                w2[i][1] = pk2(t.z, t.w);          // GRU: (n gate, zero pad)
+            }
 #pragma unroll
             for (int b = 0; b < R; ++b)
 #pragma unroll
@@ -304,14 +309,21 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
                     const float av = kk == 0 ? a[b][q].x : (kk == 1 ? a[b][q].y : (kk == 2 ? a[b][q].z : a[b][q].w));
 #pragma unroll
                     for (int i = 0; i < TI; ++i) {
-                        acc[b][q][i][0] = fmaf(av, w[i].x, acc[b][q][i][0]);
-                        acc[b][q][i][1] = fmaf(av, w[i].y, acc[b][q][i][1]);
-                        acc[b][q][i][2] = fmaf(av, w[i].z, acc[b][q][i][2]);
-                        if (S::G == 4) acc[b][q][i][3] = fmaf(av, w[i].w, acc[b][q][i][3]);
+                        ffma2(acc2[b][q][i][0], av, w2[i][0]);
+                        ffma2(acc2[b][q][i][1], av, w2[i][1]);
                     }
                 }
         }
     }
+#pragma unroll
+    for (int b = 0; b < R; ++b)
+#pragma unroll
+        for (int q = 0; q < TMr; ++q)
+#pragma unroll
+            for (int i = 0; i < TI; ++i) {
+                upk2(acc2[b][q][i][0], acc[b][q][i][0], acc[b][q][i][1]);
+                upk2(acc2[b][q][i][1], acc[b][q][i][2], acc[b][q][i][3]);
+            }
 }
 
 // reduce-scatter of the SK partial tiles: on return pre[b][n][g] holds the full sums of the NE
@@ -700,12 +712,13 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
         const int mt = (wv / M::WX) * M::LY + L::y(lane);
         const bool live = !(M::TT < M::PER && mt >= M::MTl);
         float acc[R][TMr][TN];
+        f32x2 acc2[R][TMr][TN / 2];
 #pragma unroll
         for (int b = 0; b < R; ++b)
 #pragma unroll
             for (int q = 0; q < TMr; ++q)
 #pragma unroll
-                for (int j = 0; j < TN; ++j) acc[b][q][j] = 0.f;
+                for (int j = 0; j < TN / 2; ++j) acc2[b][q][j] = 0ull;
         if (live) {
             int rbase[TMr];
 #pragma unroll
@@ -726,11 +739,12 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
                     if (k == 0 && T::PACK && kk >= S::G) continue;    // padded gate column
-                    float w[TN];
+                    f32x2 w2[TN / 2];
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
                         const float4 t = ld4(wb + (n + kk) * KST + g * GSTR);
-                        w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
+                        w2[2 * g] = pk2(t.x, t.y);
+                        w2[2 * g + 1] = pk2(t.z, t.w);
                     }
 #pragma unroll
                     for (int b = 0; b < R; ++b)
@@ -738,11 +752,17 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
                         for (int q = 0; q < TMr; ++q) {
                             const float av = kk == 0 ? a[b][q].x : (kk == 1 ? a[b][q].y : (kk == 2 ? a[b][q].z : a[b][q].w));
 #pragma unroll
-                            for (int j = 0; j < TN; ++j) acc[b][q][j] = fmaf(av, w[j], acc[b][q][j]);
+                            for (int j = 0; j < TN / 2; ++j) ffma2(acc2[b][q][j], av, w2[j]);
                         }
                 }
             }
         }
+#pragma unroll
+        for (int b = 0; b < R; ++b)
+#pragma unroll
+            for (int q = 0; q < TMr; ++q)
+#pragma unroll
+                for (int j = 0; j < TN / 2; ++j) upk2(acc2[b][q][j], acc[b][q][2 * j], acc[b][q][2 * j + 1]);
         if constexpr (SPLIT == 1) {
             if (live) {
 #pragma unroll
@@ -816,6 +836,19 @@ struct BwMap {
     static constexpr int MG = NTHR / TILES;
     static constexpr int M = R * T::Mrow;
     static constexpr int ROWS = (M + MG - 1) / MG;                        // row iterations per thread
+    // lanes: x = n tile (dY operand, pair-blocked), y = (kappa tile, row group) (X operand, period 2)
+    static constexpr int LX = NT4 >= 16 ? 16 : NT4;
+    static constexpr int LY = 32 / LX;
+    static_assert(NT4 % LX == 0 && (KT * MG) % LY == 0, "bwd-weight lane grid");
+    static constexpr int WXN = NT4 / LX;
+    TTS_DEV static void coords(int tid, int &nt, int &kt, int &mg) {
+        using L = Lanes<LX>;
+        const int lane = tid & 31, warp = tid >> 5;
+        nt = (warp % WXN) * LX + L::x(lane);
+        const int rest = (warp / WXN) * LY + L::y(lane);
+        kt = rest % KT;
+        mg = rest / KT;
+    }
 };
 
 template <class S, int k, int R, int TK>
@@ -826,12 +859,16 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
     constexpr int KSo = (k == 0) ? DY0<S>::DS : St<S, (k == 0 ? 0 : k - 1)>::KS;
     constexpr int BSo = (k == 0) ? DY0<S>::BS : St<S, (k == 0 ? 0 : k - 1)>::BS;
     constexpr int ISo = (k == 0) ? 0 : (T::Mrow / Jp) * KSo;
-    // tile coordinates: n tile fastest, then kappa tile, then the row group
-    const int nt = tid % M::NT4;
-    const int kt = (tid / M::NT4) % M::KT;
-    const int mg = tid / M::TILES;
+    int nt, kt, mg;
+    M::coords(tid, nt, kt, mg);
     const int n0 = nt * 4;
     const int yoff = (k == 0) ? n0 : (n0 / T::r) * ISo + (n0 % T::r);
+    f32x2 acc2[TK][2];
+#pragma unroll
+    for (int a = 0; a < TK; ++a) {
+        acc2[a][0] = pk2(acc[a][0], acc[a][1]);
+        acc2[a][1] = pk2(acc[a][2], acc[a][3]);
+    }
 #pragma unroll 2
     for (int it = 0; it < M::ROWS; ++it) {
         const int m = it * M::MG + mg;
@@ -840,6 +877,7 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
         const float *xp = X + b * T::BS + mr * T::KS + kt * TK;
         const float *yp = dY + b * BSo + ((k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r) + yoff;
         const float4 y = ld4(yp);
+        const f32x2 y01 = pk2(y.x, y.y), y23 = pk2(y.z, y.w);
         float x[TK];
 #pragma unroll
         for (int g = 0; g < TK / 4; ++g) {
@@ -848,11 +886,14 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
         }
 #pragma unroll
         for (int a = 0; a < TK; ++a) {
-            acc[a][0] = fmaf(x[a], y.x, acc[a][0]);
-            acc[a][1] = fmaf(x[a], y.y, acc[a][1]);
-            acc[a][2] = fmaf(x[a], y.z, acc[a][2]);
-            if (!(k == 0 && T::PACK && S::G == 3)) acc[a][3] = fmaf(x[a], y.w, acc[a][3]);
+            ffma2(acc2[a][0], x[a], y01);
+            ffma2(acc2[a][1], x[a], y23);
         }
+    }
+#pragma unroll
+    for (int a = 0; a < TK; ++a) {
+        upk2(acc2[a][0], acc[a][0], acc[a][1]);
+        upk2(acc2[a][1], acc[a][2], acc[a][3]);
     }
 }
 
@@ -863,9 +904,8 @@ TTS_DEV void flush_dw(float (&acc)[TK][4], float *__restrict__ stg, float *__res
     using T = St<S, k>;
     using M = BwMap<S, k, R, TK>;
     constexpr int I0p = T::PACK ? T::I / (T::PACK ? S::G : 1) : 1;
-    const int nt = tid % M::NT4;
-    const int kt = (tid / M::NT4) % M::KT;
-    const int mg = tid / M::TILES;
+    int nt, kt, mg;
+    M::coords(tid, nt, kt, mg);
     __syncthreads();
     for (int g = 0; g < M::MG; ++g) {
         if (mg == g) {
@@ -1333,12 +1373,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_ttlin_fwd_s(const __grid_constant__
         // ---- output stage: thread = (row tile mt, batch-row group rb); lanes run along rows, so every
         // global store of a warp covers 32 consecutive floats
         float acc[OM::RPT][OM::TMr][OM::TN];
+        f32x2 acc2[OM::RPT][OM::TMr][OM::TN / 2];
 #pragma unroll
         for (int i = 0; i < OM::RPT; ++i)
 #pragma unroll
             for (int q = 0; q < OM::TMr; ++q)
 #pragma unroll
-                for (int j = 0; j < OM::TN; ++j) acc[i][q][j] = 0.f;
+                for (int j = 0; j < OM::TN / 2; ++j) acc2[i][q][j] = 0ull;
         const float *xb = X0 + mt * T0::KS;
         const float *wb = wsm + WOff<S, 0>::v;
 #pragma unroll 2
@@ -1353,11 +1394,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_ttlin_fwd_s(const __grid_constant__
                 }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-                float w[OM::TN];
+                f32x2 w2[OM::TN / 2];
 #pragma unroll
                 for (int g = 0; g < OM::TN / 4; ++g) {
                     const float4 t = ld4(wb + (k4 + kk) * T0::NS + 4 * g);
-                    w[4 * g] = t.x; w[4 * g + 1] = t.y; w[4 * g + 2] = t.z; w[4 * g + 3] = t.w;
+                    w2[2 * g] = pk2(t.x, t.y);
+                    w2[2 * g + 1] = pk2(t.z, t.w);
                 }
 #pragma unroll
                 for (int i = 0; i < OM::RPT; ++i)
@@ -1365,10 +1407,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_ttlin_fwd_s(const __grid_constant__
                     for (int q = 0; q < OM::TMr; ++q) {
                         const float x = kk == 0 ? av[i][q].x : (kk == 1 ? av[i][q].y : (kk == 2 ? av[i][q].z : av[i][q].w));
 #pragma unroll
-                        for (int j = 0; j < OM::TN; ++j) acc[i][q][j] = fmaf(x, w[j], acc[i][q][j]);
+                        for (int j = 0; j < OM::TN / 2; ++j) ffma2(acc2[i][q][j], x, w2[j]);
                     }
             }
         }
+#pragma unroll
+        for (int i = 0; i < OM::RPT; ++i)
+#pragma unroll
+            for (int q = 0; q < OM::TMr; ++q)
+#pragma unroll
+                for (int j = 0; j < OM::TN / 2; ++j) upk2(acc2[i][q][j], acc[i][q][2 * j], acc[i][q][2 * j + 1]);
 #pragma unroll
         for (int i = 0; i < OM::RPT; ++i) {
             const int b = rb * OM::RPT + i;
