@@ -371,6 +371,14 @@ def main():
         dom_ms = kms[dom] / args.steps
         achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
         whole = mult * fwd_flops * B * T * world * args.steps / (total_ms * 1e-3) / 1e12 / world
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                ent = json.load(f).get(cfg["name"])
+            if ent and ent["kernel"] == names[dom].replace("k_ttlinear", "k_ttlinear"):
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
         line = {
             "metric": "TT-RNN cell-steps/sec (batch x T), %s" % cfg["mode"],
             "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -382,7 +390,8 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "fp32_ffma", "kernel": names[dom], "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
                          "peak_source": "ttrnn_ffma_probe measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
                          "algorithmic_flops_per_seqstep": per_seqstep,
                          "whole_step_tflops_per_gpu": whole, "whole_step_frac": whole / peak if peak else None,
