@@ -28,6 +28,8 @@ constexpr int p2div(int n, int want) {
 }
 
 #define TTS_DEV __device__ __forceinline__
+// k-loops over groups of four: fully unrolled up to 8 groups (no loop-carried register shuffles), else by 4
+constexpr int unroll_of(int groups) { return groups <= 8 ? groups : 4; }
 
 TTS_DEV void cp_async16(float *smem_dst, const float *gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -181,7 +183,7 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
                 for (int j = 0; j < TN / 2; ++j) acc2[b][q][j] = 0ull;
         const float *xb = X + mt * T::KS;
         const float *wb = W + tn * 4;
-#pragma unroll 2
+#pragma unroll(unroll_of(T::K / 4))
         for (int k4 = 0; k4 < T::K; k4 += 4) {
             float4 a[R][TMr];
 #pragma unroll
@@ -286,7 +288,7 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
         for (int q = 0; q < TMr; ++q)
 #pragma unroll
             for (int i = 0; i < TI; ++i) { acc2[b][q][i][0] = 0ull; acc2[b][q][i][1] = 0ull; }
-#pragma unroll 2
+#pragma unroll(unroll_of(FM::KPART / 4))
     for (int k4 = 0; k4 < FM::KPART; k4 += 4) {
         float4 a[R][TMr];
 #pragma unroll
@@ -727,10 +729,15 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
                 rbase[q] = (k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r;
             }
             const float *wb = WT + tn * 4;
-#pragma unroll 2
+            static_assert(k == 0 || M::REDP % T::r == 0 || T::r % M::REDP == 0 || SPLIT == 1, "split must align with the rank runs");
+            const int nsp = sp * M::REDP;                             // first reduction index of this split
+            const int abase = (k == 0) ? nsp : (nsp / T::r) * ISo + (nsp % T::r);
+            const float *wsp = wb + nsp * KST;
+#pragma unroll(unroll_of(M::REDP / 4))
             for (int n4 = 0; n4 < M::REDP; n4 += 4) {
-                const int n = sp * M::REDP + n4;                      // first reduction index of the group
-                const int aoff = (k == 0) ? n : (n / T::r) * ISo + (n % T::r);
+                // nsp is a multiple of r (or the whole split lies inside one run), so the offset separates
+                const int aoff = abase + ((k == 0) ? n4 : (n4 / T::r) * ISo + (n4 % T::r));
+                const int n = n4;
                 float4 a[R][TMr];
 #pragma unroll
                 for (int b = 0; b < R; ++b)
@@ -742,7 +749,7 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
                     f32x2 w2[TN / 2];
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
-                        const float4 t = ld4(wb + (n + kk) * KST + g * GSTR);
+                        const float4 t = ld4(wsp + (n + kk) * KST + g * GSTR);
                         w2[2 * g] = pk2(t.x, t.y);
                         w2[2 * g + 1] = pk2(t.z, t.w);
                     }
@@ -869,13 +876,7 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
         acc2[a][0] = pk2(acc[a][0], acc[a][1]);
         acc2[a][1] = pk2(acc[a][2], acc[a][3]);
     }
-#pragma unroll 2
-    for (int it = 0; it < M::ROWS; ++it) {
-        const int m = it * M::MG + mg;
-        if (M::M % M::MG != 0 && m >= M::M) break;
-        const int b = m / T::Mrow, mr = m % T::Mrow;
-        const float *xp = X + b * T::BS + mr * T::KS + kt * TK;
-        const float *yp = dY + b * BSo + ((k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r) + yoff;
+    auto row_fma = [&](const float *xp, const float *yp) {
         const float4 y = ld4(yp);
         const f32x2 y01 = pk2(y.x, y.y), y23 = pk2(y.z, y.w);
         float x[TK];
@@ -888,6 +889,31 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
         for (int a = 0; a < TK; ++a) {
             ffma2(acc2[a][0], x[a], y01);
             ffma2(acc2[a][1], x[a], y23);
+        }
+    };
+    if constexpr (T::Mrow % M::MG == 0 && (k == 0 || M::MG % Jp == 0 || Jp % M::MG == 0)) {
+        // rows of this thread: mr = i*MG + mg for every batch row b -> compile-time offsets from one base
+        constexpr int NI = T::Mrow / M::MG;
+        const float *xp0 = X + mg * T::KS + kt * TK;
+        const float *yp0 = dY + yoff + ((k == 0) ? mg * KSo : (mg / Jp) * KSo + (mg % Jp) * T::r);
+#pragma unroll 1
+        for (int b = 0; b < R; ++b) {
+#pragma unroll(unroll_of(NI) == NI ? NI : 4)
+            for (int i = 0; i < NI; ++i) {
+                const int dm = i * M::MG;                                        // compile-time row distance
+                const int dy = (k == 0) ? dm * KSo
+                                        : ((M::MG % Jp == 0) ? (dm / Jp) * KSo : (dm / Jp) * KSo + (dm % Jp) * T::r);
+                row_fma(xp0 + b * T::BS + dm * T::KS, yp0 + b * BSo + dy);
+            }
+        }
+    } else {
+#pragma unroll 2
+        for (int it = 0; it < M::ROWS; ++it) {
+            const int m = it * M::MG + mg;
+            if (M::M % M::MG != 0 && m >= M::M) break;
+            const int b = m / T::Mrow, mr = m % T::Mrow;
+            row_fma(X + b * T::BS + mr * T::KS + kt * TK,
+                    dY + b * BSo + ((k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r) + yoff);
         }
     }
 #pragma unroll
