@@ -859,7 +859,7 @@ struct BwMap {
 };
 
 template <class S, int k, int R, int TK>
-TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restrict__ dY, float (&acc)[TK][4], int tid) {
+TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restrict__ dY, f32x2 (&acc2)[TK][2], int tid) {
     using T = St<S, k>;
     using M = BwMap<S, k, R, TK>;
     constexpr int Jp = (k == 0) ? 1 : St<S, (k == 0 ? 0 : k - 1)>::J;
@@ -870,12 +870,6 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
     M::coords(tid, nt, kt, mg);
     const int n0 = nt * 4;
     const int yoff = (k == 0) ? n0 : (n0 / T::r) * ISo + (n0 % T::r);
-    f32x2 acc2[TK][2];
-#pragma unroll
-    for (int a = 0; a < TK; ++a) {
-        acc2[a][0] = pk2(acc[a][0], acc[a][1]);
-        acc2[a][1] = pk2(acc[a][2], acc[a][3]);
-    }
     auto row_fma = [&](const float *xp, const float *yp) {
         const float4 y = ld4(yp);
         const f32x2 y01 = pk2(y.x, y.y), y23 = pk2(y.z, y.w);
@@ -916,18 +910,19 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
                     dY + b * BSo + ((k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r) + yoff);
         }
     }
-#pragma unroll
-    for (int a = 0; a < TK; ++a) {
-        upk2(acc2[a][0], acc[a][0], acc[a][1]);
-        upk2(acc2[a][1], acc[a][2], acc[a][3]);
-    }
 }
 
 // end of launch: sum the MG row groups of stage k and add the result to the gradient slot
 // (blob layout r,i,j,r').  stg: shared staging of K*NS floats (reuses the activation slots).
 template <class S, int k, int R, int TK>
-TTS_DEV void flush_dw(float (&acc)[TK][4], float *__restrict__ stg, float *__restrict__ slot, int tid) {
+TTS_DEV void flush_dw(f32x2 (&acc2)[TK][2], float *__restrict__ stg, float *__restrict__ slot, int tid) {
     using T = St<S, k>;
+    float acc[TK][4];
+#pragma unroll
+    for (int a = 0; a < TK; ++a) {
+        upk2(acc2[a][0], acc[a][0], acc[a][1]);
+        upk2(acc2[a][1], acc[a][2], acc[a][3]);
+    }
     using M = BwMap<S, k, R, TK>;
     constexpr int I0p = T::PACK ? T::I / (T::PACK ? S::G : 1) : 1;
     int nt, kt, mg;
@@ -1038,10 +1033,10 @@ TTS_DEV void fwd_chain_keep(float *xs, const float *hcur, const float *wsm, int 
 // persistent dW register tiles of every stage
 template <class S, int R, class TB>
 struct DwRegs {
-    float a0[TB::WTK[0]][4];
-    float a1[S::D > 1 ? TB::WTK[S::D > 1 ? 1 : 0] : 1][4];
-    float a2[S::D > 2 ? TB::WTK[S::D > 2 ? 2 : 0] : 1][4];
-    float a3[S::D > 3 ? TB::WTK[S::D > 3 ? 3 : 0] : 1][4];
+    f32x2 a0[TB::WTK[0]][2];
+    f32x2 a1[S::D > 1 ? TB::WTK[S::D > 1 ? 1 : 0] : 1][2];
+    f32x2 a2[S::D > 2 ? TB::WTK[S::D > 2 ? 2 : 0] : 1][2];
+    f32x2 a3[S::D > 3 ? TB::WTK[S::D > 3 ? 3 : 0] : 1][2];
 };
 
 template <class S, int R, class TB, int k, bool WANT_DX = true, bool DWI = true>
@@ -1094,7 +1089,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
     float *dy0 = xs + SM::XALL;
     float *dhc = dy0 + SM::DY;
     float *xch = dhc + SM::DHC;
-    float *hbuf[2] = {xs + SM::template XOff<S::D - 1>::v, xch + SM::XCH};
+    // the two h_{t-1} slots as offsets from the shared base (a pointer array would lose the address space)
+    constexpr int HOFF0 = SM::W + SM::WT + SM::template XOff<S::D - 1>::v;
+    constexpr int HOFF1 = SM::W + SM::WT + SM::XALL + SM::DY + SM::DHC + SM::XCH;
 
     stage_weights_k<S, 0>(a.cores, wsm, tid);
     stage_weights_t<S, 0>(a.cores, wt, tid);
@@ -1120,15 +1117,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
     }
     DwRegs<S, R, TB> dw;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a0) / 16); ++q) dw.a0[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a0) / 16); ++q) dw.a0[q][c] = 0ull;
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a1) / 16); ++q) dw.a1[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a1) / 16); ++q) dw.a1[q][c] = 0ull;
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a2) / 16); ++q) dw.a2[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a2) / 16); ++q) dw.a2[q][c] = 0ull;
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a3) / 16); ++q) dw.a3[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a3) / 16); ++q) dw.a3[q][c] = 0ull;
     }
 
     const long long ntiles = (a.B + R - 1) / R;
@@ -1186,12 +1183,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 }
             }
         };
-        fetch_h(hbuf[(a.steps - 1) & 1], a.t0 + a.steps - 1);
+        fetch_h(smem + (((a.steps - 1) & 1) ? HOFF1 : HOFF0), a.t0 + a.steps - 1);
         fetch_regs(a.steps - 1);
         cp_async_wait_all();
         for (int t = a.steps - 1; t >= 0; --t) {
             const int tg = a.t0 + t;
-            float *hcur = hbuf[t & 1];
+            float *hcur = smem + ((t & 1) ? HOFF1 : HOFF0);
             __syncthreads();
             // operands of this step (fetched during the previous one)
             float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE];
@@ -1209,7 +1206,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             }
             // request the operands of step t-1 now; they land while this step computes
             if (t > 0) {
-                fetch_h(hbuf[(t - 1) & 1], tg - 1);
+                fetch_h(smem + (((t - 1) & 1) ? HOFF1 : HOFF0), tg - 1);
                 fetch_regs(t - 1);
             }
             // ---- recompute the hh chain keeping every X_k
@@ -1553,15 +1550,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_ttlin_bwd_s(const __grid_constant__
     for (int j = 0; j < CPT; ++j) dbias[j] = 0.f;
     DwRegs<S, R, TB> dw;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a0) / 16); ++q) dw.a0[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a0) / 16); ++q) dw.a0[q][c] = 0ull;
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a1) / 16); ++q) dw.a1[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a1) / 16); ++q) dw.a1[q][c] = 0ull;
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a2) / 16); ++q) dw.a2[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a2) / 16); ++q) dw.a2[q][c] = 0ull;
 #pragma unroll
-        for (int q = 0; q < (int)(sizeof(dw.a3) / 16); ++q) dw.a3[q][c] = 0.f;
+        for (int q = 0; q < (int)(sizeof(dw.a3) / 16); ++q) dw.a3[q][c] = 0ull;
     }
     const long long ntiles = (a.rows + R - 1) / R;
     for (long long tile_i = blockIdx.x; tile_i < ntiles; tile_i += gridDim.x) {
