@@ -390,8 +390,23 @@ TTS_DEV void final_reduce(float (&acc)[R][FM::TMr][FM::TI][4], float (&pre)[R][F
 // MUFU-based logistic (ex2.approx + rcp.approx): measured parity error stays at 1-4e-7 forward and
 // <= 7e-7 on gradients (tools/parity_report.py), bars are 1e-5 / 1e-4.  -DTTS_ACCURATE_GATES restores expf + IEEE division.
 TTS_DEV float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// branch-free tanh: odd minimax polynomial on |x| < 0.6 (max rel err 8e-8), 1 - 2/(e^{2|x|}+1) beyond
+// (libdevice tanhf takes the same two routes but branches, which diverges inside a warp)
+TTS_DEV float tanh_g(float x) {
+    const float ax = fabsf(x);
+    const float p = x * x;
+    float r = fmaf(p, -0.00598506f, 0.02086822f);
+    r = fmaf(r, p, -0.05380359f);
+    r = fmaf(r, p, 0.13332133f);
+    r = fmaf(r, p, -0.33333305f);
+    const float small = fmaf(x * p, r, x);
+    const float e = __expf(2.0f * ax);
+    const float big = copysignf(1.0f - __fdividef(2.0f, e + 1.0f), x);
+    return ax < 0.6f ? small : big;
+}
 #else
 TTS_DEV float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+TTS_DEV float tanh_g(float x) { return tanhf(x); }
 #endif
 
 // ---- per (shape, R) tuning table ----------------------------------------------------------------
@@ -581,15 +596,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ R
                     if (LSTM) {
                         const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
                         const float fg = sigmoidf_acc(pre[b][n][1] + bhh[n][1] + ain[1]);
-                        const float gg = tanhf(pre[b][n][2] + bhh[n][2] + ain[2]);
+                        const float gg = tanh_g(pre[b][n][2] + bhh[n][2] + ain[2]);
                         const float og = sigmoidf_acc(pre[b][n][3] + bhh[n][3] + ain[3]);
                         const float cn = fg * cst[b][n] + ig * gg;
                         cst[b][n] = cn;
-                        hnew = og * tanhf(cn);
+                        hnew = og * tanh_g(cn);
                     } else {
                         const float rg = sigmoidf_acc(ain[0] + (pre[b][n][0] + bhh[n][0]));
                         const float zg = sigmoidf_acc(ain[1] + (pre[b][n][1] + bhh[n][1]));
-                        const float ng = tanhf(ain[2] + rg * (pre[b][n][2] + bhh[n][2]));
+                        const float ng = tanh_g(ain[2] + rg * (pre[b][n][2] + bhh[n][2]));
                         hnew = (1.0f - zg) * ng + zg * hpr[b][n];
                     }
                     hpr[b][n] = hnew;
@@ -1236,10 +1251,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                     if (LSTM) {
                         const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
                         const float fg = sigmoidf_acc(pre[b][n][1] + bhh[n][1] + ain[1]);
-                        const float gg = tanhf(pre[b][n][2] + bhh[n][2] + ain[2]);
+                        const float gg = tanh_g(pre[b][n][2] + bhh[n][2] + ain[2]);
                         const float og = sigmoidf_acc(pre[b][n][3] + bhh[n][3] + ain[3]);
                         const float cn = fg * cprev[b][n] + ig * gg;
-                        const float tc = tanhf(cn);
+                        const float tc = tanh_g(cn);
                         const float dc = dcs[b][n] + dh * og * (1.0f - tc * tc);
                         d_hh[0] = dc * gg * ig * (1.0f - ig);
                         d_hh[1] = dc * cprev[b][n] * fg * (1.0f - fg);
@@ -1255,7 +1270,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                         const float un = pre[b][n][2] + bhh[n][2];
                         const float rg = sigmoidf_acc(ain[0] + ur);
                         const float zg = sigmoidf_acc(ain[1] + uz);
-                        const float ng = tanhf(ain[2] + rg * un);
+                        const float ng = tanh_g(ain[2] + rg * un);
                         const float d_n = dh * (1.0f - zg) * (1.0f - ng * ng);
                         const float d_z = dh * (hprev[b][n] - ng) * zg * (1.0f - zg);
                         const float d_r = d_n * un * rg * (1.0f - rg);
