@@ -498,8 +498,8 @@ TTS_DEV const float *fwd_chain_pp(float *hs, float *P, float *Q, const float *ws
     }
 }
 
-template <class S, int CELL, int R, int MODE, class TU>
-__global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ RnnFwdSArgs a) {
+template <class S, int CELL, int R, int MODE, class TU, int MINB = 1>
+__global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant__ RnnFwdSArgs a) {
     extern __shared__ __align__(16) float smem[];
     using SM = FwdSmem<S, R, TU>;
     using FM = typename SM::FM;
@@ -556,10 +556,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ R
             }
         __syncthreads();
 
-        for (int t = 0; t < a.steps; ++t) {
-            // ---- operands of the gate phase, requested before the chain so their latency hides
-            float xin[R][NE][4];
-            float x1[R];
+        // operands of the gate phase are fetched one step ahead (the loads of step t+1 are issued at the top
+        // of step t and land while the chain of step t runs)
+        float xin_n[R][NE][4], x1_n[R];
+        auto fetch_in = [&](int tl) {
             if (MODE == MODE_XG) {
 #pragma unroll
                 for (int b = 0; b < R; ++b)
@@ -567,13 +567,27 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_fwd_s(const __grid_constant__ R
                     for (int n = 0; n < NE; ++n)
 #pragma unroll
                         for (int g = 0; g < G; ++g)
-                            xin[b][n][g] = (row0 + b < a.B)
-                                ? __ldg(a.xg + (row0 + b) * a.xg_bstride + (long long)t * GH + g * H + hid[n]) : 0.f;
+                            xin_n[b][n][g] = (row0 + b < a.B)
+                                ? __ldg(a.xg + (row0 + b) * a.xg_bstride + (long long)tl * GH + g * H + hid[n]) : 0.f;
             } else {
 #pragma unroll
                 for (int b = 0; b < R; ++b)
-                    x1[b] = (row0 + b < a.B) ? __ldg(a.x1 + (row0 + b) * a.x1_bstride + t) : 0.f;
+                    x1_n[b] = (row0 + b < a.B) ? __ldg(a.x1 + (row0 + b) * a.x1_bstride + tl) : 0.f;
             }
+        };
+        fetch_in(0);
+        for (int t = 0; t < a.steps; ++t) {
+            float xin[R][NE][4];
+            float x1[R];
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                x1[b] = x1_n[b];
+#pragma unroll
+                for (int n = 0; n < NE; ++n)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) xin[b][n][g] = xin_n[b][n][g];
+            }
+            if (t + 1 < a.steps) fetch_in(t + 1);
             // ---- stages d-1 .. 1
             const float *X0 = fwd_chain_pp<S, R, TU, S::D - 1>(hs, P, Q, wsm, tid);
             // ---- stage 0 (split over K) + reduce-scatter + gate math + state update

@@ -20,7 +20,8 @@ struct TtsRnnFwdEntry {
 };
 
 // best registered forward kernel for (hh shape, cell, mode) at batch B on `sms` SMs, or nullptr
-const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms);
+const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms,
+                                       int prefer_R = 0);
 
 struct TtsRnnBwdEntry {
     const char *name;
@@ -32,7 +33,8 @@ struct TtsRnnBwdEntry {
     int (*launch)(const tts::RnnBwdSArgs *args, int grid, cudaStream_t st);
     int (*prepare)(int *max_blocks_per_sm);
 };
-const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms);
+const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms,
+                                       int prefer_R = 0);
 
 struct TtsTtlFwdEntry {
     const char *name;

@@ -37,14 +37,14 @@ bool match_shape(const ttrnn_tt_shape *s) {
     return s->ranks[S::D] == 1;
 }
 
-template <class S, int CELL, int R, int MODE, class TU>
+template <class S, int CELL, int R, int MODE, class TU, int MINB = 1>
 int launch_fwd(const tts::RnnFwdSArgs *a, int grid, cudaStream_t st) {
-    tts::k_rnn_fwd_s<S, CELL, R, MODE, TU><<<grid, tts::NTHR, tts::FwdSmem<S, R, TU>::BYTES, st>>>(*a);
+    tts::k_rnn_fwd_s<S, CELL, R, MODE, TU, MINB><<<grid, tts::NTHR, tts::FwdSmem<S, R, TU>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
-template <class S, int CELL, int R, int MODE, class TU>
+template <class S, int CELL, int R, int MODE, class TU, int MINB = 1>
 int prepare_fwd(int *occ) {
-    auto k = tts::k_rnn_fwd_s<S, CELL, R, MODE, TU>;
+    auto k = tts::k_rnn_fwd_s<S, CELL, R, MODE, TU, MINB>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::FwdSmem<S, R, TU>::BYTES);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::FwdSmem<S, R, TU>::BYTES);
@@ -57,12 +57,15 @@ int prepare_fwd(int *occ) {
 // Tune<FTMr, FTI, FSK, TM1, TN1, TM2, TN2, TM3, TN3>: final-stage tile (rows, first-mode slices, k-split)
 // and (rows, columns) of the thread tile of stages 1..3
 using tts::Tune;
+#define TTS_FWD2(S, CELL, R, MODE, ...)                                                                    \
+    {#S "(2 CTAs/SM)", CELL, MODE, R, tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>,              \
+     &launch_fwd<S, CELL, R, MODE, __VA_ARGS__, 2>, &prepare_fwd<S, CELL, R, MODE, __VA_ARGS__, 2>}
 const TtsRnnFwdEntry kFwd[] = {
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
-    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD2(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
@@ -189,8 +192,11 @@ const TtsTtlBwdEntry *tts_find_ttl_bwd(const ttrnn_tt_shape *s, long long rows, 
     return nullptr;
 }
 
-const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms) {
+const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R) {
     const TtsRnnBwdEntry *best = nullptr;
+    if (prefer_R > 0)
+        for (const auto &e : kBwd)
+            if (e.cell == cell && e.mode == mode && e.match(hh) && e.smem <= kMaxSmem && e.R == prefer_R) return &e;
     long long best_cost = 0;
     for (const auto &e : kBwd) {
         if (e.cell != cell || e.mode != mode || !e.match(hh) || e.smem > kMaxSmem) continue;
@@ -205,8 +211,11 @@ const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int m
     return best;
 }
 
-const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms) {
+const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R) {
     const TtsRnnFwdEntry *best = nullptr;
+    if (prefer_R > 0)
+        for (const auto &e : kFwd)
+            if (e.cell == cell && e.mode == mode && e.match(hh) && e.smem <= kMaxSmem && e.R == prefer_R) return &e;
     long long best_cost = 0;
     for (const auto &e : kFwd) {
         if (e.cell != cell || e.mode != mode || !e.match(hh) || e.smem > kMaxSmem) continue;

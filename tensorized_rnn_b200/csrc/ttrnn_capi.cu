@@ -21,6 +21,7 @@ std::atomic<long long> g_opt_rows{0};
 std::atomic<long long> g_opt_chunk{0};
 std::atomic<long long> g_opt_chunk_bytes{4LL << 30};
 std::atomic<long long> g_opt_static{1};
+std::atomic<long long> g_opt_srows_fwd{0}, g_opt_srows_bwd{0};
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
 struct TimedLaunch { int kind; cudaEvent_t a, b; };
@@ -484,6 +485,8 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "chunk_steps")) { g_opt_chunk.store(value); return 0; }
     if (!strcmp(key, "chunk_bytes")) { g_opt_chunk_bytes.store(value > 0 ? value : (4LL << 30)); return 0; }
     if (!strcmp(key, "static_kernels")) { g_opt_static.store(value); return 0; }
+    if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
+    if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
     return 1;
 }
 
@@ -542,7 +545,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
 
         // ---- statically specialised kernel for this hh shape, if one is registered -------------------
         const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
-        const TtsRnnFwdEntry *se = g_opt_static.load() ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms) : nullptr;
+        const TtsRnnFwdEntry *se = g_opt_static.load() ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_fwd.load()) : nullptr;
         if (se) {
             int occ = 0;
             int rc = se->prepare(&occ);
@@ -680,7 +683,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
 
         // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
         const int mode = (l == 0 && d->input_size == 1 && !d_x) ? tts::MODE_RANK1 : tts::MODE_XG;
-        const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms) : nullptr;
+        const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load()) : nullptr;
         if (be) {
             int occ = 0;
             int rc = be->prepare(&occ);
