@@ -138,6 +138,11 @@ int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K
 /* Tuning knobs (process-wide; also read from the environment at load time):
  *   "rows_per_cta"  batch rows owned by one CTA of the recurrent kernels (0 = auto)
  *   "chunk_steps"   timesteps per ih-projection chunk (0 = auto, bounded by memory)
+ *   "chunk_bytes"   byte budget of one ih-projection chunk (default 4 GiB)
+ *   "static_kernels" 0 = always use the runtime-shape kernels
+ *   "static_rows_fwd" / "static_rows_bwd"  force the rows-per-CTA variant of the static kernels
+ *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of
+ *                   recomputing them (default 0 = recompute)
  * returns 0 if the key is known. */
 int ttrnn_set_option(const char *key, int64_t value);
 

@@ -480,6 +480,12 @@ struct RnnFwdSArgs {
     long long out_bstride;
     float *c_save;
     float *h_out, *c_out;
+    // optional (training, two-core chains): keep X_0 (output of stage 1) and the hh pre-activations of every
+    // step so that backward does not recompute the chain.  Row b, step t at  base + b*bstride + t*per_step.
+    float *x0_save;          // per step: Mrow_0 * K_0 floats (unpadded rows)
+    long long x0_bstride;
+    float *u_save;           // per step: G*H floats
+    long long u_bstride;
 };
 
 enum { MODE_XG = 0, MODE_RANK1 = 1 };
@@ -590,6 +596,17 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
             if (t + 1 < a.steps) fetch_in(t + 1);
             // ---- stages d-1 .. 1
             const float *X0 = fwd_chain_pp<S, R, TU, S::D - 1>(hs, P, Q, wsm, tid);
+            if (a.x0_save) {
+                // X_0 tile -> HBM (coalesced float4), overlapped with the final stage which only reads it
+                using T0s = St<S, 0>;
+                constexpr int X0F = T0s::Mrow * T0s::K;
+                for (int e = tid * 4; e < R * X0F; e += NTHR * 4) {
+                    const int b = e / X0F, rem = e % X0F;
+                    if (row0 + b < a.B)
+                        *reinterpret_cast<float4 *>(a.x0_save + (row0 + b) * a.x0_bstride + (long long)t * X0F + rem) =
+                            ld4(X0 + b * T0s::BS + (rem / T0s::K) * T0s::KS + (rem % T0s::K));
+                }
+            }
             // ---- stage 0 (split over K) + reduce-scatter + gate math + state update
             float pre[R][NE][4];
             {
@@ -606,6 +623,11 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
 #pragma unroll
                     for (int g = 0; g < G; ++g)
                         ain[g] = (MODE == MODE_XG) ? xin[b][n][g] : fmaf(x1[b], weff[n][g], bih[n][g]);
+                    if (a.u_save && row0 + b < a.B) {
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            a.u_save[(row0 + b) * a.u_bstride + (long long)t * GH + g * H + h] = pre[b][n][g];
+                    }
                     float hnew;
                     if (LSTM) {
                         const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
@@ -1045,6 +1067,10 @@ struct RnnBwdSArgs {
     const float *dh_in, *dc_in;
     float *dh_out, *dc_out;
     float *partial;          // [gridDim.x][core_floats + 3*G*H]: cores, db_hh, d_weff, db_ih  (+= at the end)
+    const float *x0_save;    // SAVED kernels: X_0 tiles / hh pre-activations written by the forward kernel
+    long long x0_bstride;    //   (whole sequence, not offset by t0; row stride in floats)
+    const float *u_save;
+    long long u_bstride;
 };
 
 template <class S, int R, class TB, int k, bool DWI = true>
@@ -1099,8 +1125,9 @@ TTS_DEV void flush_all(DwRegs<S, R, TB> &dw, float *stg, float *slot, int tid) {
     if constexpr (k + 1 < S::D) flush_all<S, R, TB, k + 1>(dw, stg, slot, tid);
 }
 
-template <class S, int CELL, int R, int MODE, class TB, bool DWI = true>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI = true, bool SAVED = false>
 __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
+    static_assert(!SAVED || (S::D == 2 && DWI), "saved-activation backward is implemented for two-core chains");
     extern __shared__ __align__(16) float smem[];
     using SM = BwdSmem<S, R, TB, DWI>;
     static_assert(DWI || (CELL == TTRNN_CELL_LSTM && MODE == MODE_XG),
@@ -1187,9 +1214,30 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 else st4(d4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
         };
-        float xin_n[R][NE][4], x1_n[R], cprev_n[R][NE], dho_n[R][NE];
+        float xin_n[R][NE][4], x1_n[R], cprev_n[R][NE], dho_n[R][NE], pre_n[R][NE][4];
+        auto fetch_x0 = [&](int tgl) {                    // saved X_0 tile of global step tgl -> its slot
+            using T0s = St<S, 0>;
+            constexpr int X0F = T0s::Mrow * T0s::K;
+            float *dst = xs + SM::template XOff<0>::v;
+            for (int e = tid * 4; e < R * X0F; e += NTHR * 4) {
+                const int b = e / X0F, rem = e % X0F;
+                float *d4 = dst + b * T0s::BS + (rem / T0s::K) * T0s::KS + (rem % T0s::K);
+                if (row0 + b < a.B) cp_async16(d4, a.x0_save + (row0 + b) * a.x0_bstride + (long long)tgl * X0F + rem);
+                else st4(d4, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        };
         auto fetch_regs = [&](int tl) {                   // operands of local step tl
             const int tgl = a.t0 + tl;
+            if (SAVED) {
+#pragma unroll
+                for (int b = 0; b < R; ++b)
+#pragma unroll
+                    for (int n = 0; n < NE; ++n)
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            pre_n[b][n][g] = (row0 + b < a.B)
+                                ? __ldg(a.u_save + (row0 + b) * a.u_bstride + (long long)tgl * GH + g * H + hid[n]) : 0.f;
+            }
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 const long long row = row0 + b;
@@ -1214,20 +1262,24 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
         };
         fetch_h(smem + (((a.steps - 1) & 1) ? HOFF1 : HOFF0), a.t0 + a.steps - 1);
         fetch_regs(a.steps - 1);
+        if (SAVED) fetch_x0(a.t0 + a.steps - 1);
         cp_async_wait_all();
         for (int t = a.steps - 1; t >= 0; --t) {
             const int tg = a.t0 + t;
             float *hcur = smem + ((t & 1) ? HOFF1 : HOFF0);
             __syncthreads();
             // operands of this step (fetched during the previous one)
-            float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE];
+            float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE], pre[R][NE][4];
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 x1[b] = x1_n[b];
 #pragma unroll
                 for (int n = 0; n < NE; ++n) {
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) xin[b][n][g] = xin_n[b][n][g];
+                    for (int g = 0; g < 4; ++g) {
+                        xin[b][n][g] = xin_n[b][n][g];
+                        if (SAVED) pre[b][n][g] = pre_n[b][n][g];      // chain outputs kept by the forward kernel
+                    }
                     cprev[b][n] = cprev_n[b][n];
                     dho[b][n] = dho_n[b][n];
                     hprev[b][n] = hcur[b * TL::BS + (hid[n] / TL::K) * TL::KS + (hid[n] % TL::K)];
@@ -1238,10 +1290,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 fetch_h(smem + (((t - 1) & 1) ? HOFF1 : HOFF0), tg - 1);
                 fetch_regs(t - 1);
             }
-            // ---- recompute the hh chain keeping every X_k
-            fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
-            float pre[R][NE][4];
-            {
+            if constexpr (!SAVED) {
+                // ---- recompute the hh chain keeping every X_k
+                fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
                 float acc[R][FM::TMr][FM::TI][4];
                 final_partial<S, R, FM>((S::D == 1) ? hcur : xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg,
                                         kh, acc);
@@ -1310,10 +1361,12 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                         g_bhh[n][g] += d_hh[g];
                     }
                 }
+            if (SAVED) cp_async_wait_all();               // X_0 tile of this step (and h_{t-2}) have landed
             __syncthreads();
             // ---- backward chain: core gradients (register tiles) and dh_{t-1}
             bwd_chain<S, R, TB, 0, true, DWI>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
             cp_async_wait_all();
+            if (SAVED && t > 0) fetch_x0(tg - 1);         // the X_0 slot is free again: refill for the next step
         }
         __syncthreads();
 #pragma unroll

@@ -13,6 +13,7 @@ struct TtlBwdSArgs;
 struct TtsRnnFwdEntry {
     const char *name;
     int cell, mode, R;
+    long long x0_floats;                                                      // > 0: the kernel can keep X_0 (floats per row-step)
     size_t smem;
     bool (*match)(const ttrnn_tt_shape *hh);
     int (*launch)(const tts::RnnFwdSArgs *args, int grid, cudaStream_t st);   // 0 = ok, else cudaError_t
@@ -27,6 +28,7 @@ struct TtsRnnBwdEntry {
     const char *name;
     int cell, mode, R;
     int split;                                                               // 1: core gradients come from a batched kernel
+    int saved;                                                               // 1: consumes X_0 / pre-activations kept by forward
     size_t smem;
     long long slot_floats;                                                   // floats per gradient slot
     bool (*match)(const ttrnn_tt_shape *hh);
@@ -34,7 +36,7 @@ struct TtsRnnBwdEntry {
     int (*prepare)(int *max_blocks_per_sm);
 };
 const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms,
-                                       int prefer_R = 0);
+                                       int prefer_R = 0, int saved = 0);
 
 struct TtsTtlFwdEntry {
     const char *name;

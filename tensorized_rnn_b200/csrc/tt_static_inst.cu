@@ -50,15 +50,18 @@ int prepare_fwd(int *occ) {
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::FwdSmem<S, R, TU>::BYTES);
 }
 
+template <class S> constexpr long long x0_floats() {
+    return S::D == 2 ? (long long)tts::St<S, 0>::Mrow * tts::St<S, 0>::K : 0;
+}
 #define TTS_FWD(S, CELL, R, MODE, ...)                                                                     \
-    {#S, CELL, MODE, R, tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>,                            \
+    {#S, CELL, MODE, R, x0_floats<S>(), tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>,            \
      &launch_fwd<S, CELL, R, MODE, __VA_ARGS__>, &prepare_fwd<S, CELL, R, MODE, __VA_ARGS__>}
 
 // Tune<FTMr, FTI, FSK, TM1, TN1, TM2, TN2, TM3, TN3>: final-stage tile (rows, first-mode slices, k-split)
 // and (rows, columns) of the thread tile of stages 1..3
 using tts::Tune;
 #define TTS_FWD2(S, CELL, R, MODE, ...)                                                                    \
-    {#S "(2 CTAs/SM)", CELL, MODE, R, tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>,              \
+    {#S "(2 CTAs/SM)", CELL, MODE, R, x0_floats<S>(), tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>, \
      &launch_fwd<S, CELL, R, MODE, __VA_ARGS__, 2>, &prepare_fwd<S, CELL, R, MODE, __VA_ARGS__, 2>}
 const TtsRnnFwdEntry kFwd[] = {
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
@@ -76,14 +79,14 @@ const TtsRnnFwdEntry kFwd[] = {
 };
 
 
-template <class S, int CELL, int R, int MODE, class TB, bool DWI>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI, bool SV = false>
 int launch_bwd(const tts::RnnBwdSArgs *a, int grid, cudaStream_t st) {
-    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES, st>>>(*a);
+    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
-template <class S, int CELL, int R, int MODE, class TB, bool DWI>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI, bool SV = false>
 int prepare_bwd(int *occ) {
-    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI>;
+    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB, DWI>::BYTES);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES);
@@ -92,10 +95,14 @@ template <class S>
 constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * tts::n_in<S>(); }
 
 #define TTS_BWD(S, CELL, R, MODE, ...)                                                                      \
-    {#S, CELL, MODE, R, 0, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(), &match_shape<S>,  \
+    {#S, CELL, MODE, R, 0, 0, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(), &match_shape<S>, \
      &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true>, &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true>}
+#define TTS_BWD_SAVED(S, CELL, R, MODE, ...)                                                                \
+    {#S "(saved)", CELL, MODE, R, 0, 1, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(),      \
+     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true, true>,                                \
+     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true, true>}
 #define TTS_BWD_SPLIT(S, CELL, R, MODE, ...)                                                                \
-    {#S "(split)", CELL, MODE, R, 1, tts::BwdSmem<S, R, __VA_ARGS__, false>::BYTES, slot_floats<S>(),        \
+    {#S "(split)", CELL, MODE, R, 1, 0, tts::BwdSmem<S, R, __VA_ARGS__, false>::BYTES, slot_floats<S>(),     \
      &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false>,                                     \
      &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, false>}
 
@@ -117,6 +124,10 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
     TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, TB_d2),
     TTS_BWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, TB_d2),
+    TTS_BWD_SAVED(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVED(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVED(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVED(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),
@@ -192,14 +203,17 @@ const TtsTtlBwdEntry *tts_find_ttl_bwd(const ttrnn_tt_shape *s, long long rows, 
     return nullptr;
 }
 
-const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R) {
+const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R,
+                                       int saved) {
     const TtsRnnBwdEntry *best = nullptr;
     if (prefer_R > 0)
         for (const auto &e : kBwd)
-            if (e.cell == cell && e.mode == mode && e.match(hh) && e.smem <= kMaxSmem && e.R == prefer_R) return &e;
+            if (e.cell == cell && e.mode == mode && e.saved == saved && e.match(hh) && e.smem <= kMaxSmem &&
+                e.R == prefer_R)
+                return &e;
     long long best_cost = 0;
     for (const auto &e : kBwd) {
-        if (e.cell != cell || e.mode != mode || !e.match(hh) || e.smem > kMaxSmem) continue;
+        if (e.cell != cell || e.mode != mode || e.saved != saved || !e.match(hh) || e.smem > kMaxSmem) continue;
         const long long tiles = (B + e.R - 1) / e.R;
         const long long waves = (tiles + sms - 1) / sms;
         const long long cost = waves * e.R;

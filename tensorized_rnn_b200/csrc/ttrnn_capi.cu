@@ -22,6 +22,9 @@ std::atomic<long long> g_opt_chunk{0};
 std::atomic<long long> g_opt_chunk_bytes{4LL << 30};
 std::atomic<long long> g_opt_static{1};
 std::atomic<long long> g_opt_srows_fwd{0}, g_opt_srows_bwd{0};
+// budget for kept chain activations (0 = always recompute).  Off by default: measured on cfg2 it trades
+// +0.9 ms forward (X_0 stores) for -1.2 ms backward and costs 9 GB, a 1.6 % net gain.
+std::atomic<long long> g_opt_save_bytes{0};
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
 struct TimedLaunch { int kind; cudaEvent_t a, b; };
@@ -262,6 +265,9 @@ struct RnnLayout {
     long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
     int nslots = 0;
+    // kept chain activations (two-core static chains, within the save_bytes budget): per layer offsets into `saved`
+    bool save_on[TTRNN_MAX_LAYERS] = {};
+    long long sv_x0[TTRNN_MAX_LAYERS] = {}, sv_u[TTRNN_MAX_LAYERS] = {}, x0f[TTRNN_MAX_LAYERS] = {};
 };
 
 int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, RnnLayout *lo) {
@@ -282,6 +288,28 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->sv_hs = 0;
     lo->sv_cs = r4((L - 1) * lo->BTH);
     lo->sv_total = lo->sv_cs + (lstm ? r4(L * lo->BTH) : 0);
+    if (g_opt_static.load() && g_opt_save_bytes.load() > 0) {
+        long long extra = 0;
+        for (int l = 0; l < L; ++l) {
+            const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
+            const TtsRnnFwdEntry *se = tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_fwd.load());
+            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1);
+            if (se && be && se->x0_floats > 0) {
+                lo->save_on[l] = true;
+                lo->x0f[l] = se->x0_floats;
+                extra += r4(B * T * se->x0_floats) + r4(B * T * GH);
+            }
+        }
+        if (extra * 4 > g_opt_save_bytes.load()) {
+            for (int l = 0; l < L; ++l) lo->save_on[l] = false;
+        } else {
+            for (int l = 0; l < L; ++l)
+                if (lo->save_on[l]) {
+                    lo->sv_x0[l] = lo->sv_total; lo->sv_total += r4(B * T * lo->x0f[l]);
+                    lo->sv_u[l] = lo->sv_total;  lo->sv_total += r4(B * T * GH);
+                }
+        }
+    }
     // forward scratch
     long long o = 0;
     lo->f_xg = o; o += lo->xg_floats;
@@ -485,6 +513,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "chunk_steps")) { g_opt_chunk.store(value); return 0; }
     if (!strcmp(key, "chunk_bytes")) { g_opt_chunk_bytes.store(value > 0 ? value : (4LL << 30)); return 0; }
     if (!strcmp(key, "static_kernels")) { g_opt_static.store(value); return 0; }
+    if (!strcmp(key, "save_bytes")) { g_opt_save_bytes.store(value); return 0; }
     if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
     if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
     return 1;
@@ -589,6 +618,10 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
                 sa.c_in = first ? c0 : st_c;
                 sa.out = lout + (long long)t0 * H; sa.out_bstride = (long long)T * H;
                 sa.c_save = csave ? csave + (long long)t0 * H : nullptr;
+                if (sv && lo.save_on[l] && se->x0_floats == lo.x0f[l]) {
+                    sa.x0_save = sv + lo.sv_x0[l] + (long long)t0 * lo.x0f[l]; sa.x0_bstride = (long long)T * lo.x0f[l];
+                    sa.u_save = sv + lo.sv_u[l] + (long long)t0 * GH;          sa.u_bstride = (long long)T * GH;
+                }
                 sa.h_out = (last && l == L - 1 && hT) ? hT : st_h;
                 sa.c_out = (last && l == L - 1 && cT) ? cT : st_c;
                 {
@@ -684,6 +717,11 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
         // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
         const int mode = (l == 0 && d->input_size == 1 && !d_x) ? tts::MODE_RANK1 : tts::MODE_XG;
         const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load()) : nullptr;
+        if (be && lo.save_on[l] && sv) {
+            // forward kept X_0 and the hh pre-activations of this layer: use the kernel that consumes them
+            if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1))
+                be = bs;
+        }
         if (be) {
             int occ = 0;
             int rc = be->prepare(&occ);
@@ -706,6 +744,10 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             sa.cores = params + lp.off_hh_cores;
             sa.hs = lout; sa.cs = lcs; sa.h0 = h0; sa.c0 = c0; sa.dhs = dhs;
             sa.partial = be->split ? nullptr : part_hh;
+            if (be->saved) {
+                sa.x0_save = sv + lo.sv_x0[l]; sa.x0_bstride = (long long)T * lo.x0f[l];
+                sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * GH;
+            }
             float *aux = sc + lo.b_aux;
             float *aux_g = aux + r4(GH);
             float *one = aux_g + r4(GH);

@@ -106,6 +106,33 @@ def test_static_kernels_match_oracle(case):
     assert not bad, "gradient rel err above %.0e: %s" % (GRAD_TOL, bad)
 
 
+def test_saved_activation_backward_matches_recompute():
+    """`save_bytes` > 0: forward keeps X_0 and the hh pre-activations of two-core chains, backward consumes
+    them instead of recomputing the chain.  Gradients must agree with the recompute path."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    for cell, cls in (("gru", tr.TTGRU), ("lstm", tr.TTLSTM)):
+        torch.manual_seed(21)
+        m = quiet(cls, 1, 256, 1, torch.device("cpu"), n_cores=2, tt_rank=4).to(dev)
+        x = torch.rand(19, 23, 1, device=dev)
+        res = []
+        for budget in (0, 1 << 30):
+            lib.ttrnn_set_option(b"save_bytes", budget)
+            try:
+                for p in m.parameters():
+                    p.grad = None
+                r = m(x)
+                out = r[0]
+                h = r[1][0] if cell == "lstm" else r[1]
+                (out.sum() + 3 * h.sum()).backward()
+                res.append((out.detach().clone(), [p.grad.clone() for p in m.parameters()]))
+            finally:
+                lib.ttrnn_set_option(b"save_bytes", 0)
+        assert torch.equal(res[0][0], res[1][0])
+        for a, b in zip(res[0][1], res[1][1]):
+            assert rel_err(b, a) <= GRAD_TOL
+
+
 def test_static_and_runtime_shape_kernels_agree():
     """Same inputs through the static kernels and through the runtime-shape kernels (static_kernels=0)."""
     dev = torch.device("cuda:0")
