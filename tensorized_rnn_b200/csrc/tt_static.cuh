@@ -83,6 +83,24 @@ struct St {
     static constexpr int CORE = r * I * J * rn;       // floats of core k in the blob
 };
 
+// Column of gate g of first-mode slice i0' in the gate-packed stage-0 layouts (W_0, W_0^T rows, dY_0):
+//   LSTM (G = 4):            i0'*4 + g
+//   GRU  (G = 3), I0' even:  slices are packed in pairs so that FFMA2 lanes carry no padding:
+//                            [r0 z0 r1 z1 | n0 n1 - -] per pair of slices  ("pair packing")
+//   GRU, I0' odd:            i0'*4 + g with the 4th column unused
+template <class S> constexpr bool gru_pairs() { return S::G == 3 && ((S::I[0] / 3) % 2 == 0); }
+template <class S> TT_HD constexpr int gate_col(int i0p, int g) {
+    if (gru_pairs<S>()) {
+        const int p = i0p / 2, e = i0p % 2;
+        return (g < 2) ? p * 8 + e * 2 + g : p * 8 + 4 + e;
+    }
+    return i0p * 4 + g;
+}
+template <class S> TT_HD constexpr bool gate_col_valid(int col) {
+    if (S::G == 4) return true;
+    return gru_pairs<S>() ? (col % 8) < 6 : (col % 4) != 3;
+}
+
 template <class S> constexpr int n_in() { int v = 1; for (int k = 0; k < S::D; ++k) v *= S::J[k]; return v; }
 template <class S> constexpr int n_out() { int v = 1; for (int k = 0; k < S::D; ++k) v *= S::I[k]; return v; }
 
@@ -100,6 +118,10 @@ TTS_DEV void stage_weights_k(const float *__restrict__ cores, float *__restrict_
     constexpr int I0p = T::PACK ? T::I / (T::PACK ? S::G : 1) : 1;
     if (T::K != T::Kraw)         // zero rows of a padded contraction
         for (int e = tid; e < (T::K - T::Kraw) * T::NS; e += NTHR) wsm[WOff<S, k>::v + T::Kraw * T::NS + e] = 0.f;
+    if (k == 0 && S::G == 3) {   // padded gate columns are read as zeros
+        for (int e = tid; e < T::WFLOATS; e += NTHR) wsm[WOff<S, 0>::v + e] = 0.f;
+        __syncthreads();
+    }
     for (int e = tid; e < T::CORE; e += NTHR) {
         const int ap = e % T::rn;
         int t = e / T::rn;
@@ -108,12 +130,9 @@ TTS_DEV void stage_weights_k(const float *__restrict__ cores, float *__restrict_
         const int i = t % T::I;
         const int a = t / T::I;
         int col;
-        if (k == 0 && T::PACK) col = (i % I0p) * 4 + (i / I0p);   // gate index = i / I0p (gates are the high part of i_0)
+        if (k == 0 && T::PACK) col = gate_col<S>(i % I0p, i / I0p);   // gate index = i / I0p (gates are the high part of i_0)
         else col = i * T::r + a;
         wsm[WOff<S, k>::v + (j * T::rn + ap) * T::NS + col] = __ldg(cores + COff<S, k>::v + e);
-    }
-    if (k == 0 && S::G == 3) {   // zero the padded 4th gate column so it can be read harmlessly
-        for (int e = tid; e < T::K * I0p; e += NTHR) wsm[WOff<S, 0>::v + (e / I0p) * T::NS + (e % I0p) * 4 + 3] = 0.f;
     }
     if constexpr (k + 1 < S::D) stage_weights_k<S, k + 1>(cores, wsm, tid);
 }
@@ -242,6 +261,7 @@ template <class S, int R, int TMr_, int TI_, int SK_>
 struct FinMap {
     using T = St<S, 0>;
     static_assert(T::r == 1 && T::I % S::G == 0, "gates must align with the first output mode");
+    static_assert(!gru_pairs<S>() || TI_ % 2 == 0, "GRU pair packing needs an even number of slices per thread");
     static constexpr int TMr = TMr_, TI = TI_, SK = SK_;
     static constexpr int I0p = T::I / S::G;
     static_assert(I0p % TI == 0 && T::Mrow % TMr == 0 && (T::K / 4) % SK == 0, "final tile shape");
@@ -312,7 +332,8 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
 #pragma unroll
                     for (int i = 0; i < TI; ++i) {
                         ffma2(acc2[b][q][i][0], av, w2[i][0]);
-                        ffma2(acc2[b][q][i][1], av, w2[i][1]);
+                        // GRU pair packing: the 4th pair of every slice pair is padding
+                        if (!(gru_pairs<S>() && (i % 2 == 1))) ffma2(acc2[b][q][i][1], av, w2[i][1]);
                     }
                 }
         }
@@ -323,8 +344,18 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
         for (int q = 0; q < TMr; ++q)
 #pragma unroll
             for (int i = 0; i < TI; ++i) {
-                upk2(acc2[b][q][i][0], acc[b][q][i][0], acc[b][q][i][1]);
-                upk2(acc2[b][q][i][1], acc[b][q][i][2], acc[b][q][i][3]);
+                if (gru_pairs<S>()) {
+                    // columns of a slice pair: [r0 z0 | r1 z1 | n0 n1 | - -]; slice i reads pair (i%2) and half of pair 2
+                    const int i0 = i & ~1;
+                    float lo, hi;
+                    upk2(acc2[b][q][i0][i % 2], acc[b][q][i][0], acc[b][q][i][1]);
+                    upk2(acc2[b][q][i0 + 1][0], lo, hi);
+                    acc[b][q][i][2] = (i % 2 == 0) ? lo : hi;
+                    acc[b][q][i][3] = 0.f;
+                } else {
+                    upk2(acc2[b][q][i][0], acc[b][q][i][0], acc[b][q][i][1]);
+                    upk2(acc2[b][q][i][1], acc[b][q][i][2], acc[b][q][i][3]);
+                }
             }
 }
 
@@ -695,7 +726,7 @@ TTS_DEV void stage_weights_t(const float *__restrict__ cores, float *__restrict_
         t /= T::J;
         const int i = t % T::I;
         const int a = t / T::I;
-        const int row = (k == 0 && T::PACK) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
+        const int row = (k == 0 && T::PACK) ? gate_col<S>(i % I0p, i / I0p) : i * T::r + a;
         wt[WTOff<S, k>::v + row * TT_::KST + j * T::rn + ap] = __ldg(cores + COff<S, k>::v + e);
     }
     if constexpr (k + 1 < S::D) stage_weights_t<S, k + 1>(cores, wt, tid);
@@ -736,6 +767,7 @@ struct BdMap {
     static constexpr int ITER = (TT + PER - 1) / PER;
     static_assert(TT % PER == 0 || TT < PER, "bwd-data tile count");
     static_assert(SPLIT == 1 || TT <= PER, "split stages use one tile per thread");
+    static_assert(!(k == 0 && T::PACK) || SPLIT == 1 || S::G == 4, "stage 0 of a GRU chain must not be split");
     static constexpr int CW = TN / SPLIT > 0 ? TN / SPLIT : 1;  // columns kept per thread after the reduce-scatter
     static_assert(SPLIT == 1 || TN % SPLIT == 0, "split must divide the tile columns");
     static constexpr int XCH_FLOATS = (SPLIT > 1) ? (SPLIT - 1) * R * TMr * CW * NTHR : 0;
@@ -796,7 +828,7 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
                     for (int q = 0; q < TMr; ++q) a[b][q] = ld4(dY + b * BSo + rbase[q] + aoff);
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {
-                    if (k == 0 && T::PACK && kk >= S::G) continue;    // padded gate column
+                    if (k == 0 && T::PACK && !gate_col_valid<S>(n4 + kk)) continue;    // padded gate column (k = 0 is never split)
                     f32x2 w2[TN / 2];
 #pragma unroll
                     for (int g = 0; g < NG; ++g) {
@@ -999,7 +1031,7 @@ TTS_DEV void flush_dw(f32x2 (&acc2)[TK][2], float *__restrict__ stg, float *__re
         t /= T::J;
         const int i = t % T::I;
         const int a = t / T::I;
-        const int col = (k == 0 && T::PACK) ? (i % I0p) * 4 + (i / I0p) : i * T::r + a;
+        const int col = (k == 0 && T::PACK) ? gate_col<S>(i % I0p, i / I0p) : i * T::r + a;
         slot[COff<S, k>::v + e] += stg[(j * T::rn + ap) * T::NS + col];
     }
     __syncthreads();
@@ -1349,7 +1381,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                     }
                     // delta_hh -> dY_0 [b][mr][i0'*4 + g]
                     const int mr = h % T0::Mrow, i0p = h / T0::Mrow;
-                    st4(dy0 + b * DY0<S>::BS + mr * DY0<S>::DS + i0p * 4, make_float4(d_hh[0], d_hh[1], d_hh[2], d_hh[3]));
+                    float *dyr = dy0 + b * DY0<S>::BS + mr * DY0<S>::DS;
+                    if (G == 4) {
+                        st4(dyr + i0p * 4, make_float4(d_hh[0], d_hh[1], d_hh[2], d_hh[3]));
+                    } else {
+                        *reinterpret_cast<float2 *>(dyr + gate_col<S>(i0p, 0)) = make_float2(d_hh[0], d_hh[1]);
+                        dyr[gate_col<S>(i0p, 2)] = d_hh[2];
+                    }
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         if (MODE == MODE_RANK1) {
