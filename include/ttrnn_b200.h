@@ -115,6 +115,24 @@ int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const flo
                             float *d_x, float *d_cores, float *d_bias,
                             void *scratch, void *stream);
 
+/* One cell step from the two pre-activation blocks a = W_ih x + b_ih and u = W_hh h + b_hh,
+ * both (B, G*H): the gate math and state update of LSTMCell.forward
+ * (tensorized_rnn/lstm.py:26-32) / GRUCell.forward (tensorized_rnn/gru.py:33-44).  Serves the
+ * module mirror's cell-step mode, i.e. the reference features that need one module call per
+ * timestep: is_naive=True (TTLinearSet, tensorized_rnn/tt_linearset.py:27-38) and
+ * log_grads=True (hooks of tensorized_rnn/lstm.py:35-39,66-80, gru.py:47-48,76-85).
+ * LSTM: h_prev may be NULL; GRU: c_prev / c / dc / dc_prev are ignored. */
+int ttrnn_cell_forward(int32_t cell, int64_t B, int32_t H, const float *a, const float *u,
+                       const float *h_prev, const float *c_prev, float *h, float *c, void *stream);
+/* Backward of one step.  dh / dc may be NULL (= zero).  da, du (B, G*H),
+ * dh_prev (direct term only: GRU dh*z, LSTM zero) and dc_prev are OVERWRITTEN.  dc_total (optional,
+ * LSTM) receives dL/dc_t including the path through h_t = o * tanh(c_t): the value a tensor hook
+ * on the reference's `cy` sees (lstm.py:38-39), which log_grads records. */
+int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, const float *u,
+                        const float *h_prev, const float *c_prev, const float *dh, const float *dc,
+                        float *da, float *du, float *dh_prev, float *dc_prev, float *dc_total,
+                        void *stream);
+
 /* Measurement helpers (bench.py only).
  * ttrnn_ffma_probe: dependent-chain-free FP32 FFMA loop on every SM; writes the
  * number of FLOPs executed to *flops_out (host) and leaves a checksum in sink

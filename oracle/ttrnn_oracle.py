@@ -130,6 +130,49 @@ def ttlinear(cores: Sequence[Tensor], bias: Optional[Tensor], x: Tensor) -> Tens
     return y if bias is None else y + bias
 
 
+def ttlinear_set(gates: Sequence[Tuple[Sequence[Tensor], Optional[Tensor]]], x: Tensor) -> Tensor:
+    """tensorized_rnn/tt_linearset.py:27-38: n_gates independent TTLinear maps ("naive TT"), outputs
+    concatenated column-wise (gate g fills columns [g*H, (g+1)*H))."""
+    return torch.cat([ttlinear(cores, bias, x) for cores, bias in gates], dim=1)
+
+
+def _proj(p: "LayerParams", short: str, x: Tensor) -> Tensor:
+    """ih / hh projection of one layer: concat-gates TTLinear, or the naive per-gate set."""
+    if short + "_gates" in p:
+        return ttlinear_set(p[short + "_gates"], x)
+    return ttlinear(p[short + "_cores"], p[short + "_bias"], x)
+
+
+def av_norm(t: Tensor, average_logs: bool = False) -> Tensor:
+    """tensorized_rnn/rnn_utils.py:217-226: batch mean of ||t_b||^2 (or of its log)."""
+    norms = (t ** 2).sum(list(range(1, t.dim())))
+    if average_logs:
+        norms = torch.log(norms)
+    return norms.mean()
+
+
+class StepLog(object):
+    """What `log_grads=True` records for one state variable of one layer over one minibatch
+    (rnn_utils.py:127-172): per-step activation norms in time order, gradient norms prepended as
+    backward walks the sequence in reverse."""
+
+    def __init__(self):
+        self.act, self.log_act, self.grad, self.log_grad = [], [], [], []
+
+    def forward(self, t: Tensor) -> None:
+        with torch.no_grad():
+            self.act.append(av_norm(t.detach()))
+            self.log_act.append(av_norm(t.detach(), True))
+
+    def backward(self, g: Tensor) -> None:
+        with torch.no_grad():
+            self.grad.insert(0, av_norm(g.detach()))
+            self.log_grad.insert(0, av_norm(g.detach(), True))
+
+    def stacked(self) -> Dict[str, Tensor]:
+        return {k: torch.stack(getattr(self, k)) for k in ("act", "log_act", "grad", "log_grad")}
+
+
 def tt_dense(cores: Sequence[Tensor]) -> Tensor:
     """Densify the stored TT cores into the (M x N) matrix W (test helper).
 
@@ -163,7 +206,7 @@ def lstm_cell(p: LayerParams, x: Tensor, h: Tensor, c: Tensor) -> Tuple[Tensor, 
     Gate order i, f, g, o; both the ih and the hh TTLinear carry a bias.
     """
     hid = h.shape[1]
-    gates = ttlinear(p["ih_cores"], p["ih_bias"], x) + ttlinear(p["hh_cores"], p["hh_bias"], h)
+    gates = _proj(p, "ih", x) + _proj(p, "hh", h)
     i = torch.sigmoid(gates[:, :hid])
     f = torch.sigmoid(gates[:, hid:2 * hid])
     g = torch.tanh(gates[:, 2 * hid:3 * hid])
@@ -180,8 +223,8 @@ def gru_cell(p: LayerParams, x: Tensor, h: Tensor) -> Tensor:
     product.
     """
     hid = h.shape[1]
-    a = ttlinear(p["ih_cores"], p["ih_bias"], x)
-    u = ttlinear(p["hh_cores"], p["hh_bias"], h)
+    a = _proj(p, "ih", x)
+    u = _proj(p, "hh", h)
     r = torch.sigmoid(a[:, :hid] + u[:, :hid])
     z = torch.sigmoid(a[:, hid:2 * hid] + u[:, hid:2 * hid])
     n = torch.tanh(a[:, 2 * hid:] + r * u[:, 2 * hid:])
@@ -192,7 +235,8 @@ def gru_cell(p: LayerParams, x: Tensor, h: Tensor) -> Tensor:
 # Sequence loops
 # --------------------------------------------------------------------------
 def lstm_forward(layers: Sequence[LayerParams], x: Tensor,
-                 init_states: Optional[Tuple[Tensor, Tensor]] = None
+                 init_states: Optional[Tuple[Tensor, Tensor]] = None,
+                 logs: Optional[Dict[str, "StepLog"]] = None
                  ) -> Tuple[Tensor, Tuple[Tensor, Tensor]]:
     """tensorized_rnn/lstm.py:101-135.
 
@@ -216,13 +260,22 @@ def lstm_forward(layers: Sequence[LayerParams], x: Tensor,
         for li, p in enumerate(layers):
             h, c = state[li]
             inp, c_new = lstm_cell(p, inp, h, c)
+            if logs is not None:          # lstm.py:35-39, 66-80 (log_grads hooks)
+                hl = logs.setdefault("hidden_%d" % li, StepLog())
+                cl = logs.setdefault("cell_%d" % li, StepLog())
+                hl.forward(inp)
+                cl.forward(c_new)
+                if inp.requires_grad:
+                    inp.register_hook(hl.backward)
+                    c_new.register_hook(cl.backward)
             state[li] = (inp, c_new)
         outputs[:, t, :] = inp                      # lstm.py:133 (in-place write)
     return outputs, (inp, c_new)
 
 
 def gru_forward(layers: Sequence[LayerParams], x: Tensor,
-                init_states: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+                init_states: Optional[Tensor] = None,
+                logs: Optional[Dict[str, "StepLog"]] = None) -> Tuple[Tensor, Tensor]:
     """tensorized_rnn/gru.py:104-136 (same loop shape as the LSTM, no cell state)."""
     batch, seq_len, _ = x.shape
     hid = _hidden_size(layers[0])
@@ -235,13 +288,19 @@ def gru_forward(layers: Sequence[LayerParams], x: Tensor,
         inp = x[:, t, :]
         for li, p in enumerate(layers):
             inp = gru_cell(p, inp, state[li])
+            if logs is not None:          # gru.py:47-48, 76-85
+                hl = logs.setdefault("hidden_%d" % li, StepLog())
+                hl.forward(inp)
+                if inp.requires_grad:
+                    inp.register_hook(hl.backward)
             state[li] = inp
         outputs[:, t, :] = inp                      # gru.py:134
     return outputs, inp
 
 
 def _hidden_size(p: LayerParams) -> int:
-    return int(np.prod([int(c.shape[2]) for c in p["hh_cores"]]))
+    cores = p["hh_gates"][0][0] if "hh_gates" in p else p["hh_cores"]
+    return int(np.prod([int(c.shape[2]) for c in cores]))
 
 
 # --------------------------------------------------------------------------
@@ -255,27 +314,38 @@ def layers_from_state_dict(sd: Dict[str, Tensor], num_layers: int, dtype=None,
     `cell{l}.input_weights.parameters.{k}`, `cell{l}.input_weights.bias`, and
     the same under `hidden_weights`.
     """
+    def grab(prefix):
+        cores = []
+        k = 0
+        while "%s.parameters.%d" % (prefix, k) in sd:
+            t = sd["%s.parameters.%d" % (prefix, k)].detach().clone().contiguous()
+            if dtype is not None:
+                t = t.to(dtype)
+            cores.append(t.requires_grad_(requires_grad))
+            k += 1
+        bias = None
+        if prefix + ".bias" in sd:
+            bias = sd[prefix + ".bias"].detach().clone()
+            if dtype is not None:
+                bias = bias.to(dtype)
+            bias = bias.requires_grad_(requires_grad)
+        return cores, bias
+
     layers: List[LayerParams] = []
     for li in range(num_layers):
         p: LayerParams = {}
         for short, long in (("ih", "input_weights"), ("hh", "hidden_weights")):
-            cores = []
-            k = 0
-            while "cell%d.%s.parameters.%d" % (li, long, k) in sd:
-                t = sd["cell%d.%s.parameters.%d" % (li, long, k)].detach().clone().contiguous()
-                if dtype is not None:
-                    t = t.to(dtype)
-                cores.append(t.requires_grad_(requires_grad))
-                k += 1
-            p[short + "_cores"] = cores
-            bkey = "cell%d.%s.bias" % (li, long)
-            if bkey in sd:
-                b = sd[bkey].detach().clone()
-                if dtype is not None:
-                    b = b.to(dtype)
-                p[short + "_bias"] = b.requires_grad_(requires_grad)
+            base = "cell%d.%s" % (li, long)
+            if base + ".gates.0.parameters.0" in sd:
+                # naive form (tt_linearset.py): `gates.{g}` (the same tensors are also listed as `gate{g}`)
+                gates = []
+                g = 0
+                while "%s.gates.%d.parameters.0" % (base, g) in sd:
+                    gates.append(grab("%s.gates.%d" % (base, g)))
+                    g += 1
+                p[short + "_gates"] = gates
             else:
-                p[short + "_bias"] = None
+                p[short + "_cores"], p[short + "_bias"] = grab(base)
         layers.append(p)
     return layers
 
@@ -285,9 +355,11 @@ def flat_params(layers: Sequence[LayerParams]) -> List[Tensor]:
     out: List[Tensor] = []
     for p in layers:
         for short in ("ih", "hh"):
-            out += list(p[short + "_cores"])
-            if p[short + "_bias"] is not None:
-                out.append(p[short + "_bias"])
+            pairs = p[short + "_gates"] if short + "_gates" in p else [(p[short + "_cores"], p[short + "_bias"])]
+            for cores, bias in pairs:
+                out += list(cores)
+                if bias is not None:
+                    out.append(bias)
     return out
 
 

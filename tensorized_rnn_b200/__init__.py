@@ -8,9 +8,10 @@ TT-matrix contractions and BPTT run in hand-written CUDA kernels behind the C AB
 from .shapes import auto_shape, tt_shape
 from .tensor_train import TensorTrain, transpose
 from .initializers import glorot_initializer, random_matrix, matrix_with_random_cores
-from .layers import TTLinear
+from .layers import TTLinear, TTLinearSet
+from .rnn_utils import ActivGradLogger, av_norm
 from .rnn import TTLSTM, TTLSTMCell, TTGRU, TTGRUCell, param_count
 
 __all__ = ["auto_shape", "tt_shape", "TensorTrain", "transpose", "glorot_initializer", "random_matrix",
-           "matrix_with_random_cores", "TTLinear", "TTLSTM", "TTLSTMCell", "TTGRU", "TTGRUCell", "param_count"]
+           "matrix_with_random_cores", "TTLinear", "TTLinearSet", "ActivGradLogger", "av_norm", "TTLSTM", "TTLSTMCell", "TTGRU", "TTGRUCell", "param_count"]
 __version__ = "0.1.0"

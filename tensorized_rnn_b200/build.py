@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libttrnn_b200.so")
 SOURCES = ["ttrnn_capi.cu", "tt_static_inst.cu"]
-HEADERS = ["tt_plan.h", "tt_stage.cuh", "tt_kernels.cuh", "tt_static.cuh", "tt_static_api.h",
+HEADERS = ["tt_plan.h", "tt_stage.cuh", "tt_kernels.cuh", "tt_cell.cuh", "tt_static.cuh", "tt_static_api.h",
            os.path.join("..", "..", "include", "ttrnn_b200.h")]
 
 NVCC_FLAGS = [
@@ -42,6 +42,20 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+# headers each translation unit includes (an up-to-date object file is not recompiled)
+TU_DEPS = {
+    "ttrnn_capi.cu": HEADERS,
+    "tt_static_inst.cu": ["tt_plan.h", "tt_static.cuh", "tt_static_api.h", os.path.join("..", "..", "include", "ttrnn_b200.h")],
+}
+
+
+def _obj_stale(src: str, obj: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in [src] + TU_DEPS[src])
+
+
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -50,6 +64,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     for src in SOURCES:
         obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
+        if not force and os.environ.get("TTRNN_NVCC_EXTRA") is None and not _obj_stale(src, obj):
+            continue
         extra = os.environ.get("TTRNN_NVCC_EXTRA", "").split()
         cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

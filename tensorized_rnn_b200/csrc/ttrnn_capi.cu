@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "tt_kernels.cuh"
+#include "tt_cell.cuh"
 #include "tt_static.cuh"
 #include "tt_static_api.h"
 
@@ -968,6 +969,54 @@ int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const flo
         return 1;
     if (reduce_partials(part, used, slot, 0, p.core_floats, d_cores, st)) return 1;
     if (d_bias && reduce_partials(part, used, slot, p.core_floats, p.n_out, d_bias, st)) return 1;
+    return 0;
+}
+
+// ---- stand-alone cell step (cell-step mode: is_naive / log_grads) -------------------------------
+static int cell_args_ok(int cell, int64_t B, int H) {
+    if (cell != TTRNN_CELL_LSTM && cell != TTRNN_CELL_GRU) return fail("unknown cell kind %d", cell);
+    if (B < 1 || H < 1) return fail("batch and hidden_size must be >= 1");
+    return 0;
+}
+
+int ttrnn_cell_forward(int32_t cell, int64_t B, int32_t H, const float *a, const float *u, const float *h_prev,
+                       const float *c_prev, float *h, float *c, void *stream) {
+    if (cell_args_ok(cell, B, H)) return 1;
+    const bool lstm = cell == TTRNN_CELL_LSTM;
+    if (!a || !u || !h || (lstm ? (!c_prev || !c) : !h_prev)) return fail("ttrnn_cell_forward: null operand");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    CellStepArgs p;
+    memset(&p, 0, sizeof p);
+    p.B = B; p.H = H; p.a = a; p.u = u; p.h_prev = h_prev; p.c_prev = c_prev; p.h = h; p.c = c;
+    long long blocks = (B * (long long)H + 255) / 256;
+    if (blocks > (long long)dv.sms * 8) blocks = (long long)dv.sms * 8;
+    if (lstm) k_cell_fwd<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else k_cell_fwd<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, const float *u, const float *h_prev,
+                        const float *c_prev, const float *dh, const float *dc, float *da, float *du,
+                        float *dh_prev, float *dc_prev, float *dc_total, void *stream) {
+    if (cell_args_ok(cell, B, H)) return 1;
+    const bool lstm = cell == TTRNN_CELL_LSTM;
+    if (!a || !u || !da || !du || !dh_prev || (lstm ? (!c_prev || !dc_prev) : !h_prev))
+        return fail("ttrnn_cell_backward: null operand");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    CellStepArgs p;
+    memset(&p, 0, sizeof p);
+    p.B = B; p.H = H; p.a = a; p.u = u; p.h_prev = h_prev; p.c_prev = c_prev; p.dh = dh; p.dc = dc;
+    p.da = da; p.du = du; p.dh_prev = dh_prev; p.dc_prev = dc_prev; p.dc_total = dc_total;
+    long long blocks = (B * (long long)H + 255) / 256;
+    if (blocks > (long long)dv.sms * 8) blocks = (long long)dv.sms * 8;
+    if (lstm) k_cell_bwd<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else k_cell_bwd<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
     return 0;
 }
 

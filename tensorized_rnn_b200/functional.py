@@ -223,3 +223,65 @@ class _TTLinearFunction(torch.autograd.Function):
 def ttlinear(shape: _lib.TTShape, n_in: int, n_out: int, x: torch.Tensor, bias: Optional[torch.Tensor],
              cores: Sequence[torch.Tensor]) -> torch.Tensor:
     return _TTLinearFunction.apply(shape, n_in, n_out, x, bias, *cores)
+
+
+class _CellStepFunction(torch.autograd.Function):
+    """Gate math + state update of ONE timestep from the two pre-activation blocks (cell-step mode:
+    is_naive / log_grads).  Reference: lstm.py:26-32, gru.py:33-44; backward = SURVEY.md 8a-10."""
+
+    @staticmethod
+    def forward(ctx, cell: str, c_grad_hook, a, u, h_prev, c_prev):
+        lib = _lib.load()
+        for name, t in (("input projection", a), ("hidden projection", u), ("hx", h_prev)):
+            _require_cuda_f32(name, t)
+        lstm = cell == "lstm"
+        if lstm:
+            _require_cuda_f32("cx", c_prev)
+        B, H = h_prev.shape
+        G = 4 if lstm else 3
+        if tuple(a.shape) != (B, G * H) or tuple(u.shape) != (B, G * H):
+            raise ValueError("gate blocks must be (%d, %d), got %s and %s" % (B, G * H, tuple(a.shape), tuple(u.shape)))
+        a, u, h_prev = a.contiguous(), u.contiguous(), h_prev.contiguous()
+        c_prev = c_prev.contiguous() if lstm else None
+        with torch.cuda.device(a.device):
+            h = torch.empty_like(h_prev)
+            c = torch.empty_like(h_prev) if lstm else None
+            stream = torch.cuda.current_stream(a.device).cuda_stream
+            _lib.check(lib.ttrnn_cell_forward(_lib.CELL_LSTM if lstm else _lib.CELL_GRU, B, H, _ptr(a), _ptr(u),
+                                              _ptr(h_prev), _ptr(c_prev), _ptr(h), _ptr(c), stream),
+                       "ttrnn_cell_forward")
+        ctx.cell, ctx.c_grad_hook = cell, c_grad_hook
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(a, u, h_prev, c_prev)
+        return (h, c) if lstm else h
+
+    @staticmethod
+    def backward(ctx, *grads):
+        lib = _lib.load()
+        a, u, h_prev, c_prev = ctx.saved_tensors
+        lstm = ctx.cell == "lstm"
+        dh = grads[0]
+        dc = grads[1] if lstm else None
+        B, H = h_prev.shape
+        dh = None if dh is None else dh.contiguous()
+        dc = None if dc is None else dc.contiguous()
+        with torch.cuda.device(a.device):
+            da, du = torch.empty_like(a), torch.empty_like(u)
+            dh_prev = torch.empty_like(h_prev)
+            dc_prev = torch.empty_like(h_prev) if lstm else None
+            dc_total = torch.empty_like(h_prev) if (lstm and ctx.c_grad_hook is not None) else None
+            stream = torch.cuda.current_stream(a.device).cuda_stream
+            _lib.check(lib.ttrnn_cell_backward(_lib.CELL_LSTM if lstm else _lib.CELL_GRU, B, H, _ptr(a), _ptr(u),
+                                               _ptr(h_prev), _ptr(c_prev), _ptr(dh), _ptr(dc), _ptr(da), _ptr(du),
+                                               _ptr(dh_prev), _ptr(dc_prev), _ptr(dc_total), stream),
+                       "ttrnn_cell_backward")
+        if dc_total is not None:
+            ctx.c_grad_hook(dc_total)      # total dL/dc_t, as a tensor hook on the reference's `cy` sees it
+        return None, None, da, du, (None if lstm else dh_prev), dc_prev
+
+
+def cell_step(cell: str, a: torch.Tensor, u: torch.Tensor, h_prev: torch.Tensor,
+              c_prev: Optional[torch.Tensor] = None, c_grad_hook=None):
+    """One LSTM / GRU step from a = W_ih x + b_ih and u = W_hh h + b_hh.  LSTM -> (h, c); GRU -> h.
+    `c_grad_hook(grad)` (LSTM) is called during backward with the total gradient of c_t."""
+    return _CellStepFunction.apply(cell, c_grad_hook, a, u, h_prev, c_prev)

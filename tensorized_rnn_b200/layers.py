@@ -71,3 +71,32 @@ class TTLinear(nn.Module):
         y = ttlinear(shape, self.in_features_total, self.out_features_total, x.reshape(-1, x.shape[-1]),
                      self.bias, list(self.weight_t.tt_cores))
         return y.reshape(*lead, self.out_features_total)
+
+
+class TTLinearSet(nn.Module):
+    """n_gates independent TTLinear maps whose outputs are concatenated column-wise: the "naive TT"
+    weight of reference tensorized_rnn/tt_linearset.py:5-38 (constructor signature, sub-module names
+    `gate{i}` / `gates.{i}` and so the state_dict keys are the reference's).  Each gate runs the
+    batched TT-matvec CUDA kernels; the concatenation is a plain copy."""
+
+    def __init__(self, in_features=None, out_features=None, n_gates=4, bias=True, init=None, shape=None,
+                 auto_shapes=True, d=3, tt_rank=8, auto_shape_mode='ascending',
+                 auto_shape_criterion='entropy'):
+        super(TTLinearSet, self).__init__()
+        self.n_gates = n_gates
+        self.in_features = in_features
+        self.out_features = out_features
+        gates = []
+        for i in range(n_gates):
+            cur_gate = TTLinear(in_features=in_features, out_features=out_features,
+                                bias=bias, auto_shapes=auto_shapes, d=d, tt_rank=tt_rank,
+                                init=init, shape=shape, auto_shape_mode=auto_shape_mode,
+                                auto_shape_criterion=auto_shape_criterion)
+            setattr(self, 'gate{}'.format(i), cur_gate)
+            gates.append(cur_gate)
+        self.gates = nn.ModuleList(gates)
+
+    def forward(self, x):
+        batch_size, in_size = x.size()
+        assert in_size == self.in_features
+        return torch.cat([gate(x) for gate in self.gates], dim=1)

@@ -7,9 +7,15 @@ final state of the last layer) follow reference tensorized_rnn/tt_lstm.py:6-62,
 tensorized_rnn/lstm.py:44-135 and tensorized_rnn/gru.py:52-194.  The time loop, the TT
 contractions and the gate math run in the CUDA library (one call per sequence).
 
-Not in this round (raise NotImplementedError instead of silently diverging):
-  * is_naive=True  (TTLinearSet, reference tt_linearset.py)   -- SURVEY.md section 8f-3
-  * log_grads=True (per-step hooks, reference rnn_utils.py:42-215) -- SURVEY.md section 8f-2
+Two execution modes, chosen per module:
+  * fused (default): one C-ABI call per sequence -> persistent recurrent CUDA kernels;
+  * cell-step: one cell call per (timestep, layer), as the reference's Python loop does
+    (lstm.py:123-133), used when the reference feature needs per-step module calls:
+    `is_naive=True` (one TT matrix per gate, tt_linearset.py:5-38; the gate blocks come from
+    G batched TT-matvec kernel calls and a fused gate kernel, `ttrnn_cell_forward/backward`) and
+    `log_grads=True` (forward hooks on the cells + tensor hooks on h_t / c_t feeding
+    `ActivGradLogger`, rnn_utils.py:42-215; each step is then one fused single-step call).
+  `new_core='first'/'last'` (rnn_utils.py:29-34) only changes the TT shapes and runs in either mode.
 """
 from __future__ import annotations
 
@@ -19,7 +25,9 @@ import torch
 from torch import nn
 
 from .functional import RnnSpec, rnn_sequence
-from .layers import TTLinear
+from .functional import cell_step
+from .layers import TTLinear, TTLinearSet
+from .rnn_utils import ActivGradLogger
 from .shapes import tt_shape
 
 
@@ -35,9 +43,6 @@ class _TTCellBase(nn.Module):
 
     def __init__(self, input_size, hidden_size, bias, device, n_cores, tt_rank, is_naive=False, new_core=None):
         super().__init__()
-        if is_naive:
-            raise NotImplementedError("is_naive=True (one TT matrix per gate) is not implemented in "
-                                      "tensorized_rnn_b200 yet; use the concat-gates form (is_naive=False)")
         assert new_core in [None, 'first', 'last']
         self.input_size = input_size
         self.hidden_size = hidden_size
@@ -51,7 +56,15 @@ class _TTCellBase(nn.Module):
         self.input_weights = self._create_input_hidden_weights()
         self.hidden_weights = self._create_hidden_hidden_weights()
 
+    # bias of the per-gate TTLinears of the naive form: the reference gives the TT-LSTM gates none
+    # (tt_lstm.py:20,33) and the TT-GRU gates `self.bias` (gru.py:152,165)
+    naive_bias_follows_flag = False
+
     def _tt_linear(self, in_features):
+        if self.is_naive:
+            return TTLinearSet(in_features=in_features, out_features=self.hidden_size, n_gates=self.n_gate,
+                               bias=(self.bias if self.naive_bias_follows_flag else False), auto_shapes=True,
+                               d=self.n_cores, tt_rank=self.tt_rank).to(self.device)
         shape = tt_shape(in_features, self.hidden_size, self.n_cores, self.n_gate, new_core=self.new_core)
         return TTLinear(out_features=self.n_gate * self.hidden_size, shape=shape, bias=self.bias,
                         auto_shapes=False, d=self.n_cores, tt_rank=self.tt_rank).to(self.device)
@@ -63,17 +76,21 @@ class _TTCellBase(nn.Module):
         return self._tt_linear(self.hidden_size)
 
     def flat_parameters(self) -> List[torch.Tensor]:
-        """Parameters in C-ABI blob order: ih cores, ih bias, hh cores, hh bias."""
+        """Parameters in C-ABI blob order: ih cores, ih bias, hh cores, hh bias (naive form: gate by gate)."""
         out: List[torch.Tensor] = []
-        for lin in (self.input_weights, self.hidden_weights):
-            out += list(lin.weight_t.tt_cores)
-            if lin.bias is not None:
-                out.append(lin.bias)
+        for w in (self.input_weights, self.hidden_weights):
+            for lin in (list(w.gates) if self.is_naive else [w]):
+                out += list(lin.weight_t.tt_cores)
+                if lin.bias is not None:
+                    out.append(lin.bias)
         return out
 
     def _single_step_spec(self) -> RnnSpec:
-        return RnnSpec(self.cell_kind, self.input_size, self.hidden_size, self.input_weights.bias is not None,
-                       [self.input_weights.tt_modes()], [self.hidden_weights.tt_modes()])
+        if getattr(self, "_step_spec", None) is None:
+            self._step_spec = RnnSpec(self.cell_kind, self.input_size, self.hidden_size,
+                                      self.input_weights.bias is not None,
+                                      [self.input_weights.tt_modes()], [self.hidden_weights.tt_modes()])
+        return self._step_spec
 
 
 class TTLSTMCell(_TTCellBase):
@@ -82,18 +99,36 @@ class TTLSTMCell(_TTCellBase):
     cell_kind = "lstm"
 
     def forward(self, input, hx, cx):
-        out, h, c = rnn_sequence(self._single_step_spec(), input.unsqueeze(1), hx, cx, self.flat_parameters())
-        return h, c
+        hooked = hasattr(self, '_h_backward_hook')
+        if self.is_naive or hooked:
+            # two projections + the fused gate kernel.  The c_t hook of log_grads (reference lstm.py:35-39)
+            # must see dL/dc_t INCLUDING the path through h_t = o*tanh(c_t), which is internal to the gate
+            # kernel, so the kernel's backward hands that total to the hook.
+            hy, cy = cell_step("lstm", self.input_weights(input), self.hidden_weights(hx), hx, cx,
+                               c_grad_hook=getattr(self, '_c_backward_hook', None))
+            if hooked and hy.requires_grad:
+                assert hasattr(self, '_c_backward_hook')
+                assert cy.requires_grad
+                hy.register_hook(self._h_backward_hook)
+        else:
+            out, hy, cy = rnn_sequence(self._single_step_spec(), input.unsqueeze(1), hx, cx, self.flat_parameters())
+        return hy, cy
 
 
 class TTGRUCell(_TTCellBase):
     """One TT-GRU cell (reference gru.py:139-172; step semantics gru.py:25-50)."""
     n_gate = 3
     cell_kind = "gru"
+    naive_bias_follows_flag = True
 
     def forward(self, input, hx):
-        out, h = rnn_sequence(self._single_step_spec(), input.unsqueeze(1), hx, None, self.flat_parameters())
-        return h
+        if self.is_naive:
+            hy = cell_step("gru", self.input_weights(input), self.hidden_weights(hx), hx)
+        else:
+            out, hy = rnn_sequence(self._single_step_spec(), input.unsqueeze(1), hx, None, self.flat_parameters())
+        if hasattr(self, '_h_backward_hook') and hy.requires_grad:      # reference gru.py:47-48
+            hy.register_hook(self._h_backward_hook)
+        return hy
 
 
 class _TTRNNBase(nn.Module):
@@ -104,9 +139,6 @@ class _TTRNNBase(nn.Module):
                  is_naive=False, log_grads=False, new_core=None):
         assert new_core in [None, 'first', 'last']
         super().__init__()
-        if log_grads:
-            raise NotImplementedError("log_grads=True (per-timestep activation/gradient hooks) is not implemented "
-                                      "in tensorized_rnn_b200 yet: the fused sequence kernel has no per-step modules")
         self.n_cores = n_cores
         self.tt_rank = tt_rank
         self.is_naive = is_naive
@@ -123,6 +155,27 @@ class _TTRNNBase(nn.Module):
             setattr(self, 'cell{}'.format(i), cell)
             self._all_layers.append(cell)
         self._spec: Optional[RnnSpec] = None
+        if log_grads:
+            self._install_loggers()
+
+    def _install_loggers(self):
+        """Per-layer loggers + hooks (reference lstm.py:66-80, gru.py:76-85): forward hooks on the cell
+        modules, tensor-level backward hooks handed to the cells."""
+        for i, cell in enumerate(self._all_layers):
+            h_logger = ActivGradLogger("hidden_{}".format(i))
+            h_forward, h_backward = h_logger.create_hooks(0)
+            cell.register_forward_hook(h_forward)
+            cell._h_backward_hook = h_backward
+            if self.cell_kind == "lstm":
+                c_logger = ActivGradLogger("cell_{}".format(i))
+                c_forward, c_backward = c_logger.create_hooks(1)
+                cell.register_forward_hook(c_forward)
+                cell._c_backward_hook = c_backward
+
+    @property
+    def cell_step_mode(self) -> bool:
+        """True when every (timestep, layer) is a separate cell call (is_naive / log_grads)."""
+        return bool(self.is_naive or self.log_grads)
 
     def _make_cell(self, in_size):
         return self.cell_cls(in_size, self.hidden_size, self.bias, self.device, n_cores=self.n_cores,
@@ -176,9 +229,32 @@ class TTLSTM(_TTRNNBase):
         """input (batch, seq_len, input_size) -> outputs (batch, seq_len, hidden), (h_T, c_T) of the last layer.
         `init_states` = (h0, c0), each (batch, hidden), shared by every layer; None = zeros."""
         self._check_input(input)
+        if self.cell_step_mode:
+            return self._forward_cell_steps(input, init_states)
         h0, c0 = (None, None) if init_states is None else init_states
         out, h, c = rnn_sequence(self.spec(), input, h0, c0, self.flat_parameters())
         return out, (h, c)
+
+    def _forward_cell_steps(self, input, init_states):
+        """The reference's own loop (lstm.py:116-135): step-major, layer-minor, one shared initial state.
+        Outputs are stacked at the end instead of written in place, which spares autograd the
+        reference's T CopySlices nodes; values are identical."""
+        batch_size, seq_len, _ = input.size()
+        if init_states is None:
+            h = torch.zeros(batch_size, self.hidden_size, device=input.device)
+            c = torch.zeros(batch_size, self.hidden_size, device=input.device)
+        else:
+            h, c = init_states
+        internal_state = [(h, c)] * self.num_layers
+        outputs = []
+        for step in range(seq_len):
+            x = input[:, step, :]
+            for i, cell in enumerate(self._all_layers):
+                (h, c) = internal_state[i]
+                x, new_c = cell(x, h, c)
+                internal_state[i] = (x, new_c)
+            outputs.append(x)
+        return torch.stack(outputs, dim=1), (x, new_c)
 
 
 class TTGRU(_TTRNNBase):
@@ -192,5 +268,21 @@ class TTGRU(_TTRNNBase):
     def forward(self, input, init_states=None):
         """input (batch, seq_len, input_size) -> outputs (batch, seq_len, hidden), h_T of the last layer."""
         self._check_input(input)
+        if self.cell_step_mode:
+            return self._forward_cell_steps(input, init_states)
         out, h = rnn_sequence(self.spec(), input, init_states, None, self.flat_parameters())
         return out, h
+
+    def _forward_cell_steps(self, input, init_states):
+        """The reference's own loop (gru.py:119-136)."""
+        batch_size, seq_len, _ = input.size()
+        h = torch.zeros(batch_size, self.hidden_size, device=input.device) if init_states is None else init_states
+        internal_state = [h] * self.num_layers
+        outputs = []
+        for step in range(seq_len):
+            x = input[:, step, :]
+            for i, cell in enumerate(self._all_layers):
+                x = cell(x, internal_state[i])
+                internal_state[i] = x
+            outputs.append(x)
+        return torch.stack(outputs, dim=1), x

@@ -77,11 +77,7 @@ def test_new_core_variants_build_with_reference_shapes():
     assert tuple(m.cell0.hidden_weights.weight_t.tt_cores[0].shape) == (1, 3, 1, 2)
 
 
-def test_unsupported_options_fail_loudly():
-    with pytest.raises(NotImplementedError):
-        quiet(tr.TTLSTM, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2, is_naive=True)
-    with pytest.raises(NotImplementedError):
-        quiet(tr.TTGRU, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2, log_grads=True)
+def test_invalid_options_fail_loudly():
     with pytest.raises(AssertionError):
         quiet(tr.TTGRU, 4, 8, 1, torch.device("cpu"), n_cores=2, tt_rank=2, new_core="middle")
 
