@@ -13,7 +13,9 @@ Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA event
 step, L2 flushed between steps, max over ranks); `e2e` = the same pass through the public module
 API from pinned HOST input with the H2D copy and a D2H read of the result inside the timed region;
 `roofline` = the dominant kernel against the FP32 FFMA peak measured live by an FFMA probe kernel
-(MEASURED_PEAKS.json carries no FP32 figure); `cpu_baseline` = the CPU oracle (a restatement of the
+(MEASURED_PEAKS.json carries no FP32 figure), in ALGORITHMIC FLOPs of the reference's core-by-core
+sweep (where the engine contracts the ih projection in the cheaper dense order it executes fewer
+FLOPs than credited; `roofline.ih_projection` lists both costs per layer); `cpu_baseline` = the CPU oracle (a restatement of the
 reference's PyTorch path; the reference itself cannot travel to the GPU box) timed on the host
 cores on a bounded sample.  `--impl reference` times that CPU path alone.
 """
@@ -379,6 +381,17 @@ def main():
                 traffic = ent["dram_bytes_per_launch"]
         except Exception:
             traffic = None
+        # contraction order the engine chose for each layer's batched ih projection (0 = TT chain, 1 = dense
+        # W_ih formed once per call, 2 = rank-one input): the roofline figures above always credit the
+        # reference's core-by-core sweep; where the dense order is cheaper the kernels execute
+        # FEWER multiply-adds than credited, so both costs are reported
+        routes = []
+        desc = model.spec().desc(B, T)
+        for l in range(cfg["L"]):
+            cm, dm = C.c_int64(0), C.c_int64(0)
+            rt = int(lib.ttrnn_rnn_ih_route(C.byref(desc), l, C.byref(cm), C.byref(dm)))
+            routes.append({"layer": l, "route": {0: "tt_chain", 1: "dense", 2: "rank_one"}.get(rt, str(rt)),
+                           "chain_macs_per_row": cm.value, "dense_macs_per_row": dm.value})
         line = {
             "metric": "TT-RNN cell-steps/sec (batch x T), %s" % cfg["mode"],
             "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -395,7 +408,7 @@ def main():
                          "peak_source": "ttrnn_ffma_probe measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
                          "algorithmic_flops_per_seqstep": per_seqstep,
                          "whole_step_tflops_per_gpu": whole, "whole_step_frac": whole / peak if peak else None,
-                         "fwd_flops_per_seqstep": fwd_flops, "kernels": share},
+                         "fwd_flops_per_seqstep": fwd_flops, "kernels": share, "ih_projection": routes},
         }
         if world == 1 and not args.no_cpu_baseline:
             Bs, Ts = CPU_SAMPLE_B[args.config], CPU_SAMPLE_T[args.config]

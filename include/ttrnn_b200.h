@@ -153,12 +153,23 @@ int64_t ttrnn_launch_count(int32_t reset);
 int ttrnn_kernel_timing(int32_t enable);
 int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K_KINDS]*/);
 
+/* Which contraction order the batched ih projection of `layer` uses: 0 = TT chain core by core
+ * (t3nsor/ops.py:81-90), 1 = dense route (W_ih formed once per call from the cores, then one dense
+ * FP32 contraction per row; chosen when I*G*H <= dense_ih_ratio % of the chain's multiply-adds),
+ * 2 = rank-one input mode (I = 1).  Also reports both costs per row.  < 0 on a malformed desc. */
+int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row,
+                       int64_t *dense_macs_per_row);
+
 /* Tuning knobs (process-wide; also read from the environment at load time):
  *   "rows_per_cta"  batch rows owned by one CTA of the recurrent kernels (0 = auto)
  *   "chunk_steps"   timesteps per ih-projection chunk (0 = auto, bounded by memory)
  *   "chunk_bytes"   byte budget of one ih-projection chunk (default 4 GiB)
  *   "static_kernels" 0 = always use the runtime-shape kernels
  *   "static_rows_fwd" / "static_rows_bwd"  force the rows-per-CTA variant of the static kernels
+ *   "save_u_bytes"  budget for keeping only the hh pre-activations (G*H floats per row and step) so that
+ *                   backward skips the final stage of the chain recompute (default 16 GiB; 0 = recompute)
+ *   "dense_ih"      0 = never take the dense route of the ih projection (default 1)
+ *   "dense_ih_ratio" dense route allowed while I*G*H * 100 <= chain multiply-adds * ratio (default 130)
  *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of
  *                   recomputing them (default 0 = recompute)
  * returns 0 if the key is known. */

@@ -51,6 +51,7 @@ SYMBOLS = {
     "ttrnn_ttlinear_backward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 8),
     "ttrnn_cell_forward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 7),
     "ttrnn_cell_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 12),
+    "ttrnn_rnn_ih_route": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ttrnn_ffma_probe": (C.c_int, [C.c_int32, _P, C.POINTER(C.c_double), _P]),
     "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
     "ttrnn_kernel_timing": (C.c_int, [C.c_int32]),
@@ -81,7 +82,8 @@ def load() -> C.CDLL:
         raise RuntimeError("tensorized_rnn_b200: ABI version mismatch between %s and the Python binding" % _LIB_PATH)
     for key, env in (("rows_per_cta", "TTRNN_ROWS_PER_CTA"), ("chunk_steps", "TTRNN_CHUNK_STEPS"),
                      ("chunk_bytes", "TTRNN_CHUNK_BYTES"), ("static_rows_fwd", "TTRNN_STATIC_ROWS_FWD"),
-                     ("static_rows_bwd", "TTRNN_STATIC_ROWS_BWD"), ("static_kernels", "TTRNN_STATIC_KERNELS")):
+                     ("static_rows_bwd", "TTRNN_STATIC_ROWS_BWD"), ("static_kernels", "TTRNN_STATIC_KERNELS"),
+                     ("dense_ih", "TTRNN_DENSE_IH"), ("dense_ih_ratio", "TTRNN_DENSE_IH_RATIO")):
         if os.environ.get(env):
             lib.ttrnn_set_option(key.encode(), int(os.environ[env]))
     _lib = lib

@@ -1157,9 +1157,15 @@ TTS_DEV void flush_all(DwRegs<S, R, TB> &dw, float *stg, float *slot, int tid) {
     if constexpr (k + 1 < S::D) flush_all<S, R, TB, k + 1>(dw, stg, slot, tid);
 }
 
-template <class S, int CELL, int R, int MODE, class TB, bool DWI = true, bool SAVED = false>
+// SV = 0: recompute the whole chain;  SV = 1: forward kept X_0 and the hh pre-activations (two-core chains);
+// SV = 2: forward kept only the hh pre-activations u (G*H floats per row and step): stages d-1..1 are
+//         recomputed (their X_k feed the core gradients) but the final stage, its reduce-scatter and two
+//         barriers are skipped -- for two-core chains that is 60 % of the recomputed multiply-adds
+template <class S, int CELL, int R, int MODE, class TB, bool DWI = true, int SV = 0>
 __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
+    constexpr bool SAVED = (SV == 1), SAVEU = (SV != 0);
     static_assert(!SAVED || (S::D == 2 && DWI), "saved-activation backward is implemented for two-core chains");
+    static_assert(!SAVEU || DWI, "kept pre-activations need the fused backward");
     extern __shared__ __align__(16) float smem[];
     using SM = BwdSmem<S, R, TB, DWI>;
     static_assert(DWI || (CELL == TTRNN_CELL_LSTM && MODE == MODE_XG),
@@ -1260,7 +1266,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
         };
         auto fetch_regs = [&](int tl) {                   // operands of local step tl
             const int tgl = a.t0 + tl;
-            if (SAVED) {
+            if (SAVEU) {
 #pragma unroll
                 for (int b = 0; b < R; ++b)
 #pragma unroll
@@ -1310,7 +1316,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         xin[b][n][g] = xin_n[b][n][g];
-                        if (SAVED) pre[b][n][g] = pre_n[b][n][g];      // chain outputs kept by the forward kernel
+                        if (SAVEU) pre[b][n][g] = pre_n[b][n][g];      // chain outputs kept by the forward kernel
                     }
                     cprev[b][n] = cprev_n[b][n];
                     dho[b][n] = dho_n[b][n];
@@ -1322,9 +1328,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 fetch_h(smem + (((t - 1) & 1) ? HOFF1 : HOFF0), tg - 1);
                 fetch_regs(t - 1);
             }
-            if constexpr (!SAVED) {
-                // ---- recompute the hh chain keeping every X_k
-                fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
+            // ---- recompute the hh chain keeping every X_k
+            if constexpr (!SAVED) fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
+            if constexpr (!SAVEU) {
                 float acc[R][FM::TMr][FM::TI][4];
                 final_partial<S, R, FM>((S::D == 1) ? hcur : xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg,
                                         kh, acc);

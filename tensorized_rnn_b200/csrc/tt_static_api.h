@@ -28,7 +28,7 @@ struct TtsRnnBwdEntry {
     const char *name;
     int cell, mode, R;
     int split;                                                               // 1: core gradients come from a batched kernel
-    int saved;                                                               // 1: consumes X_0 / pre-activations kept by forward
+    int saved;                                                               // 1: consumes X_0 + hh pre-activations kept by forward, 2: pre-activations only
     size_t smem;
     long long slot_floats;                                                   // floats per gradient slot
     bool (*match)(const ttrnn_tt_shape *hh);

@@ -79,12 +79,12 @@ const TtsRnnFwdEntry kFwd[] = {
 };
 
 
-template <class S, int CELL, int R, int MODE, class TB, bool DWI, bool SV = false>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0>
 int launch_bwd(const tts::RnnBwdSArgs *a, int grid, cudaStream_t st) {
     tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
-template <class S, int CELL, int R, int MODE, class TB, bool DWI, bool SV = false>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0>
 int prepare_bwd(int *occ) {
     auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB, DWI>::BYTES);
@@ -99,8 +99,12 @@ constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * 
      &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true>, &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true>}
 #define TTS_BWD_SAVED(S, CELL, R, MODE, ...)                                                                \
     {#S "(saved)", CELL, MODE, R, 0, 1, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(),      \
-     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true, true>,                                \
-     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true, true>}
+     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 1>,                                   \
+     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 1>}
+#define TTS_BWD_SAVEU(S, CELL, R, MODE, ...)                                                                \
+    {#S "(kept u)", CELL, MODE, R, 0, 2, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(),     \
+     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 2>,                                   \
+     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 2>}
 #define TTS_BWD_SPLIT(S, CELL, R, MODE, ...)                                                                \
     {#S "(split)", CELL, MODE, R, 1, 0, tts::BwdSmem<S, R, __VA_ARGS__, false>::BYTES, slot_floats<S>(),     \
      &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false>,                                     \
@@ -128,6 +132,12 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD_SAVED(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVED(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVED(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
+    TTS_BWD_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),

@@ -11,6 +11,7 @@
 
 #include "tt_kernels.cuh"
 #include "tt_cell.cuh"
+#include "tt_gemm.cuh"
 #include "tt_static.cuh"
 #include "tt_static_api.h"
 
@@ -26,6 +27,13 @@ std::atomic<long long> g_opt_srows_fwd{0}, g_opt_srows_bwd{0};
 // budget for kept chain activations (0 = always recompute).  Off by default: measured on cfg2 it trades
 // +0.9 ms forward (X_0 stores) for -1.2 ms backward and costs 9 GB, a 1.6 % net gain.
 std::atomic<long long> g_opt_save_bytes{0};
+// budget for keeping only the hh pre-activations u (G*H floats per row and step) so that backward skips the
+// final stage of the chain recompute (measured on cfg2: see profiles/)
+std::atomic<long long> g_opt_save_u_bytes{16LL << 30};
+// dense route of the batched ih projection (tt_gemm.cuh): used when I*G*H <= ratio% of the chain's
+// multiply-adds per row (and the shape fits the GEMM tiles); 0 disables
+std::atomic<long long> g_opt_dense_ih{1};
+std::atomic<long long> g_opt_dense_ratio{130};
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
 struct TimedLaunch { int kind; cudaEvent_t a, b; };
@@ -253,6 +261,31 @@ int build_rnn_plan(const ttrnn_rnn_desc *d, RnnPlan *rp) {
     return 0;
 }
 
+// ---- dense route of the batched ih projection (tt_gemm.cuh) -------------------------------------
+constexpr int kDenseMaxSplit = 40;
+
+long long chain_macs(const ChainPlan &p) {
+    long long m = 0;
+    for (int k = 0; k < p.d; ++k) m += (long long)p.st[k].Mrow * p.st[k].K * p.st[k].N;
+    return m;
+}
+// forward / recompute / dW^T all need: G*H % 128 == 0, I % 4 == 0
+bool dense_ih_ok(const ChainPlan &ih) {
+    if (!g_opt_dense_ih.load()) return false;
+    if (ih.n_out % ttg::BN != 0 || ih.n_in % 4 != 0 || ih.n_in < 4 || ih.n_in > 2048) return false;
+    return (long long)ih.n_in * ih.n_out * 100 <= chain_macs(ih) * g_opt_dense_ratio.load();
+}
+// dX = delta * W additionally needs I % 128 == 0
+bool dense_ih_bwd_ok(const ChainPlan &ih, bool want_dx) { return dense_ih_ok(ih) && (!want_dx || ih.n_in % ttg::BN == 0); }
+
+struct DenseIh {
+    float *eye, *wt, *w, *dwt, *dbias, *part, *pbias;
+};
+long long dense_fwd_floats(const ChainPlan &ih) { return r4((long long)ih.n_in * ih.n_in) + r4((long long)ih.n_in * ih.n_out); }
+long long dense_bwd_floats(const ChainPlan &ih) {
+    const long long wn = r4((long long)ih.n_in * ih.n_out);
+    return r4((long long)ih.n_in * ih.n_in) + 3 * wn + r4(ih.n_out) + kDenseMaxSplit * (wn + r4(ih.n_out));
+}
 // ---- workspace layout --------------------------------------------------------------------
 struct RnnLayout {
     int Tc = 0;                 // timesteps per chunk
@@ -261,13 +294,13 @@ struct RnnLayout {
     // saved (floats)
     long long sv_hs = 0, sv_cs = 0, sv_total = 0;
     // fwd scratch (floats)
-    long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_aux = 0, f_total = 0;
+    long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_aux = 0, f_dense = 0, f_total = 0;
     // bwd scratch (floats)
-    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_total = 0;
+    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_dense = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
     int nslots = 0;
     // kept chain activations (two-core static chains, within the save_bytes budget): per layer offsets into `saved`
-    bool save_on[TTRNN_MAX_LAYERS] = {};
+    int save_mode[TTRNN_MAX_LAYERS] = {};
     long long sv_x0[TTRNN_MAX_LAYERS] = {}, sv_u[TTRNN_MAX_LAYERS] = {}, x0f[TTRNN_MAX_LAYERS] = {};
 };
 
@@ -289,26 +322,32 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->sv_hs = 0;
     lo->sv_cs = r4((L - 1) * lo->BTH);
     lo->sv_total = lo->sv_cs + (lstm ? r4(L * lo->BTH) : 0);
-    if (g_opt_static.load() && g_opt_save_bytes.load() > 0) {
-        long long extra = 0;
+    // kept activations of the static recurrent kernels, per layer:
+    //   mode 1 (two-core chains, "save_bytes" budget, off by default): X_0 tiles + hh pre-activations u
+    //   mode 2 ("save_u_bytes" budget, default 16 GiB): u only -- backward skips the final stage of the recompute
+    if (g_opt_static.load()) {
+        long long extra1 = 0, extra2 = 0;
+        int mode1[TTRNN_MAX_LAYERS] = {}, mode2[TTRNN_MAX_LAYERS] = {};
         for (int l = 0; l < L; ++l) {
             const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
             const TtsRnnFwdEntry *se = tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_fwd.load());
-            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1);
-            if (se && be && se->x0_floats > 0) {
-                lo->save_on[l] = true;
+            if (!se) continue;
+            if (se->x0_floats > 0 && tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1)) {
+                mode1[l] = 1;
                 lo->x0f[l] = se->x0_floats;
-                extra += r4(B * T * se->x0_floats) + r4(B * T * GH);
+                extra1 += r4(B * T * se->x0_floats) + r4(B * T * GH);
+            }
+            if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 2)) {
+                mode2[l] = 1;
+                extra2 += r4(B * T * GH);
             }
         }
-        if (extra * 4 > g_opt_save_bytes.load()) {
-            for (int l = 0; l < L; ++l) lo->save_on[l] = false;
-        } else {
-            for (int l = 0; l < L; ++l)
-                if (lo->save_on[l]) {
-                    lo->sv_x0[l] = lo->sv_total; lo->sv_total += r4(B * T * lo->x0f[l]);
-                    lo->sv_u[l] = lo->sv_total;  lo->sv_total += r4(B * T * GH);
-                }
+        const bool use1 = extra1 > 0 && extra1 * 4 <= g_opt_save_bytes.load();
+        const bool use2 = !use1 && extra2 > 0 && extra2 * 4 <= g_opt_save_u_bytes.load();
+        for (int l = 0; l < L; ++l) {
+            lo->save_mode[l] = (use1 && mode1[l]) ? 1 : ((use2 && mode2[l]) ? 2 : 0);
+            if (lo->save_mode[l] == 1) { lo->sv_x0[l] = lo->sv_total; lo->sv_total += r4(B * T * lo->x0f[l]); }
+            if (lo->save_mode[l] != 0) { lo->sv_u[l] = lo->sv_total; lo->sv_total += r4(B * T * GH); }
         }
     }
     // forward scratch
@@ -318,6 +357,13 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->f_sc = o; o += r4(lo->BH);
     lo->f_hs = o; o += (L > 1 ? 2 * r4(lo->BTH) : 0);     // used only when nothing is saved
     lo->f_aux = o; o += r4(GH) + 4;                       // rank-one input mode: dense W_ih column + a 1.0f
+    long long dfw = 0, dbw = 0;                           // dense ih route: identity, W^T (+ W, dW^T, split partials)
+    for (int l = 0; l < L; ++l)
+        if (dense_ih_ok(rp.layer[l].ih)) {
+            if (dense_fwd_floats(rp.layer[l].ih) > dfw) dfw = dense_fwd_floats(rp.layer[l].ih);
+            if (dense_bwd_floats(rp.layer[l].ih) > dbw) dbw = dense_bwd_floats(rp.layer[l].ih);
+        }
+    lo->f_dense = o; o += dfw;
     lo->f_total = o;
     // backward scratch
     long long maxp = 0;
@@ -348,6 +394,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     }
     lo->b_spill = o; o += r4(spill) * lo->nslots;
     lo->b_aux = o; o += 2 * r4(GH) + 4;                   // rank-one input mode: W_ih column, its gradient, a 1.0f
+    lo->b_dense = o; o += dbw;
     lo->b_total = o;
     return 0;
 }
@@ -469,6 +516,96 @@ int axpy1(const float *src, float *dst, long long n, int accumulate, cudaStream_
     return 0;
 }
 
+// ---- dense route: launch helpers ----------------------------------------------------------------
+void dense_carve(float *base, const ChainPlan &ih, bool bwd, DenseIh *D) {
+    const long long wn = r4((long long)ih.n_in * ih.n_out);
+    D->eye = base; base += r4((long long)ih.n_in * ih.n_in);
+    D->wt = base; base += wn;
+    D->w = D->dwt = D->dbias = D->part = D->pbias = nullptr;
+    if (!bwd) return;
+    D->w = base; base += wn;
+    D->dwt = base; base += wn;
+    D->dbias = base; base += r4(ih.n_out);
+    D->part = base; base += kDenseMaxSplit * wn;
+    D->pbias = base;
+}
+
+// W^T (I x G*H): the TT matvec applied to the rows of the identity; optionally W (G*H x I) as well
+int dense_prepare(const ChainPlan &ih, const ttrnn_tt_shape *shape, const DevInfo &dv, const float *cores, DenseIh &D,
+                  bool need_w, cudaStream_t st) {
+    const int I = ih.n_in, GH = ih.n_out;
+    ttg::k_eye<<<(I * I + 255) / 256 > 1024 ? 1024 : (I * I + 255) / 256, 256, 0, st>>>(D.eye, I);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    if (launch_ttlinear_fwd(ih, dv, I, I, D.eye, 0, cores, nullptr, nullptr, D.wt, 0, st, shape)) return 1;
+    if (need_w) {
+        dim3 grid((GH + 31) / 32, (I + 31) / 32);
+        ttg::k_transpose<<<grid, 256, 0, st>>>(D.wt, D.w, I, GH);
+        ++g_launches;
+        CU_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+// C[r, :] = A[r, :] * B (+ bias + bias2) over ragged rows (time-chunk views)
+int dense_rows_gemm(int kind, long long rows, int rpb, const float *a, long long a_bstride, int K, const float *b, int N,
+                    const float *bias, const float *bias2, float *c, long long c_bstride, cudaStream_t st) {
+    if (rows < 1 || rows > 0x7fffffffLL) return fail("dense ih projection: row count out of range");
+    ttg::GemmRowsArgs g;
+    memset(&g, 0, sizeof g);
+    g.rows = (unsigned)rows; g.K = K; g.N = N;
+    g.a.p = a; g.a.bstride = a_bstride; g.a.rpb = rpb; g.a.ld = K;
+    g.b = b; g.ldb = N; g.bias = bias; g.bias2 = bias2;
+    g.c.p = c; g.c.bstride = c_bstride; g.c.rpb = rpb; g.c.ld = N;
+    const long long tiles = ((rows + 127) / 128) * (N / ttg::BN);
+    if (tiles > 0x7fffffffLL) return fail("dense ih projection: too many tiles");
+    {
+        KernelTimer tm(kind, st);
+        ttg::k_gemm_rows<8><<<(unsigned)tiles, ttg::NT, 0, st>>>(g);
+    }
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// dwt (I x G*H) (+)= X^T delta over the rows of one chunk; dbias (G*H) (+)= column sums of delta
+int dense_dw(const DevInfo &dv, long long rows, int rpb, const float *x, long long x_bstride, int I, const float *delta,
+             long long d_bstride, int GH, DenseIh &D, bool accumulate, bool want_bias, cudaStream_t st) {
+    if (rows < 1 || rows > 0x7fffffffLL) return fail("dense ih backward: row count out of range");
+    const int TMsel = (I <= 64) ? 4 : 8;
+    const int BM = 16 * TMsel;
+    const int tiles = ((I + BM - 1) / BM) * (GH / ttg::BN);
+    // two CTAs per SM are resident: size the split so that the grid fills whole waves (2 waves if possible)
+    long long nsplit = (4LL * dv.sms) / tiles;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > kDenseMaxSplit) nsplit = (2LL * dv.sms) / tiles > 0 ? (2LL * dv.sms) / tiles : 1;
+    if (nsplit > kDenseMaxSplit) nsplit = kDenseMaxSplit;
+    if (nsplit > (rows + 255) / 256) nsplit = (rows + 255) / 256;
+    if (nsplit < 1) nsplit = 1;
+    ttg::GemmRedArgs g;
+    memset(&g, 0, sizeof g);
+    g.rows = (unsigned)rows; g.M = I; g.N = GH; g.nsplit = (int)nsplit;
+    g.a.p = x; g.a.bstride = x_bstride; g.a.rpb = rpb; g.a.ld = I;
+    g.b.p = delta; g.b.bstride = d_bstride; g.b.rpb = rpb; g.b.ld = GH;
+    g.part = D.part; g.pbias = want_bias ? D.pbias : nullptr;
+    {
+        KernelTimer tm(TTRNN_K_TTLINEAR_BWD, st);
+        if (TMsel == 4) ttg::k_gemm_red<4><<<(unsigned)(tiles * nsplit), ttg::NT, 0, st>>>(g);
+        else ttg::k_gemm_red<8><<<(unsigned)(tiles * nsplit), ttg::NT, 0, st>>>(g);
+    }
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    const long long wn = (long long)I * GH;
+    ttg::k_sum_splits<<<(unsigned)((wn / 4 + 255) / 256), 256, 0, st>>>(D.part, (int)nsplit, wn, wn, D.dwt, accumulate ? 1 : 0);
+    ++g_launches;
+    if (want_bias) {
+        ttg::k_sum_splits<<<(unsigned)((GH / 4 + 255) / 256), 256, 0, st>>>(D.pbias, (int)nsplit, GH, GH, D.dbias, accumulate ? 1 : 0);
+        ++g_launches;
+    }
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -515,9 +652,23 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "chunk_bytes")) { g_opt_chunk_bytes.store(value > 0 ? value : (4LL << 30)); return 0; }
     if (!strcmp(key, "static_kernels")) { g_opt_static.store(value); return 0; }
     if (!strcmp(key, "save_bytes")) { g_opt_save_bytes.store(value); return 0; }
+    if (!strcmp(key, "save_u_bytes")) { g_opt_save_u_bytes.store(value); return 0; }
     if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
     if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
+    if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
+    if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
     return 1;
+}
+
+int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row, int64_t *dense_macs_per_row) {
+    RnnPlan rp;
+    if (build_rnn_plan(desc, &rp)) return -1;
+    if (layer < 0 || layer >= desc->num_layers) { fail("layer %d out of range", layer); return -1; }
+    const ChainPlan &ih = rp.layer[layer].ih;
+    if (chain_macs_per_row) *chain_macs_per_row = chain_macs(ih);
+    if (dense_macs_per_row) *dense_macs_per_row = (int64_t)ih.n_in * ih.n_out;
+    if (layer == 0 && desc->input_size == 1) return 2;
+    return dense_ih_ok(ih) ? 1 : 0;
 }
 
 int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc) {
@@ -573,6 +724,23 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
         const float *b_ih = d->has_bias ? params + lp.off_ih_bias : nullptr;
         const float *b_hh = d->has_bias ? params + lp.off_hh_bias : nullptr;
 
+        // ---- batched ih projection of one time chunk: xg[b, t, :] = W_ih x[b, t0+t, :] + b_ih (+ b_hh for LSTM),
+        // through the TT chain or, when that is the cheaper contraction order, through dense W_ih^T
+        const bool dense = dense_ih_ok(lp.ih) && !(l == 0 && d->input_size == 1);
+        DenseIh D;
+        if (dense) {
+            dense_carve(sc + lo.f_dense, lp.ih, false, &D);
+            if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, false, st)) return 1;
+        }
+        auto project = [&](int t0, int tc) -> int {
+            if (dense)
+                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
+                                       D.wt, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st);
+            return launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                       params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
+                                       &d->ih[l]);
+        };
+
         // ---- statically specialised kernel for this hh shape, if one is registered -------------------
         const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
         const TtsRnnFwdEntry *se = g_opt_static.load() ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_fwd.load()) : nullptr;
@@ -605,10 +773,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
             for (int t0 = 0; t0 < T; t0 += chunk) {
                 const int tc = (T - t0 < chunk) ? T - t0 : chunk;
                 if (mode == tts::MODE_XG) {
-                    if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                            params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg,
-                                            (long long)tc * GH, st, &d->ih[l]))
-                        return 1;
+                    if (project(t0, tc)) return 1;
                     sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
                 } else {
                     sa.x1 = lin + t0; sa.x1_bstride = T;
@@ -619,8 +784,10 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
                 sa.c_in = first ? c0 : st_c;
                 sa.out = lout + (long long)t0 * H; sa.out_bstride = (long long)T * H;
                 sa.c_save = csave ? csave + (long long)t0 * H : nullptr;
-                if (sv && lo.save_on[l] && se->x0_floats == lo.x0f[l]) {
+                if (sv && lo.save_mode[l] == 1 && se->x0_floats == lo.x0f[l]) {
                     sa.x0_save = sv + lo.sv_x0[l] + (long long)t0 * lo.x0f[l]; sa.x0_bstride = (long long)T * lo.x0f[l];
+                }
+                if (sv && lo.save_mode[l] != 0) {
                     sa.u_save = sv + lo.sv_u[l] + (long long)t0 * GH;          sa.u_bstride = (long long)T * GH;
                 }
                 sa.h_out = (last && l == L - 1 && hT) ? hT : st_h;
@@ -654,11 +821,8 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
 
         for (int t0 = 0; t0 < T; t0 += lo.Tc) {
             const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
-            // (1) batched ih projection of the chunk: xg[b, t, :] = W_ih x[b, t0+t, :] + b_ih (+ b_hh for LSTM)
-            if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
-                                    &d->ih[l]))
-                return 1;
+            // (1) batched ih projection of the chunk
+            if (project(t0, tc)) return 1;
             // (2) persistent recurrence over the chunk
             const bool first = (t0 == 0), last = (t0 + tc == T);
             a.steps = tc;
@@ -715,12 +879,55 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
         const float *b_ih = d->has_bias ? params + lp.off_ih_bias : nullptr;
         const float *b_hh = d->has_bias ? params + lp.off_hh_bias : nullptr;
 
-        // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
+        // ---- ih projection (recompute) and its backward per time chunk: TT chain or dense route ---------
         const int mode = (l == 0 && d->input_size == 1 && !d_x) ? tts::MODE_RANK1 : tts::MODE_XG;
+        const bool dense = mode == tts::MODE_XG && dense_ih_bwd_ok(lp.ih, dlin != nullptr);
+        DenseIh D;
+        if (dense) {
+            dense_carve(sc + lo.b_dense, lp.ih, true, &D);
+            if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, dlin != nullptr, st)) return 1;
+        }
+        bool dense_first = true;
+        auto project = [&](int t0, int tc) -> int {
+            if (dense)
+                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
+                                       D.wt, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st);
+            return launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                       params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
+                                       &d->ih[l]);
+        };
+        // xg holds delta_ih of the chunk: core / bias gradients (accumulated over chunks) and dX
+        auto project_bwd = [&](int t0, int tc, int *ih_used) -> int {
+            if (dense) {
+                if (dense_dw(dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin, xg, (long long)tc * GH, GH,
+                             D, !dense_first, d->has_bias != 0, st))
+                    return 1;
+                dense_first = false;
+                if (dlin)
+                    return dense_rows_gemm(TTRNN_K_TTLINEAR_BWD, B * tc, tc, xg, (long long)tc * GH, GH, D.w, nin, nullptr,
+                                           nullptr, dlin + (long long)t0 * nin, (long long)T * nin, st);
+                return 0;
+            }
+            return launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
+                                       params + lp.off_ih_cores, xg, (long long)tc * GH,
+                                       dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
+                                       lo.nslots, sc + lo.b_spill, 1, st, ih_used, &d->ih[l]);
+        };
+        // after the last chunk: dense dW^T -> TT cores (I-row TT-matvec backward on the identity), bias copy
+        auto project_finish = [&](int *ih_used) -> int {
+            if (!dense) return 0;
+            if (launch_ttlinear_bwd(lp.ih, dv, nin, nin, D.eye, 0, params + lp.off_ih_cores, D.dwt, 0, nullptr, 0, part_ih,
+                                    lo.nslots, sc + lo.b_spill, 0, st, ih_used, &d->ih[l]))
+                return 1;
+            return 0;
+        };
+
+        // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
         const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load()) : nullptr;
-        if (be && lo.save_on[l] && sv) {
-            // forward kept X_0 and the hh pre-activations of this layer: use the kernel that consumes them
-            if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1))
+        if (be && lo.save_mode[l] != 0 && sv) {
+            // forward kept (X_0 and) the hh pre-activations of this layer: use the kernel that consumes them
+            if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(),
+                                                            lo.save_mode[l]))
                 be = bs;
         }
         if (be) {
@@ -745,10 +952,8 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             sa.cores = params + lp.off_hh_cores;
             sa.hs = lout; sa.cs = lcs; sa.h0 = h0; sa.c0 = c0; sa.dhs = dhs;
             sa.partial = be->split ? nullptr : part_hh;
-            if (be->saved) {
-                sa.x0_save = sv + lo.sv_x0[l]; sa.x0_bstride = (long long)T * lo.x0f[l];
-                sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * GH;
-            }
+            if (be->saved == 1) { sa.x0_save = sv + lo.sv_x0[l]; sa.x0_bstride = (long long)T * lo.x0f[l]; }
+            if (be->saved != 0) { sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * GH; }
             float *aux = sc + lo.b_aux;
             float *aux_g = aux + r4(GH);
             float *one = aux_g + r4(GH);
@@ -777,10 +982,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     const int t0 = ci * lo.Tc;
                     const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
                     const bool last = (t0 + tc == T);
-                    if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                            params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
-                                            &d->ih[l]))
-                        return 1;
+                    if (project(t0, tc)) return 1;
                     sa.t0 = t0; sa.steps = tc;
                     sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
                     sa.dh_in = last ? (l == L - 1 ? d_hT : nullptr) : sdh;
@@ -806,12 +1008,9 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                             if (h0 && hh_dw(h0, H, xg, B, 1)) return 1;
                         }
                     }
-                    if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                            params + lp.off_ih_cores, xg, (long long)tc * GH,
-                                            dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
-                                            lo.nslots, sc + lo.b_spill, 1, st, &ih_used, &d->ih[l]))
-                        return 1;
+                    if (project_bwd(t0, tc, &ih_used)) return 1;
                 }
+                if (project_finish(&ih_used)) return 1;
             }
             // fold the per-CTA slots into the gradient blob
             const long long cf = lp.hh.core_floats;
@@ -834,7 +1033,11 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             } else {
                 if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
                 if (d->has_bias) {
-                    if (reduce_partials(part_ih, ih_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) return 1;
+                    if (dense) {
+                        if (axpy1(D.dbias, d_params + lp.off_ih_bias, GH, 0, st)) return 1;
+                    } else if (reduce_partials(part_ih, ih_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) {
+                        return 1;
+                    }
                     if (lstm) {
                         if (axpy1(d_params + lp.off_ih_bias, d_params + lp.off_hh_bias, GH, 0, st)) return 1;
                     } else {
@@ -877,10 +1080,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
             const bool last = (t0 + tc == T);
             // (1) recompute the ih projection of the chunk
-            if (launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                    params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
-                                    &d->ih[l]))
-                return 1;
+            if (project(t0, tc)) return 1;
             // (2) reverse-time recurrence: xg <- delta_ih, hh core grads, dh/dc carried across chunks
             a.t0 = t0; a.steps = tc;
             a.xg = xg; a.xg_bstride = (long long)tc * GH;
@@ -894,17 +1094,18 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             ++g_launches;
             CU_CHECK(cudaGetLastError());
             // (3) ih backward over the chunk: core grads, bias grad, gradient wrt the layer input
-            if (launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
-                                    params + lp.off_ih_cores, xg, (long long)tc * GH,
-                                    dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
-                                    lo.nslots, sc + lo.b_spill, 1, st, &ih_slots_used, &d->ih[l]))
-                return 1;
+            if (project_bwd(t0, tc, &ih_slots_used)) return 1;
         }
+        if (project_finish(&ih_slots_used)) return 1;
         // (4) fold the per-CTA partials into the gradient blob
         if (reduce_partials(part_hh, grid, hh_slot, 0, lp.hh.core_floats, d_params + lp.off_hh_cores, st)) return 1;
         if (reduce_partials(part_ih, ih_slots_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
         if (d->has_bias) {
-            if (reduce_partials(part_ih, ih_slots_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) return 1;
+            if (dense) {
+                if (axpy1(D.dbias, d_params + lp.off_ih_bias, GH, 0, st)) return 1;
+            } else if (reduce_partials(part_ih, ih_slots_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) {
+                return 1;
+            }
             if (lstm) {
                 if (axpy1(d_params + lp.off_ih_bias, d_params + lp.off_hh_bias, GH, 0, st)) return 1;
             } else {

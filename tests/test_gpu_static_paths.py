@@ -107,30 +107,65 @@ def test_static_kernels_match_oracle(case):
 
 
 def test_saved_activation_backward_matches_recompute():
-    """`save_bytes` > 0: forward keeps X_0 and the hh pre-activations of two-core chains, backward consumes
-    them instead of recomputing the chain.  Gradients must agree with the recompute path."""
+    """Three backward variants of the static BPTT kernel must agree: full recompute (both budgets 0), kept
+    hh pre-activations only (`save_u_bytes`, the default: backward skips the final stage of the recompute) and
+    kept X_0 + pre-activations (`save_bytes`, two-core chains)."""
     dev = torch.device("cuda:0")
     lib = _lib.load()
-    for cell, cls in (("gru", tr.TTGRU), ("lstm", tr.TTLSTM)):
+    cases = [("gru", tr.TTGRU, 1, 256, 1, 2, 4), ("lstm", tr.TTLSTM, 1, 256, 1, 2, 4), ("lstm", tr.TTLSTM, 40, 256, 2, 3, 8)]
+    for cell, cls, I, H, L, d, r in cases:
         torch.manual_seed(21)
-        m = quiet(cls, 1, 256, 1, torch.device("cpu"), n_cores=2, tt_rank=4).to(dev)
-        x = torch.rand(19, 23, 1, device=dev)
+        m = quiet(cls, I, H, L, torch.device("cpu"), n_cores=d, tt_rank=r).to(dev)
+        x = torch.rand(19, 23, I, device=dev)
         res = []
-        for budget in (0, 1 << 30):
-            lib.ttrnn_set_option(b"save_bytes", budget)
+        for save_all, save_u in ((0, 0), (0, 1 << 30), (1 << 30, 0)):
+            lib.ttrnn_set_option(b"save_bytes", save_all)
+            lib.ttrnn_set_option(b"save_u_bytes", save_u)
             try:
                 for p in m.parameters():
                     p.grad = None
-                r = m(x)
-                out = r[0]
-                h = r[1][0] if cell == "lstm" else r[1]
+                rr = m(x)
+                out = rr[0]
+                h = rr[1][0] if cell == "lstm" else rr[1]
                 (out.sum() + 3 * h.sum()).backward()
                 res.append((out.detach().clone(), [p.grad.clone() for p in m.parameters()]))
             finally:
                 lib.ttrnn_set_option(b"save_bytes", 0)
-        assert torch.equal(res[0][0], res[1][0])
+                lib.ttrnn_set_option(b"save_u_bytes", 16 << 30)
+        for other in res[1:]:
+            assert torch.equal(res[0][0], other[0])
+            for a, b in zip(res[0][1], other[1]):
+                assert rel_err(b, a) <= GRAD_TOL
+
+
+def test_dense_and_tt_chain_ih_routes_agree():
+    """The batched ih projection contracted core by core (dense_ih = 0) and through the densified W_ih
+    (dense_ih = 1, the default where it is cheaper) are the same map: outputs and every gradient must agree,
+    including dX of inner layers and the TT-core gradients obtained by projecting the dense gradient."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    for cell, cls, I, H, L, d, r in (("lstm", tr.TTLSTM, 40, 256, 3, 3, 8), ("gru", tr.TTGRU, 28, 256, 2, 4, 16)):
+        torch.manual_seed(33)
+        m = quiet(cls, I, H, L, torch.device("cpu"), n_cores=d, tt_rank=r).to(dev)
+        desc = m.spec().desc(11, 13)
+        routes = [lib.ttrnn_rnn_ih_route(ctypes.byref(desc), l, None, None) for l in range(L)]
+        assert all(rt == 1 for rt in routes), routes
+        x = torch.rand(11, 13, I, device=dev)
+        w = torch.randn(11, 13, H, device=dev)
+        res = []
+        for flag in (1, 0):
+            lib.ttrnn_set_option(b"dense_ih", flag)
+            try:
+                for p in m.parameters():
+                    p.grad = None
+                rr = m(x)
+                ((rr[0] * w).sum()).backward()
+                res.append((rr[0].detach().clone(), [p.grad.clone() for p in m.parameters()]))
+            finally:
+                lib.ttrnn_set_option(b"dense_ih", 1)
+        assert rel_err(res[0][0], res[1][0]) <= FWD_TOL
         for a, b in zip(res[0][1], res[1][1]):
-            assert rel_err(b, a) <= GRAD_TOL
+            assert rel_err(a, b) <= GRAD_TOL
 
 
 def test_static_and_runtime_shape_kernels_agree():
