@@ -168,6 +168,8 @@ int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain
  *   "static_rows_fwd" / "static_rows_bwd"  force the rows-per-CTA variant of the static kernels
  *   "save_u_bytes"  budget for keeping only the hh pre-activations (G*H floats per row and step) so that
  *                   backward skips the final stage of the chain recompute (default 16 GiB; 0 = recompute)
+ *   "row_plan"      0 = one kernel variant per BPTT launch (default 1: a tail variant with fewer rows per
+ *                   CTA may run the rows that do not fill a whole wave)
  *   "dense_ih"      0 = never take the dense route of the ih projection (default 1)
  *   "dense_ih_ratio" dense route allowed while I*G*H * 100 <= chain multiply-adds * ratio (default 130)
  *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of

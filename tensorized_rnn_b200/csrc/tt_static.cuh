@@ -35,7 +35,27 @@ TTS_DEV void cp_async16(float *smem_dst, const float *gsrc) {
     unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
 }
+TTS_DEV void cp_async4(float *smem_dst, const float *gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
 TTS_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// Rank-one input mode: the scalar inputs x[b, t] of a CTA's R rows are staged in shared memory in windows
+// of XW timesteps (cp.async, double-buffered) instead of being carried in registers one step ahead: the
+// recurrent kernels run at the 255-register limit and the compiler was spilling those prefetch registers,
+// which turned every prefetch into a synchronous wait on its own load (ncu: STL stalled on long scoreboard).
+constexpr int XW = 32;
+template <int R>
+TTS_DEV void x1_fetch_window(float *__restrict__ dst, const float *__restrict__ x1, long long bstride, long long row0,
+                             long long B, int steps, int w, int tid) {
+    for (int e = tid; e < R * XW; e += NTHR) {
+        const int b = e / XW, j = e % XW;
+        const int tl = w * XW + j;
+        if (row0 + b < B && tl < steps) cp_async4(dst + e, x1 + (row0 + b) * bstride + tl);
+        else dst[e] = 0.f;
+    }
+}
 
 // Packed FP32x2 FMA (Blackwell FFMA2): c.lo += a*w.lo, c.hi += a*w.hi with a scalar `a` operand.  Same FLOP
 // rate as FFMA (measured 74.1 vs 72.5 TFLOP/s, tools/ffma2_probe.cu) for half the issue slots, which is what
@@ -375,15 +395,14 @@ TTS_DEV void final_reduce(float (&acc)[R][FM::TMr][FM::TI][4], float (&pre)[R][F
             const int owner = e % SK;                    // compile-time after unrolling
             const int n = e / SK;
             const int q = e / TI, i = e % TI;
+            // this thread is the dlt-th partner of `owner`, dlt = (kh - owner) mod SK (warp-uniform; 0 = it owns e):
+            // one uniform branch per element, the slot index only enters the address
+            const int dlt = (kh - owner + SK) % SK;
+            if (dlt != 0) {
+                float4 *dst = x4 + ((dlt - 1) * NE * R + n * R) * NTHR + owner * PER + tprime;
 #pragma unroll
-            for (int dlt = 1; dlt < SK; ++dlt) {
-                // this thread is the dlt-th partner of `owner` iff (kh - owner) mod SK == dlt
-                if (((kh - owner + SK) % SK) == dlt) {
-#pragma unroll
-                    for (int b = 0; b < R; ++b)
-                        x4[((dlt - 1) * NE * R + n * R + b) * NTHR + owner * PER + tprime] =
-                            make_float4(acc[b][q][i][0], acc[b][q][i][1], acc[b][q][i][2], acc[b][q][i][3]);
-                }
+                for (int b = 0; b < R; ++b)
+                    dst[b * NTHR] = make_float4(acc[b][q][i][0], acc[b][q][i][1], acc[b][q][i][2], acc[b][q][i][3]);
             }
         }
         __syncthreads();
@@ -491,7 +510,8 @@ struct FwdSmem {
     }
     static constexpr int P = pfloats(), Q = qfloats();
     static constexpr int XCH = FM::XCH_FLOATS;
-    static constexpr int TOTAL = W + HS + P + Q + XCH;
+    static constexpr int X1W = 2 * R * XW;               // rank-one input windows
+    static constexpr int TOTAL = W + HS + P + Q + XCH + X1W;
     static constexpr size_t BYTES = (size_t)TOTAL * 4;
 };
 
@@ -515,7 +535,7 @@ struct RnnFwdSArgs {
     // step so that backward does not recompute the chain.  Row b, step t at  base + b*bstride + t*per_step.
     float *x0_save;          // per step: Mrow_0 * K_0 floats (unpadded rows)
     long long x0_bstride;
-    float *u_save;           // per step: G*H floats
+    float *u_save;           // per step: 4*H floats: the gate activations (LSTM i,f,g,o; GRU r,z,n and u_n)
     long long u_bstride;
 };
 
@@ -551,6 +571,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
     float *P = hs + SM::HS;
     float *Q = P + SM::P;
     float *xch = Q + SM::Q;
+    float *xw1 = xch + SM::XCH;
 
     stage_weights_k<S, 0>(a.cores, wsm, tid);
 
@@ -591,11 +612,15 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                 cst[b][n] = (LSTM && ok && a.c_in) ? __ldg(a.c_in + (row0 + b) * H + hid[n]) : 0.f;
                 hpr[b][n] = (ok && a.h_in) ? __ldg(a.h_in + (row0 + b) * H + hid[n]) : 0.f;
             }
+        if (MODE == MODE_RANK1) {
+            x1_fetch_window<R>(xw1, a.x1, a.x1_bstride, row0, a.B, a.steps, 0, tid);
+            cp_async_wait_all();
+        }
         __syncthreads();
 
         // operands of the gate phase are fetched one step ahead (the loads of step t+1 are issued at the top
-        // of step t and land while the chain of step t runs)
-        float xin_n[R][NE][4], x1_n[R];
+        // of step t and land while the chain of step t runs); rank-one inputs come from the shared windows
+        float xin_n[R][NE][4];
         auto fetch_in = [&](int tl) {
             if (MODE == MODE_XG) {
 #pragma unroll
@@ -606,10 +631,6 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                         for (int g = 0; g < G; ++g)
                             xin_n[b][n][g] = (row0 + b < a.B)
                                 ? __ldg(a.xg + (row0 + b) * a.xg_bstride + (long long)tl * GH + g * H + hid[n]) : 0.f;
-            } else {
-#pragma unroll
-                for (int b = 0; b < R; ++b)
-                    x1_n[b] = (row0 + b < a.B) ? __ldg(a.x1 + (row0 + b) * a.x1_bstride + tl) : 0.f;
             }
         };
         fetch_in(0);
@@ -618,12 +639,14 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
             float x1[R];
 #pragma unroll
             for (int b = 0; b < R; ++b) {
-                x1[b] = x1_n[b];
+                x1[b] = (MODE == MODE_RANK1) ? xw1[((t / XW) & 1) * R * XW + b * XW + (t % XW)] : 0.f;
 #pragma unroll
                 for (int n = 0; n < NE; ++n)
 #pragma unroll
                     for (int g = 0; g < 4; ++g) xin[b][n][g] = xin_n[b][n][g];
             }
+            if (MODE == MODE_RANK1 && (t % XW) == 0 && t + XW < a.steps)
+                x1_fetch_window<R>(xw1 + (((t / XW) + 1) & 1) * R * XW, a.x1, a.x1_bstride, row0, a.B, a.steps, t / XW + 1, tid);
             if (t + 1 < a.steps) fetch_in(t + 1);
             // ---- stages d-1 .. 1
             const float *X0 = fwd_chain_pp<S, R, TU, S::D - 1>(hs, P, Q, wsm, tid);
@@ -654,11 +677,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
 #pragma unroll
                     for (int g = 0; g < G; ++g)
                         ain[g] = (MODE == MODE_XG) ? xin[b][n][g] : fmaf(x1[b], weff[n][g], bih[n][g]);
-                    if (a.u_save && row0 + b < a.B) {
-#pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            a.u_save[(row0 + b) * a.u_bstride + (long long)t * GH + g * H + h] = pre[b][n][g];
-                    }
+                    float keep[4];                      // gate activations kept for backward
                     float hnew;
                     if (LSTM) {
                         const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
@@ -668,11 +687,19 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                         const float cn = fg * cst[b][n] + ig * gg;
                         cst[b][n] = cn;
                         hnew = og * tanh_g(cn);
+                        keep[0] = ig; keep[1] = fg; keep[2] = gg; keep[3] = og;
                     } else {
+                        const float un = pre[b][n][2] + bhh[n][2];
                         const float rg = sigmoidf_acc(ain[0] + (pre[b][n][0] + bhh[n][0]));
                         const float zg = sigmoidf_acc(ain[1] + (pre[b][n][1] + bhh[n][1]));
-                        const float ng = tanh_g(ain[2] + rg * (pre[b][n][2] + bhh[n][2]));
+                        const float ng = tanh_g(ain[2] + rg * un);
                         hnew = (1.0f - zg) * ng + zg * hpr[b][n];
+                        keep[0] = rg; keep[1] = zg; keep[2] = ng; keep[3] = un;
+                    }
+                    if (a.u_save && row0 + b < a.B) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g)
+                            a.u_save[(row0 + b) * a.u_bstride + (long long)t * (4 * H) + g * H + h] = keep[g];
                     }
                     hpr[b][n] = hnew;
                     hs[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hnew;
@@ -681,6 +708,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                         if (LSTM && a.c_save) a.c_save[(row0 + b) * a.out_bstride + (long long)t * H + h] = cst[b][n];
                     }
                 }
+            if (MODE == MODE_RANK1) cp_async_wait_all();
             __syncthreads();
         }
 #pragma unroll
@@ -873,15 +901,16 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
 #pragma unroll
             for (int j = 0; j < TN; ++j) {
                 const int owner = j / CW, c = j % CW;
+                // dlt = (sp - owner) mod SPLIT is warp-uniform (a split is a whole number of warps); 0 = own column.
+                // One uniform branch per column; the partner index only enters the address.
+                const int dlt = (sp - owner + SPLIT) % SPLIT;
+                if (dlt != 0) {
+                    float *dst = xch + (dlt - 1) * (R * TMr * CW * NTHR) + c * NTHR + owner * M::PER + tprime;
 #pragma unroll
-                for (int dlt = 1; dlt < SPLIT; ++dlt)
-                    if (((sp - owner + SPLIT) % SPLIT) == dlt) {
+                    for (int b = 0; b < R; ++b)
 #pragma unroll
-                        for (int b = 0; b < R; ++b)
-#pragma unroll
-                            for (int q = 0; q < TMr; ++q)
-                                xch[(((dlt - 1) * R + b) * TMr + q) * CW * NTHR + c * NTHR + owner * M::PER + tprime] = acc[b][q][j];
-                    }
+                        for (int q = 0; q < TMr; ++q) dst[(b * TMr + q) * CW * NTHR] = acc[b][q][j];
+                }
             }
             __syncthreads();
             if (live) {
@@ -1080,7 +1109,9 @@ struct BwdSmem {
     static constexpr int DHC = cr4(R * St<S, D - 1>::BS);
     static constexpr int XCH = cmax(FM::XCH_FLOATS, BdMap<S, D - 1, R, TB::BTM[D - 1], TB::BSP>::XCH_FLOATS);
     static constexpr int H2 = cr4(R * St<S, D - 1>::BS);          // second h_{t-1} slot (cp.async double buffer)
-    static constexpr int TOTAL = W + WT + XALL + DY + DHC + XCH + H2;
+    static constexpr int X1W = DWI ? 2 * R * XW : 0;              // rank-one input windows (kept-gates kernels)
+    static constexpr int DHO = DWI ? cr4(R * n_in<S>()) : 0;      // upstream-gradient tile dOut[:, t, :] (kept-gates kernels)
+    static constexpr int TOTAL = W + WT + XALL + DY + DHC + XCH + H2 + X1W + DHO;
     static constexpr size_t BYTES = (size_t)TOTAL * 4;
 };
 
@@ -1186,6 +1217,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
     // the two h_{t-1} slots as offsets from the shared base (a pointer array would lose the address space)
     constexpr int HOFF0 = SM::W + SM::WT + SM::template XOff<S::D - 1>::v;
     constexpr int HOFF1 = SM::W + SM::WT + SM::XALL + SM::DY + SM::DHC + SM::XCH;
+    float *xw1 = smem + HOFF1 + SM::H2;
+    float *dho_s = xw1 + SM::X1W;
 
     stage_weights_k<S, 0>(a.cores, wsm, tid);
     stage_weights_t<S, 0>(a.cores, wt, tid);
@@ -1252,7 +1285,20 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 else st4(d4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
         };
-        float xin_n[R][NE][4], x1_n[R], cprev_n[R][NE], dho_n[R][NE], pre_n[R][NE][4];
+        // Recompute kernels (SV = 0) fetch the per-unit operands of the gate phase into registers one step ahead.
+        // The kept-gates kernels (SV != 0) instead read this step's gate activations / c_{t-1} at the top of the
+        // step (they are consumed after the chain recompute), take x[b, t] from the shared windows and the
+        // upstream gradient from a cp.async tile: no value is carried across steps in registers, which at 255
+        // registers per thread were being spilled (and a spilled prefetch waits for its own load).
+        float xin_n[R][NE][4], x1_n[R], cprev_n[R][NE], dho_n[R][NE];
+        auto fetch_dho = [&](int tgl) {                   // dOut[:, tgl, :] of the CTA's rows -> dho_s [b][h]
+            for (int e = tid * 4; e < R * H; e += NTHR * 4) {
+                const int b = e / H, h = e % H;
+                const long long row = row0 + b;
+                if (row < a.B && a.dhs) cp_async16(dho_s + e, a.dhs + (row * a.T + tgl) * H + h);
+                else st4(dho_s + e, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+        };
         auto fetch_x0 = [&](int tgl) {                    // saved X_0 tile of global step tgl -> its slot
             using T0s = St<S, 0>;
             constexpr int X0F = T0s::Mrow * T0s::K;
@@ -1264,18 +1310,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 else st4(d4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
         };
-        auto fetch_regs = [&](int tl) {                   // operands of local step tl
+        auto fetch_regs = [&](int tl) {                   // operands of local step tl (recompute kernels)
             const int tgl = a.t0 + tl;
-            if (SAVEU) {
-#pragma unroll
-                for (int b = 0; b < R; ++b)
-#pragma unroll
-                    for (int n = 0; n < NE; ++n)
-#pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            pre_n[b][n][g] = (row0 + b < a.B)
-                                ? __ldg(a.u_save + (row0 + b) * a.u_bstride + (long long)tgl * GH + g * H + hid[n]) : 0.f;
-            }
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 const long long row = row0 + b;
@@ -1299,34 +1335,64 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             }
         };
         fetch_h(smem + (((a.steps - 1) & 1) ? HOFF1 : HOFF0), a.t0 + a.steps - 1);
-        fetch_regs(a.steps - 1);
+        if constexpr (SAVEU) {
+            fetch_dho(a.t0 + a.steps - 1);
+            if (MODE == MODE_RANK1) {
+                const int wl = (a.steps - 1) / XW;
+                x1_fetch_window<R>(xw1 + (wl & 1) * R * XW, a.x1 + a.t0, a.x1_bstride, row0, a.B, a.steps, wl, tid);
+                if (wl >= 1)
+                    x1_fetch_window<R>(xw1 + ((wl - 1) & 1) * R * XW, a.x1 + a.t0, a.x1_bstride, row0, a.B, a.steps, wl - 1, tid);
+            }
+        } else {
+            fetch_regs(a.steps - 1);
+        }
         if (SAVED) fetch_x0(a.t0 + a.steps - 1);
         cp_async_wait_all();
         for (int t = a.steps - 1; t >= 0; --t) {
             const int tg = a.t0 + t;
             float *hcur = smem + ((t & 1) ? HOFF1 : HOFF0);
             __syncthreads();
-            // operands of this step (fetched during the previous one)
+            // operands of this step
             float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE], pre[R][NE][4];
 #pragma unroll
             for (int b = 0; b < R; ++b) {
-                x1[b] = x1_n[b];
+                const long long row = row0 + b;
+                const bool ok = row < a.B;
+                if constexpr (SAVEU) x1[b] = (MODE == MODE_RANK1) ? xw1[((t / XW) & 1) * R * XW + b * XW + (t % XW)] : 0.f;
+                else x1[b] = x1_n[b];
 #pragma unroll
                 for (int n = 0; n < NE; ++n) {
+                    if constexpr (SAVEU) {
+                        // gate activations kept by the forward kernel (LSTM i,f,g,o; GRU r,z,n,u_n) and c_{t-1}
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        xin[b][n][g] = xin_n[b][n][g];
-                        if (SAVEU) pre[b][n][g] = pre_n[b][n][g];      // chain outputs kept by the forward kernel
+                        for (int g = 0; g < 4; ++g)
+                            pre[b][n][g] = ok ? __ldg(a.u_save + row * a.u_bstride + (long long)tg * (4 * H) + g * H + hid[n]) : 0.f;
+                        float cv = 0.f;
+                        if (LSTM && ok) {
+                            if (tg > 0) cv = __ldg(a.cs + (row * a.T + (tg - 1)) * H + hid[n]);
+                            else if (a.c0) cv = __ldg(a.c0 + row * H + hid[n]);
+                        }
+                        cprev[b][n] = cv;
+                        dho[b][n] = dho_s[b * H + hid[n]];
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) xin[b][n][g] = xin_n[b][n][g];
+                        cprev[b][n] = cprev_n[b][n];
+                        dho[b][n] = dho_n[b][n];
                     }
-                    cprev[b][n] = cprev_n[b][n];
-                    dho[b][n] = dho_n[b][n];
                     hprev[b][n] = hcur[b * TL::BS + (hid[n] / TL::K) * TL::KS + (hid[n] % TL::K)];
                 }
             }
             // request the operands of step t-1 now; they land while this step computes
             if (t > 0) {
                 fetch_h(smem + (((t - 1) & 1) ? HOFF1 : HOFF0), tg - 1);
-                fetch_regs(t - 1);
+                if constexpr (!SAVEU) fetch_regs(t - 1);
+            }
+            if constexpr (SAVEU) {
+                // entering window w = t / XW from above: stage window w - 1 (its buffer was last read a step ago)
+                if (MODE == MODE_RANK1 && (t % XW) == XW - 1 && t != a.steps - 1 && t / XW >= 1)
+                    x1_fetch_window<R>(xw1 + ((t / XW - 1) & 1) * R * XW, a.x1 + a.t0, a.x1_bstride, row0, a.B, a.steps,
+                                       t / XW - 1, tid);
             }
             // ---- recompute the hh chain keeping every X_k
             if constexpr (!SAVED) fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
@@ -1347,15 +1413,16 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                     float ain[4];
 #pragma unroll
                     for (int g = 0; g < G; ++g)
-                        ain[g] = (MODE == MODE_XG) ? xin[b][n][g] : fmaf(x1[b], weff[n][g], bih[n][g]);
+                        ain[g] = SAVEU ? 0.f : ((MODE == MODE_XG) ? xin[b][n][g] : fmaf(x1[b], weff[n][g], bih[n][g]));
                     const float dh = dhd[b][n] + dhc[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] + dho[b][n];
                     float d_ih[4], d_hh[4];
                     d_ih[3] = 0.f; d_hh[3] = 0.f;
                     if (LSTM) {
-                        const float ig = sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
-                        const float fg = sigmoidf_acc(pre[b][n][1] + bhh[n][1] + ain[1]);
-                        const float gg = tanh_g(pre[b][n][2] + bhh[n][2] + ain[2]);
-                        const float og = sigmoidf_acc(pre[b][n][3] + bhh[n][3] + ain[3]);
+                        // kept-gates kernels: the activations come from the forward pass, no transcendentals but tanh(c_t)
+                        const float ig = SAVEU ? pre[b][n][0] : sigmoidf_acc(pre[b][n][0] + bhh[n][0] + ain[0]);
+                        const float fg = SAVEU ? pre[b][n][1] : sigmoidf_acc(pre[b][n][1] + bhh[n][1] + ain[1]);
+                        const float gg = SAVEU ? pre[b][n][2] : tanh_g(pre[b][n][2] + bhh[n][2] + ain[2]);
+                        const float og = SAVEU ? pre[b][n][3] : sigmoidf_acc(pre[b][n][3] + bhh[n][3] + ain[3]);
                         const float cn = fg * cprev[b][n] + ig * gg;
                         const float tc = tanh_g(cn);
                         const float dc = dcs[b][n] + dh * og * (1.0f - tc * tc);
@@ -1370,10 +1437,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                     } else {
                         const float ur = pre[b][n][0] + bhh[n][0];
                         const float uz = pre[b][n][1] + bhh[n][1];
-                        const float un = pre[b][n][2] + bhh[n][2];
-                        const float rg = sigmoidf_acc(ain[0] + ur);
-                        const float zg = sigmoidf_acc(ain[1] + uz);
-                        const float ng = tanh_g(ain[2] + rg * un);
+                        const float un = SAVEU ? pre[b][n][3] : pre[b][n][2] + bhh[n][2];
+                        const float rg = SAVEU ? pre[b][n][0] : sigmoidf_acc(ain[0] + ur);
+                        const float zg = SAVEU ? pre[b][n][1] : sigmoidf_acc(ain[1] + uz);
+                        const float ng = SAVEU ? pre[b][n][2] : tanh_g(ain[2] + rg * un);
                         const float d_n = dh * (1.0f - zg) * (1.0f - ng * ng);
                         const float d_z = dh * (hprev[b][n] - ng) * zg * (1.0f - zg);
                         const float d_r = d_n * un * rg * (1.0f - rg);
@@ -1407,6 +1474,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 }
             if (SAVED) cp_async_wait_all();               // X_0 tile of this step (and h_{t-2}) have landed
             __syncthreads();
+            if constexpr (SAVEU) {
+                if (t > 0) fetch_dho(tg - 1);             // the tile of this step has been consumed by every thread
+            }
             // ---- backward chain: core gradients (register tiles) and dh_{t-1}
             bwd_chain<S, R, TB, 0, true, DWI>(xs, hcur, dy0, dhc, wt, xch, dw, tid);
             cp_async_wait_all();

@@ -38,6 +38,13 @@ struct TtsRnnBwdEntry {
 const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms,
                                        int prefer_R = 0, int saved = 0);
 
+// Row plan of one BPTT launch: up to two phases (kernel variant, first row, row count).  When the batch does
+// not fill whole waves of the best variant, the tail runs on a variant with fewer rows per CTA instead of
+// a mostly idle second wave (cfg3: 640 rows = one wave of 148 x 3 rows + one wave of 98 x 2 rows).
+// Returns the number of phases (0 = no registered kernel).
+int tts_plan_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R, int saved,
+                     const TtsRnnBwdEntry *entry[2], long long row0[2], long long rows[2]);
+
 struct TtsTtlFwdEntry {
     const char *name;
     int R;

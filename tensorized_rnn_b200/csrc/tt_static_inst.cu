@@ -235,6 +235,50 @@ const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int m
     return best;
 }
 
+int tts_plan_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R, int saved,
+                     const TtsRnnBwdEntry *entry[2], long long row0[2], long long rows[2]) {
+    entry[0] = entry[1] = nullptr;
+    row0[0] = row0[1] = rows[0] = rows[1] = 0;
+    if (prefer_R > 0) {
+        entry[0] = tts_find_rnn_bwd(hh, cell, mode, B, sms, prefer_R, saved);
+        rows[0] = B;
+        return entry[0] ? 1 : 0;
+    }
+    auto ok = [&](const TtsRnnBwdEntry &e) {
+        return e.cell == cell && e.mode == mode && e.saved == saved && e.match(hh) && e.smem <= kMaxSmem;
+    };
+    // cost of a wave of R rows per CTA ~ (1 + R): one unit of per-step overhead (barriers, gate phase) per row of work
+    auto wave_cost = [&](const TtsRnnBwdEntry &e, long long nrows) {
+        const long long tiles = (nrows + e.R - 1) / e.R;
+        return ((tiles + sms - 1) / sms) * (1 + e.R);
+    };
+    long long best = 0;
+    int n = 0;
+    for (const auto &a : kBwd) {
+        if (!ok(a)) continue;
+        const long long c1 = wave_cost(a, B);
+        if (n == 0 || c1 < best || (c1 == best && n == 1 && a.R > entry[0]->R)) {
+            best = c1; n = 1;
+            entry[0] = &a; entry[1] = nullptr;
+            row0[0] = 0; rows[0] = B; rows[1] = 0;
+        }
+        const long long full = B / ((long long)a.R * sms);           // whole waves of variant a
+        const long long rem = B - full * a.R * sms;
+        if (full < 1 || rem == 0) continue;
+        for (const auto &b : kBwd) {
+            if (!ok(b) || b.split != a.split) continue;
+            const long long c2 = full * (1 + a.R) + wave_cost(b, rem);
+            if (c2 < best) {
+                best = c2; n = 2;
+                entry[0] = &a; entry[1] = &b;
+                row0[0] = 0; rows[0] = full * a.R * sms;
+                row0[1] = rows[0]; rows[1] = rem;
+            }
+        }
+    }
+    return n;
+}
+
 const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R) {
     const TtsRnnFwdEntry *best = nullptr;
     if (prefer_R > 0)

@@ -32,6 +32,7 @@ std::atomic<long long> g_opt_save_bytes{0};
 std::atomic<long long> g_opt_save_u_bytes{16LL << 30};
 // dense route of the batched ih projection (tt_gemm.cuh): used when I*G*H <= ratio% of the chain's
 // multiply-adds per row (and the shape fits the GEMM tiles); 0 disables
+std::atomic<long long> g_opt_row_plan{1};      // two-phase row plans of the static BPTT kernels
 std::atomic<long long> g_opt_dense_ih{1};
 std::atomic<long long> g_opt_dense_ratio{130};
 
@@ -323,8 +324,9 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->sv_cs = r4((L - 1) * lo->BTH);
     lo->sv_total = lo->sv_cs + (lstm ? r4(L * lo->BTH) : 0);
     // kept activations of the static recurrent kernels, per layer:
-    //   mode 1 (two-core chains, "save_bytes" budget, off by default): X_0 tiles + hh pre-activations u
-    //   mode 2 ("save_u_bytes" budget, default 16 GiB): u only -- backward skips the final stage of the recompute
+    //   mode 1 (two-core chains, "save_bytes" budget, off by default): X_0 tiles + gate activations
+    //   mode 2 ("save_u_bytes" budget, default 16 GiB): gate activations only (4*H floats per row and step: LSTM
+    //           i,f,g,o; GRU r,z,n,u_n) -- backward skips the final stage of the recompute and all gate math
     if (g_opt_static.load()) {
         long long extra1 = 0, extra2 = 0;
         int mode1[TTRNN_MAX_LAYERS] = {}, mode2[TTRNN_MAX_LAYERS] = {};
@@ -335,11 +337,11 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
             if (se->x0_floats > 0 && tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1)) {
                 mode1[l] = 1;
                 lo->x0f[l] = se->x0_floats;
-                extra1 += r4(B * T * se->x0_floats) + r4(B * T * GH);
+                extra1 += r4(B * T * se->x0_floats) + r4(B * T * 4 * H);
             }
             if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 2)) {
                 mode2[l] = 1;
-                extra2 += r4(B * T * GH);
+                extra2 += r4(B * T * 4 * H);
             }
         }
         const bool use1 = extra1 > 0 && extra1 * 4 <= g_opt_save_bytes.load();
@@ -347,7 +349,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
         for (int l = 0; l < L; ++l) {
             lo->save_mode[l] = (use1 && mode1[l]) ? 1 : ((use2 && mode2[l]) ? 2 : 0);
             if (lo->save_mode[l] == 1) { lo->sv_x0[l] = lo->sv_total; lo->sv_total += r4(B * T * lo->x0f[l]); }
-            if (lo->save_mode[l] != 0) { lo->sv_u[l] = lo->sv_total; lo->sv_total += r4(B * T * GH); }
+            if (lo->save_mode[l] != 0) { lo->sv_u[l] = lo->sv_total; lo->sv_total += r4(B * T * 4 * H); }
         }
     }
     // forward scratch
@@ -655,6 +657,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "save_u_bytes")) { g_opt_save_u_bytes.store(value); return 0; }
     if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
     if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
+    if (!strcmp(key, "row_plan")) { g_opt_row_plan.store(value); return 0; }
     if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
     return 1;
@@ -788,7 +791,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
                     sa.x0_save = sv + lo.sv_x0[l] + (long long)t0 * lo.x0f[l]; sa.x0_bstride = (long long)T * lo.x0f[l];
                 }
                 if (sv && lo.save_mode[l] != 0) {
-                    sa.u_save = sv + lo.sv_u[l] + (long long)t0 * GH;          sa.u_bstride = (long long)T * GH;
+                    sa.u_save = sv + lo.sv_u[l] + (long long)t0 * 4 * H;       sa.u_bstride = (long long)T * 4 * H;
                 }
                 sa.h_out = (last && l == L - 1 && hT) ? hT : st_h;
                 sa.c_out = (last && l == L - 1 && cT) ? cT : st_c;
@@ -931,14 +934,65 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                 be = bs;
         }
         if (be) {
-            int occ = 0;
-            int rc = be->prepare(&occ);
-            if (rc || occ < 1) return fail("static kernel %s cannot be configured (cuda error %d)", be->name, rc);
-            long long g = (long long)occ * dv.sms;
-            const long long tiles = (B + be->R - 1) / be->R;
-            if (g > tiles) g = tiles;
-            if (g > lo.nslots) g = lo.nslots;
-            const int sgrid = (int)g;
+            // row plan: one phase, or two when a tail variant beats a mostly idle last wave
+            const TtsRnnBwdEntry *ph_e[2] = {be, nullptr};
+            long long ph_row0[2] = {0, 0}, ph_rows[2] = {B, 0};
+            int ph_grid[2] = {0, 0};
+            int nph = 1;
+            if (!be->split && g_opt_row_plan.load()) {
+                const TtsRnnBwdEntry *pe[2];
+                long long pr0[2], pr[2];
+                const int np = tts_plan_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), be->saved,
+                                                pe, pr0, pr);
+                if (np >= 1) {
+                    nph = np;
+                    for (int q = 0; q < np; ++q) { ph_e[q] = pe[q]; ph_row0[q] = pr0[q]; ph_rows[q] = pr[q]; }
+                    be = ph_e[0];
+                }
+            }
+            int rc = 0;
+            int sgrid = 0;
+            for (int q = 0; q < nph; ++q) {
+                int occ = 0;
+                rc = ph_e[q]->prepare(&occ);
+                if (rc || occ < 1) return fail("static kernel %s cannot be configured (cuda error %d)", ph_e[q]->name, rc);
+                long long g = (long long)occ * dv.sms;
+                const long long tiles = (ph_rows[q] + ph_e[q]->R - 1) / ph_e[q]->R;
+                if (g > tiles) g = tiles;
+                if (g > lo.nslots) g = lo.nslots;
+                ph_grid[q] = (int)g;
+                if (ph_grid[q] > sgrid) sgrid = ph_grid[q];
+            }
+            // launch every phase of the plan on its rows (row-indexed pointers are offset; gradient slots are shared
+            // and accumulated: the phases run back to back on the stream)
+            auto launch_plan = [&](const tts::RnnBwdSArgs &base) -> int {
+                for (int q = 0; q < nph; ++q) {
+                    tts::RnnBwdSArgs a2 = base;
+                    const long long r0 = ph_row0[q];
+                    a2.B = ph_rows[q];
+                    if (a2.xg) a2.xg += r0 * a2.xg_bstride;
+                    if (a2.x1) a2.x1 += r0 * a2.x1_bstride;
+                    if (a2.hs) a2.hs += r0 * (long long)T * H;
+                    if (a2.cs) a2.cs += r0 * (long long)T * H;
+                    if (a2.dhs) a2.dhs += r0 * (long long)T * H;
+                    if (a2.h0) a2.h0 += r0 * H;
+                    if (a2.c0) a2.c0 += r0 * H;
+                    if (a2.dh_in) a2.dh_in += r0 * H;
+                    if (a2.dc_in) a2.dc_in += r0 * H;
+                    if (a2.dh_out) a2.dh_out += r0 * H;
+                    if (a2.dc_out) a2.dc_out += r0 * H;
+                    if (a2.x0_save) a2.x0_save += r0 * a2.x0_bstride;
+                    if (a2.u_save) a2.u_save += r0 * a2.u_bstride;
+                    int e;
+                    {
+                        KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                        e = ph_e[q]->launch(&a2, ph_grid[q], st);
+                    }
+                    ++g_launches;
+                    if (e) return fail("static kernel %s launch failed: %s", ph_e[q]->name, cudaGetErrorString((cudaError_t)e));
+                }
+                return 0;
+            };
             const long long slot = be->slot_floats;
             if (slot > lo.part_stride) return fail("internal: gradient slot too small");
             const long long ih_slot = lp.ih.core_floats + GH;
@@ -953,7 +1007,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             sa.hs = lout; sa.cs = lcs; sa.h0 = h0; sa.c0 = c0; sa.dhs = dhs;
             sa.partial = be->split ? nullptr : part_hh;
             if (be->saved == 1) { sa.x0_save = sv + lo.sv_x0[l]; sa.x0_bstride = (long long)T * lo.x0f[l]; }
-            if (be->saved != 0) { sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * GH; }
+            if (be->saved != 0) { sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * 4 * H; }
             float *aux = sc + lo.b_aux;
             float *aux_g = aux + r4(GH);
             float *one = aux_g + r4(GH);
@@ -969,12 +1023,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                 sa.dh_in = (l == L - 1) ? d_hT : nullptr;
                 sa.dc_in = (l == L - 1) ? d_cT : nullptr;
                 sa.dh_out = sdh; sa.dc_out = sdc;
-                {
-                    KernelTimer tm(TTRNN_K_RNN_BWD, st);
-                    rc = be->launch(&sa, sgrid, st);
-                }
-                ++g_launches;
-                if (rc) return fail("static kernel %s launch failed: %s", be->name, cudaGetErrorString((cudaError_t)rc));
+                if (launch_plan(sa)) return 1;
             } else {
                 sa.bias_hh = lstm ? nullptr : b_hh;
                 const int nchunks = (T + lo.Tc - 1) / lo.Tc;
@@ -988,12 +1037,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     sa.dh_in = last ? (l == L - 1 ? d_hT : nullptr) : sdh;
                     sa.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
                     sa.dh_out = sdh; sa.dc_out = sdc;
-                    {
-                        KernelTimer tm(TTRNN_K_RNN_BWD, st);
-                        rc = be->launch(&sa, sgrid, st);
-                    }
-                    ++g_launches;
-                    if (rc) return fail("static kernel %s launch failed: %s", be->name, cudaGetErrorString((cudaError_t)rc));
+                    if (launch_plan(sa)) return 1;
                     if (be->split) {
                         // hh core gradients: batched TT-matvec backward over rows (h_{t-1}, delta_t) of this chunk
                         auto hh_dw = [&](const float *xp, long long xbs, const float *dyp, long long rows, int rpb) {

@@ -132,6 +132,8 @@ class _RnnFunction(torch.autograd.Function):
         H = spec.hidden_size
         desc = spec.desc(B, T)
         d_out = None if d_out is None else d_out.contiguous()
+        if d_out is not None and d_out.data_ptr() % 16 != 0:
+            d_out = d_out.clone()          # the BPTT kernels stage dOut tiles with 16-byte cp.async
         d_hT = None if d_hT is None else d_hT.contiguous()
         d_cT = None if d_cT is None else d_cT.contiguous()
         with torch.cuda.device(x.device):
