@@ -535,7 +535,7 @@ struct RnnFwdSArgs {
     // step so that backward does not recompute the chain.  Row b, step t at  base + b*bstride + t*per_step.
     float *x0_save;          // per step: Mrow_0 * K_0 floats (unpadded rows)
     long long x0_bstride;
-    float *u_save;           // per step: 4*H floats: the gate activations (LSTM i,f,g,o; GRU r,z,n and u_n)
+    float *u_save;           // per step: H x 4 floats [h][gate]: the gate activations (LSTM i,f,g,o; GRU r,z,n and u_n)
     long long u_bstride;
 };
 
@@ -696,11 +696,9 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                         hnew = (1.0f - zg) * ng + zg * hpr[b][n];
                         keep[0] = rg; keep[1] = zg; keep[2] = ng; keep[3] = un;
                     }
-                    if (a.u_save && row0 + b < a.B) {
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            a.u_save[(row0 + b) * a.u_bstride + (long long)t * (4 * H) + g * H + h] = keep[g];
-                    }
+                    if (a.u_save && row0 + b < a.B)      // [row][t][h][4]: one 16-byte store per hidden unit
+                        st4(a.u_save + (row0 + b) * a.u_bstride + ((long long)t * H + h) * 4,
+                            make_float4(keep[0], keep[1], keep[2], keep[3]));
                     hpr[b][n] = hnew;
                     hs[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hnew;
                     if (row0 + b < a.B) {
@@ -1364,9 +1362,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 for (int n = 0; n < NE; ++n) {
                     if constexpr (SAVEU) {
                         // gate activations kept by the forward kernel (LSTM i,f,g,o; GRU r,z,n,u_n) and c_{t-1}
-#pragma unroll
-                        for (int g = 0; g < 4; ++g)
-                            pre[b][n][g] = ok ? __ldg(a.u_save + row * a.u_bstride + (long long)tg * (4 * H) + g * H + hid[n]) : 0.f;
+                        const float4 kv = ok ? __ldg(reinterpret_cast<const float4 *>(
+                                                   a.u_save + row * a.u_bstride + ((long long)tg * H + hid[n]) * 4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                        pre[b][n][0] = kv.x; pre[b][n][1] = kv.y; pre[b][n][2] = kv.z; pre[b][n][3] = kv.w;
                         float cv = 0.f;
                         if (LSTM && ok) {
                             if (tg > 0) cv = __ldg(a.cs + (row * a.T + (tg - 1)) * H + hid[n]);

@@ -36,10 +36,33 @@ for r in rows:
             e["st"][k] = e["st"].get(k, 0.0) + num(k)
 tot = sum(e["samples"] for e in lines.values()) or 1.0
 print("total samples %.0f over %d source lines" % (tot, len(lines)))
-# function ranges of tt_static.cuh (by line number) -> phase names
-PH = [(179, 250, "fwd_stage"), (296, 361, "final_partial"), (365, 419, "final_reduce"), (420, 442, "gate funcs"),
-      (777, 909, "bwd_data_stage"), (944, 997, "bwd_weight_stage"), (1000, 1040, "flush_dw"),
-      (1235, 1300, "fetch/prefetch"), (1300, 1335, "step prologue"), (1336, 1412, "gates+delta"), (34, 58, "helpers(cp.async/ffma2/ld4)")]
+# function ranges of tt_static.cuh -> phase names, located by their signatures in the current source
+import os
+SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tensorized_rnn_b200", "csrc", "tt_static.cuh")
+MARK = [("TTS_DEV void cp_async16", "helpers(cp.async/ffma2/ld4)"), ("template <class S, int k>\nstruct St {", "shape structs"),
+        ("TTS_DEV void fwd_stage(", "fwd_stage"), ("struct FinMap {", "final map"), ("TTS_DEV void final_partial(", "final_partial"),
+        ("TTS_DEV void final_reduce(", "final_reduce"), ("TTS_DEV float sigmoidf_acc", "gate funcs"), ("struct Tune {", "tuning structs"),
+        ("__global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s", "k_rnn_fwd_s body"), ("TTS_DEV void stage_weights_t(", "stage_weights_t"),
+        ("TTS_DEV void bwd_data_stage(", "bwd_data_stage"), ("struct BwMap {", "bw map"), ("TTS_DEV void bwd_weight_stage(", "bwd_weight_stage"),
+        ("TTS_DEV void flush_dw(", "flush_dw"), ("struct TuneB {", "bwd structs"),
+        ("__global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s", "k_rnn_bwd_s prologue"),
+        ("auto fetch_h = [&]", "fetch/prefetch"), ("for (int t = a.steps - 1; t >= 0; --t) {", "step prologue"),
+        ("// ---- gates and their gradients", "gates+delta"), ("// ---- backward chain: core gradients", "bwd chain call"),
+        ("// Batched TT matvec (ih projection", "batched kernels")]
+PH = []
+try:
+    text = open(SRC).read()
+    pos = []
+    for pat, name in MARK:
+        i = text.find(pat.replace("\\n", "\n"))
+        if i >= 0:
+            pos.append((text.count("\n", 0, i) + 1, name))
+    pos.sort()
+    for q, (ln, name) in enumerate(pos):
+        end = pos[q + 1][0] - 1 if q + 1 < len(pos) else 10 ** 9
+        PH.append((ln, end, name))
+except Exception:
+    pass
 ph = {}
 for (f, ln), e in lines.items():
     name = "other"
