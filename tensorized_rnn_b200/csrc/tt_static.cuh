@@ -617,6 +617,18 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
             cp_async_wait_all();
         }
         __syncthreads();
+        // per-unit output pointers of this tile (advanced by one step at the end of every step) and the number
+        // of valid rows: the per-step stores are then single predicated instructions with no 64-bit index
+        // arithmetic and no branches between the gate computations of different rows
+        const int nvalid = (a.B - row0 < R) ? (int)(a.B - row0) : R;
+        float *out_p[NE], *cs_p[NE], *us_p[NE];
+#pragma unroll
+        for (int n = 0; n < NE; ++n) {
+            out_p[n] = a.out + row0 * a.out_bstride + hid[n];
+            cs_p[n] = (LSTM && a.c_save) ? a.c_save + row0 * a.out_bstride + hid[n] : nullptr;
+            us_p[n] = a.u_save ? a.u_save + row0 * a.u_bstride + 4 * hid[n] : nullptr;
+        }
+        const bool have_cs = LSTM && a.c_save != nullptr, have_us = a.u_save != nullptr;
 
         // operands of the gate phase are fetched one step ahead (the loads of step t+1 are issued at the top
         // of step t and land while the chain of step t runs); rank-one inputs come from the shared windows
@@ -629,8 +641,8 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                     for (int n = 0; n < NE; ++n)
 #pragma unroll
                         for (int g = 0; g < G; ++g)
-                            xin_n[b][n][g] = (row0 + b < a.B)
-                                ? __ldg(a.xg + (row0 + b) * a.xg_bstride + (long long)tl * GH + g * H + hid[n]) : 0.f;
+                            xin_n[b][n][g] = (b < nvalid)
+                                ? __ldg(a.xg + row0 * a.xg_bstride + hid[n] + (long long)tl * GH + b * a.xg_bstride + g * H) : 0.f;
             }
         };
         fetch_in(0);
@@ -696,16 +708,20 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                         hnew = (1.0f - zg) * ng + zg * hpr[b][n];
                         keep[0] = rg; keep[1] = zg; keep[2] = ng; keep[3] = un;
                     }
-                    if (a.u_save && row0 + b < a.B)      // [row][t][h][4]: one 16-byte store per hidden unit
-                        st4(a.u_save + (row0 + b) * a.u_bstride + ((long long)t * H + h) * 4,
-                            make_float4(keep[0], keep[1], keep[2], keep[3]));
+                    const bool okb = b < nvalid;
+                    if (okb && have_us)                  // [row][t][h][4]: one 16-byte store per hidden unit
+                        st4(us_p[n] + b * a.u_bstride, make_float4(keep[0], keep[1], keep[2], keep[3]));
                     hpr[b][n] = hnew;
                     hs[b * TL::BS + (h / TL::K) * TL::KS + (h % TL::K)] = hnew;
-                    if (row0 + b < a.B) {
-                        a.out[(row0 + b) * a.out_bstride + (long long)t * H + h] = hnew;
-                        if (LSTM && a.c_save) a.c_save[(row0 + b) * a.out_bstride + (long long)t * H + h] = cst[b][n];
-                    }
+                    if (okb) out_p[n][b * a.out_bstride] = hnew;
+                    if (okb && have_cs) cs_p[n][b * a.out_bstride] = cst[b][n];
                 }
+#pragma unroll
+            for (int n = 0; n < NE; ++n) {
+                out_p[n] += H;
+                if (have_cs) cs_p[n] += H;
+                if (have_us) us_p[n] += 4 * H;
+            }
             if (MODE == MODE_RANK1) cp_async_wait_all();
             __syncthreads();
         }
@@ -1267,6 +1283,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 dhd[b][n] = (ok && a.dh_in) ? __ldg(a.dh_in + (row0 + b) * H + hid[n]) : 0.f;
                 dcs[b][n] = (LSTM && ok && a.dc_in) ? __ldg(a.dc_in + (row0 + b) * H + hid[n]) : 0.f;
             }
+        const int nvalid = (a.B - row0 < R) ? (int)(a.B - row0) : R;
+        const float *us_p[NE], *cs_p[NE];                 // per-unit bases of the kept gate activations / cell states
+#pragma unroll
+        for (int n = 0; n < NE; ++n) {
+            us_p[n] = a.u_save ? a.u_save + row0 * a.u_bstride + 4 * hid[n] : nullptr;
+            cs_p[n] = (LSTM && a.cs) ? a.cs + row0 * (long long)a.T * H + hid[n] : nullptr;
+        }
         // h_{t-1} tiles are double-buffered with cp.async one step ahead; per-unit operands of the gate
         // phase are fetched into registers one step ahead as well
         auto fetch_h = [&](float *dst, int tgl) {          // h_{tgl-1} -> dst (X_{d-1} layout)
@@ -1355,20 +1378,19 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
 #pragma unroll
             for (int b = 0; b < R; ++b) {
                 const long long row = row0 + b;
-                const bool ok = row < a.B;
+                const bool ok = b < nvalid;
                 if constexpr (SAVEU) x1[b] = (MODE == MODE_RANK1) ? xw1[((t / XW) & 1) * R * XW + b * XW + (t % XW)] : 0.f;
                 else x1[b] = x1_n[b];
 #pragma unroll
                 for (int n = 0; n < NE; ++n) {
                     if constexpr (SAVEU) {
                         // gate activations kept by the forward kernel (LSTM i,f,g,o; GRU r,z,n,u_n) and c_{t-1}
-                        const float4 kv = ok ? __ldg(reinterpret_cast<const float4 *>(
-                                                   a.u_save + row * a.u_bstride + ((long long)tg * H + hid[n]) * 4))
+                        const float4 kv = ok ? __ldg(reinterpret_cast<const float4 *>(us_p[n] + (long long)tg * (4 * H) + b * a.u_bstride))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                         pre[b][n][0] = kv.x; pre[b][n][1] = kv.y; pre[b][n][2] = kv.z; pre[b][n][3] = kv.w;
                         float cv = 0.f;
                         if (LSTM && ok) {
-                            if (tg > 0) cv = __ldg(a.cs + (row * a.T + (tg - 1)) * H + hid[n]);
+                            if (tg > 0) cv = __ldg(cs_p[n] + (long long)(tg - 1) * H + (long long)b * a.T * H);
                             else if (a.c0) cv = __ldg(a.c0 + row * H + hid[n]);
                         }
                         cprev[b][n] = cv;
@@ -1408,7 +1430,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 for (int n = 0; n < NE; ++n) {
                     const int h = hid[n];
                     const long long row = row0 + b;
-                    const bool ok = row < a.B;
+                    const bool ok = b < nvalid;
                     float ain[4];
 #pragma unroll
                     for (int g = 0; g < G; ++g)
