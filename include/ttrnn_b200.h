@@ -160,6 +160,11 @@ int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K
 int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row,
                        int64_t *dense_macs_per_row);
 
+/* Host-only: text table of the statically specialised kernels compiled into the library, one line per
+ * kernel "kind|name|rows_per_cta|shared_memory_bytes|fits" (fits = 1 when it is within the 227 KB opt-in limit
+ * and can be selected).  Returns the number of characters written, < 0 on a bad buffer. */
+int ttrnn_static_kernel_table(char *buf, int32_t cap);
+
 /* Tuning knobs (process-wide; also read from the environment at load time):
  *   "rows_per_cta"  batch rows owned by one CTA of the recurrent kernels (0 = auto)
  *   "chunk_steps"   timesteps per ih-projection chunk (0 = auto, bounded by memory)

@@ -52,6 +52,7 @@ SYMBOLS = {
     "ttrnn_cell_forward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 7),
     "ttrnn_cell_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 12),
     "ttrnn_rnn_ih_route": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ttrnn_static_kernel_table": (C.c_int, [C.c_char_p, C.c_int32]),
     "ttrnn_ffma_probe": (C.c_int, [C.c_int32, _P, C.POINTER(C.c_double), _P]),
     "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
     "ttrnn_kernel_timing": (C.c_int, [C.c_int32]),

@@ -79,6 +79,19 @@ TTS_DEV void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 // ---------------------------------------------------------------------------------------------
 // Shape: struct with static constexpr D, G, J[], I[], RK[] (ranks r_0..r_d)
 // ---------------------------------------------------------------------------------------------
+// floats per batch row of the X_k slot (i-block padded, see St::PAD); the runtime-indexed twin of St<S, k>::BS
+template <class S>
+constexpr int slot_floats_of(int k) {
+    int m = 1;
+    for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
+    for (int q = 0; q < k; ++q) m *= S::J[q];
+    const int ks = cpad(cr4(S::J[k] * S::RK[k + 1]));
+    const int nb = (k + 1 < S::D) ? S::I[k + 1] : 1;
+    const int rb = m / nb;
+    const int pad = (nb > 1 && ((rb * ks / 4) % 2 == 0)) ? 4 : 0;
+    return nb * (rb * ks + pad);
+}
+
 template <class S, int k>
 struct St {
     static_assert(k >= 0 && k < S::D, "stage index");
@@ -95,7 +108,17 @@ struct St {
     }
     static constexpr int Mrow = mrow();
     static constexpr int KS = cpad(K);
-    static constexpr int BS = Mrow * KS;              // floats per batch row of X_k
+    // The leading row index of X_k (k < d-1) is i_{k+1}: NB blocks of RB rows.  A stage writes X_k with lanes
+    // running over i_{k+1} (and the core-gradient / data-gradient stages read it that way), so the block stride
+    // must be an odd number of float4s or those accesses collapse onto one bank group (measured on the d3r8 chain:
+    // 8-way conflicts, 33 % excess wavefronts in bwd_weight_stage).  PAD floats are inserted after every block.
+    static constexpr int NB = (k + 1 < S::D) ? S::I[(k + 1 < S::D) ? k + 1 : 0] : 1;
+    static constexpr int RB = Mrow / NB;
+    static constexpr int PAD = (NB > 1 && ((RB * KS / 4) % 2 == 0)) ? 4 : 0;
+    static constexpr int IBS = RB * KS + PAD;         // block stride
+    static constexpr int BS = NB * IBS;               // floats per batch row of X_k
+    TT_HD static constexpr int roff(int row) { return row * KS + (row / RB) * PAD; }   // offset of row `row`
+    static_assert(BS == slot_floats_of<S>(k), "slot size formulas must agree");
     // shared-memory weight layout: k >= 1: [kappa][n] stride NS;  k == 0: [kappa][i0'][4 gates]
     static constexpr int NW = (k == 0 && PACK) ? (I / (PACK ? S::G : 1)) * 4 : N;
     static constexpr int NS = cpad(NW);
@@ -203,7 +226,11 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
     using M = FwdMap<S, k, R, TMr, TN>;
     using L = Lanes<M::LX>;
     constexpr int Jp = To::J, KSo = To::KS, BSo = To::BS;
-    constexpr int ISo = (T::Mrow / Jp) * KSo;
+    constexpr int ISo = To::IBS;
+    static_assert(To::RB == T::Mrow / Jp, "i-block rows of the output slot");
+    // rows q*MTl + mt of X_k: separable offsets when whole blocks lie between consecutive q
+    constexpr bool SEP = (T::PAD == 0) || (M::MTl % T::RB == 0);
+    constexpr int QS = M::MTl * T::KS + (M::MTl / T::RB) * T::PAD;
     constexpr int NG = TN / 4;                 // float4 column groups per thread
     constexpr int GSTR = T::N / NG;            // distance between the groups (columns)
     const int lane = tid & 31, warp = tid >> 5;
@@ -220,15 +247,18 @@ TTS_DEV void fwd_stage(const float *__restrict__ X, const float *__restrict__ W,
             for (int q = 0; q < TMr; ++q)
 #pragma unroll
                 for (int j = 0; j < TN / 2; ++j) acc2[b][q][j] = 0ull;
-        const float *xb = X + mt * T::KS;
+        const float *xb = X + T::roff(mt);
         const float *wb = W + tn * 4;
+        int xq[TMr];
+#pragma unroll
+        for (int q = 0; q < TMr; ++q) xq[q] = SEP ? q * QS : T::roff(mt + q * M::MTl) - T::roff(mt);
 #pragma unroll(unroll_of(T::K / 4))
         for (int k4 = 0; k4 < T::K; k4 += 4) {
             float4 a[R][TMr];
 #pragma unroll
             for (int b = 0; b < R; ++b)
 #pragma unroll
-                for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * M::MTl * T::KS + k4);
+                for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + xq[q] + k4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 f32x2 w2[TN / 2];
@@ -319,7 +349,12 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
                            float (&acc)[R][FM::TMr][FM::TI][4]) {
     using T = St<S, 0>;
     constexpr int TMr = FM::TMr, TI = FM::TI;
-    const float *xb = X + mt * T::KS + kh * FM::KPART;
+    constexpr bool SEP = (T::PAD == 0) || (FM::MTl % T::RB == 0);
+    constexpr int QS = FM::MTl * T::KS + (FM::MTl / T::RB) * T::PAD;
+    const float *xb = X + T::roff(mt) + kh * FM::KPART;
+    int xq[TMr];
+#pragma unroll
+    for (int q = 0; q < TMr; ++q) xq[q] = SEP ? q * QS : T::roff(mt + q * FM::MTl) - T::roff(mt);
     const float *wb = W + kh * FM::KPART * T::NS + itg * TI * 4;
     f32x2 acc2[R][TMr][TI][2];
 #pragma unroll
@@ -334,7 +369,7 @@ TTS_DEV void final_partial(const float *__restrict__ X, const float *__restrict_
 #pragma unroll
         for (int b = 0; b < R; ++b)
 #pragma unroll
-            for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + q * FM::MTl * T::KS + k4);
+            for (int q = 0; q < TMr; ++q) a[b][q] = ld4(xb + b * T::BS + xq[q] + k4);
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
             f32x2 w2[TI][2];
@@ -670,7 +705,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_fwd_s(const __grid_constant_
                     const int b = e / X0F, rem = e % X0F;
                     if (row0 + b < a.B)
                         *reinterpret_cast<float4 *>(a.x0_save + (row0 + b) * a.x0_bstride + (long long)t * X0F + rem) =
-                            ld4(X0 + b * T0s::BS + (rem / T0s::K) * T0s::KS + (rem % T0s::K));
+                            ld4(X0 + b * T0s::BS + T0s::roff(rem / T0s::K) + (rem % T0s::K));
                 }
             }
             // ---- stage 0 (split over K) + reduce-scatter + gate math + state update
@@ -828,7 +863,7 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
     constexpr int Jp = (k == 0) ? 1 : St<S, (k == 0 ? 0 : k - 1)>::J;
     constexpr int KSo = (k == 0) ? DY0<S>::DS : St<S, (k == 0 ? 0 : k - 1)>::KS;
     constexpr int BSo = (k == 0) ? DY0<S>::BS : St<S, (k == 0 ? 0 : k - 1)>::BS;
-    constexpr int ISo = (k == 0) ? 0 : (T::Mrow / Jp) * KSo;
+    constexpr int ISo = (k == 0) ? 0 : St<S, (k == 0 ? 0 : k - 1)>::IBS;
     const int lane = tid & 31;
     const int sp = tid / M::PER;                 // split index (whole warps)
     const int wloc = (tid % M::PER) >> 5;
@@ -904,7 +939,7 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
                     for (int g = 0; g < NG; ++g)
 #pragma unroll
                         for (int b = 0; b < R; ++b)
-                            st4(dX + b * T::BS + mr * T::KS + g * GSTR + tn * 4,
+                            st4(dX + b * T::BS + T::roff(mr) + g * GSTR + tn * 4,
                                 make_float4(acc[b][q][4 * g], acc[b][q][4 * g + 1], acc[b][q][4 * g + 2], acc[b][q][4 * g + 3]));
                 }
             }
@@ -941,7 +976,7 @@ TTS_DEV void bwd_data_stage(const float *__restrict__ dY, const float *__restric
 #pragma unroll
                                 for (int dlt = 1; dlt < SPLIT; ++dlt)
                                     sum += xch[(((dlt - 1) * R + b) * TMr + q) * CW * NTHR + c * NTHR + tid];
-                                dX[b * T::BS + (q * M::MTl + mt) * T::KS + col] = sum;
+                                dX[b * T::BS + T::roff(q * M::MTl + mt) + col] = sum;
                             }
                     }
                 }
@@ -991,7 +1026,7 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
     constexpr int Jp = (k == 0) ? 1 : St<S, (k == 0 ? 0 : k - 1)>::J;
     constexpr int KSo = (k == 0) ? DY0<S>::DS : St<S, (k == 0 ? 0 : k - 1)>::KS;
     constexpr int BSo = (k == 0) ? DY0<S>::BS : St<S, (k == 0 ? 0 : k - 1)>::BS;
-    constexpr int ISo = (k == 0) ? 0 : (T::Mrow / Jp) * KSo;
+    constexpr int ISo = (k == 0) ? 0 : St<S, (k == 0 ? 0 : k - 1)>::IBS;
     int nt, kt, mg;
     M::coords(tid, nt, kt, mg);
     const int n0 = nt * 4;
@@ -1011,10 +1046,11 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
             ffma2(acc2[a][1], x[a], y23);
         }
     };
-    if constexpr (T::Mrow % M::MG == 0 && (k == 0 || M::MG % Jp == 0 || Jp % M::MG == 0)) {
+    if constexpr (T::Mrow % M::MG == 0 && (k == 0 || M::MG % Jp == 0 || Jp % M::MG == 0) &&
+                  (T::PAD == 0 || M::MG % T::RB == 0 || T::RB % M::MG == 0)) {
         // rows of this thread: mr = i*MG + mg for every batch row b -> compile-time offsets from one base
         constexpr int NI = T::Mrow / M::MG;
-        const float *xp0 = X + mg * T::KS + kt * TK;
+        const float *xp0 = X + T::roff(mg) + kt * TK;
         const float *yp0 = dY + yoff + ((k == 0) ? mg * KSo : (mg / Jp) * KSo + (mg % Jp) * T::r);
 #pragma unroll 1
         for (int b = 0; b < R; ++b) {
@@ -1023,7 +1059,7 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
                 const int dm = i * M::MG;                                        // compile-time row distance
                 const int dy = (k == 0) ? dm * KSo
                                         : ((M::MG % Jp == 0) ? (dm / Jp) * KSo : (dm / Jp) * KSo + (dm % Jp) * T::r);
-                row_fma(xp0 + b * T::BS + dm * T::KS, yp0 + b * BSo + dy);
+                row_fma(xp0 + b * T::BS + dm * T::KS + (dm / T::RB) * T::PAD, yp0 + b * BSo + dy);
             }
         }
     } else {
@@ -1032,7 +1068,7 @@ TTS_DEV void bwd_weight_stage(const float *__restrict__ X, const float *__restri
             const int m = it * M::MG + mg;
             if (M::M % M::MG != 0 && m >= M::M) break;
             const int b = m / T::Mrow, mr = m % T::Mrow;
-            row_fma(X + b * T::BS + mr * T::KS + kt * TK,
+            row_fma(X + b * T::BS + T::roff(mr) + kt * TK,
                     dY + b * BSo + ((k == 0) ? mr * KSo : (mr / Jp) * KSo + (mr % Jp) * T::r) + yoff);
         }
     }
@@ -1101,12 +1137,7 @@ struct BwdSmem {
     using FM = FinMap<S, R, TU::FTMr, TU::FTI, TU::FSK>;
     static constexpr int W = w_floats<S>();
     static constexpr int WT = wt_floats<S>();
-    static constexpr int stage_bs(int k) {
-        int m = 1;
-        for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
-        for (int q = 0; q < k; ++q) m *= S::J[q];
-        return m * cpad(cr4(S::J[k] * S::RK[k + 1]));
-    }
+    static constexpr int stage_bs(int k) { return slot_floats_of<S>(k); }
     static constexpr int HS0 = cr4(R * stage_bs(S::D - 1));
     static constexpr int xoff(int k) {
         if (DWI) {
@@ -1326,7 +1357,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             float *dst = xs + SM::template XOff<0>::v;
             for (int e = tid * 4; e < R * X0F; e += NTHR * 4) {
                 const int b = e / X0F, rem = e % X0F;
-                float *d4 = dst + b * T0s::BS + (rem / T0s::K) * T0s::KS + (rem % T0s::K);
+                float *d4 = dst + b * T0s::BS + T0s::roff(rem / T0s::K) + (rem % T0s::K);
                 if (row0 + b < a.B) cp_async16(d4, a.x0_save + (row0 + b) * a.x0_bstride + (long long)tgl * X0F + rem);
                 else st4(d4, make_float4(0.f, 0.f, 0.f, 0.f));
             }
@@ -1620,7 +1651,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ttlin_fwd_s(const __grid_constant__
             for (int q = 0; q < OM::TMr; ++q)
 #pragma unroll
                 for (int j = 0; j < OM::TN / 2; ++j) acc2[i][q][j] = 0ull;
-        const float *xb = X0 + mt * T0::KS;
+        const float *xb = X0 + T0::roff(mt);
         const float *wb = wsm + WOff<S, 0>::v;
 #pragma unroll 2
         for (int k4 = 0; k4 < T0::K; k4 += 4) {
@@ -1630,7 +1661,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_ttlin_fwd_s(const __grid_constant__
 #pragma unroll
                 for (int q = 0; q < OM::TMr; ++q) {
                     const int b = rb * OM::RPT + i;
-                    av[i][q] = ld4(xb + (b < R ? b : 0) * T0::BS + q * OM::MTl * T0::KS + k4);
+                    av[i][q] = ld4(xb + (b < R ? b : 0) * T0::BS + (T0::roff(mt + q * OM::MTl) - T0::roff(mt)) + k4);
                 }
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -1693,12 +1724,7 @@ template <class S, int R, class TB, bool WANT_DX>
 struct TtlBwdSmem {
     static constexpr int W = w_floats<S>();
     static constexpr int WT = wt_floats<S>();
-    static constexpr int stage_bs(int k) {
-        int m = 1;
-        for (int q = k + 1; q < S::D; ++q) m *= S::I[q];
-        for (int q = 0; q < k; ++q) m *= S::J[q];
-        return m * cpad(cr4(S::J[k] * S::RK[k + 1]));
-    }
+    static constexpr int stage_bs(int k) { return slot_floats_of<S>(k); }
     static constexpr int xoff(int k) {
         int v = 0;
         for (int q = S::D - 1; q > k; --q) v += cr4(R * stage_bs(q));

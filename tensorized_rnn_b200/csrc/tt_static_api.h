@@ -63,3 +63,6 @@ struct TtsTtlBwdEntry {
 };
 const TtsTtlFwdEntry *tts_find_ttl_fwd(const ttrnn_tt_shape *s, long long rows);
 const TtsTtlBwdEntry *tts_find_ttl_bwd(const ttrnn_tt_shape *s, long long rows, int want_dx);
+
+// text table of the registry (kind|name|R|smem bytes|fits 227 KB), returns the number of characters written
+int tts_dump_entries(char *buf, int cap);

@@ -2,6 +2,7 @@
 // lookup used by the C ABI.  Adding a shape = one TTS_SHAPE line + one TTS_FWD line per variant.
 #include "tt_static.cuh"
 #include "tt_static_api.h"
+#include <cstdio>
 
 namespace {
 
@@ -199,6 +200,19 @@ const TtsTtlBwdEntry kTtlBwd[] = {
 };
 
 }  // namespace
+
+// text table of every registered static kernel: "kind name R smem_bytes fits\n" (tests assert that all fit)
+int tts_dump_entries(char *buf, int cap) {
+    int n = 0;
+    auto put = [&](const char *kind, const char *name, int R, size_t smem) {
+        if (n < cap) n += snprintf(buf + n, cap - n, "%s|%s|%d|%zu|%d\n", kind, name, R, smem, smem <= kMaxSmem ? 1 : 0);
+    };
+    for (const auto &e : kFwd) put("rnn_fwd", e.name, e.R, e.smem);
+    for (const auto &e : kBwd) put("rnn_bwd", e.name, e.R, e.smem);
+    for (const auto &e : kTtlFwd) put("ttl_fwd", e.name, e.R, e.smem);
+    for (const auto &e : kTtlBwd) put("ttl_bwd", e.name, e.R, e.smem);
+    return n;
+}
 
 const TtsTtlFwdEntry *tts_find_ttl_fwd(const ttrnn_tt_shape *s, long long rows) {
     if (rows < 64) return nullptr;                  // tiny calls (rank-one helper rows) stay on the generic kernel

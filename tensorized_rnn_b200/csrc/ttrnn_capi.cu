@@ -663,6 +663,11 @@ int ttrnn_set_option(const char *key, int64_t value) {
     return 1;
 }
 
+int ttrnn_static_kernel_table(char *buf, int32_t cap) {
+    if (!buf || cap < 1) return -1;
+    return tts_dump_entries(buf, cap);
+}
+
 int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row, int64_t *dense_macs_per_row) {
     RnnPlan rp;
     if (build_rnn_plan(desc, &rp)) return -1;

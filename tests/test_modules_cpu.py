@@ -142,3 +142,19 @@ def test_descriptor_validation_without_gpu():
     assert lib.ttrnn_rnn_param_count(ctypes.byref(bad)) == -1
     assert b"expected" in lib.ttrnn_last_error()
     bad.hidden_size = 256
+
+
+def test_every_registered_static_kernel_fits_shared_memory():
+    """The registry silently skips a static kernel whose shared-memory footprint exceeds the 227 KB opt-in limit
+    (the shape then runs on the slow runtime-shape kernels).  Every kernel compiled into the library must fit."""
+    import ctypes
+    from tensorized_rnn_b200 import _lib
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = lib.ttrnn_static_kernel_table(buf, len(buf))
+    assert n > 0
+    rows = [ln.split("|") for ln in buf.value.decode().strip().splitlines()]
+    assert len(rows) >= 30
+    too_big = [r for r in rows if r[4] != "1"]
+    assert not too_big, too_big
+    assert {r[0] for r in rows} == {"rnn_fwd", "rnn_bwd", "ttl_fwd", "ttl_bwd"}
