@@ -1036,7 +1036,9 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     const int t0 = ci * lo.Tc;
                     const int tc = (T - t0 < lo.Tc) ? T - t0 : lo.Tc;
                     const bool last = (t0 + tc == T);
-                    if (project(t0, tc)) return 1;
+                    // the kept-gates kernels take the gate activations from the forward pass and only WRITE delta_ih
+                    // into xg: recomputing the ih projection of the chunk would be wasted work
+                    if (be->saved == 0 && project(t0, tc)) return 1;
                     sa.t0 = t0; sa.steps = tc;
                     sa.xg = xg; sa.xg_bstride = (long long)tc * GH;
                     sa.dh_in = last ? (l == L - 1 ? d_hT : nullptr) : sdh;
