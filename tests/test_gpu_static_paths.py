@@ -168,6 +168,66 @@ def test_dense_and_tt_chain_ih_routes_agree():
             assert rel_err(a, b) <= GRAD_TOL
 
 
+def test_dense_route_split_reduction_and_chunk_accumulation():
+    """Dense ih route at a size that splits the X^T delta reduction over many CTAs and accumulates it over
+    several time chunks (chunk_steps = 16 of T = 40), against the core-by-core route on the same inputs."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    torch.manual_seed(41)
+    m = quiet(tr.TTLSTM, 40, 256, 2, torch.device("cpu"), n_cores=3, tt_rank=8).to(dev)
+    x = torch.rand(64, 40, 40, device=dev, requires_grad=True)
+    w = torch.randn(64, 40, 256, device=dev)
+    res = []
+    for dense, chunk in ((1, 16), (0, 0)):
+        lib.ttrnn_set_option(b"dense_ih", dense)
+        lib.ttrnn_set_option(b"chunk_steps", chunk)
+        try:
+            for p in m.parameters():
+                p.grad = None
+            x.grad = None
+            out, (h, c) = m(x)
+            ((out * w).sum() + c.sum()).backward()
+            res.append((out.detach().clone(), x.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+        finally:
+            lib.ttrnn_set_option(b"dense_ih", 1)
+            lib.ttrnn_set_option(b"chunk_steps", 0)
+    assert rel_err(res[0][0], res[1][0]) <= FWD_TOL
+    assert rel_err(res[0][1], res[1][1]) <= GRAD_TOL
+    for a, b in zip(res[0][2], res[1][2]):
+        assert rel_err(a, b) <= GRAD_TOL
+
+
+def test_two_phase_row_plan_matches_single_variant():
+    """A batch that does not fill whole waves of the best BPTT variant runs in two phases (tail rows on a variant
+    with fewer rows per CTA, row-offset pointers, shared gradient slots).  Must equal the one-variant launch."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    B = 3 * sms + 2 * (sms // 2) + 1            # one full wave of 3-row CTAs plus a tail
+    torch.manual_seed(43)
+    m = quiet(tr.TTLSTM, 40, 256, 1, torch.device("cpu"), n_cores=3, tt_rank=8).to(dev)
+    x = torch.rand(B, 5, 40, device=dev)
+    h0 = 0.2 * torch.randn(B, 256, device=dev)
+    c0 = 0.2 * torch.randn(B, 256, device=dev)
+    w = torch.randn(B, 5, 256, device=dev)
+    res = []
+    for plan in (1, 0):
+        lib.ttrnn_set_option(b"row_plan", plan)
+        try:
+            for p in m.parameters():
+                p.grad = None
+            h0r, c0r = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+            out, (h, c) = m(x, (h0r, c0r))
+            ((out * w).sum() + 2 * h.sum() + c.sum()).backward()
+            res.append((out.detach().clone(), h0r.grad.clone(), c0r.grad.clone(), [p.grad.clone() for p in m.parameters()]))
+        finally:
+            lib.ttrnn_set_option(b"row_plan", 1)
+    assert torch.equal(res[0][0], res[1][0])
+    assert rel_err(res[0][1], res[1][1]) <= GRAD_TOL and rel_err(res[0][2], res[1][2]) <= GRAD_TOL
+    for a, b in zip(res[0][3], res[1][3]):
+        assert rel_err(a, b) <= GRAD_TOL
+
+
 def test_static_and_runtime_shape_kernels_agree():
     """Same inputs through the static kernels and through the runtime-shape kernels (static_kernels=0)."""
     dev = torch.device("cuda:0")

@@ -80,4 +80,22 @@ if os.path.exists(lf):
                 f.write("Stall samples by phase / source line (`tools/ncu_lines.py`):\n\n```\n" + out + "```\n\n")
     import shutil
     shutil.copy(lf, os.path.join(P, "r1_launches_cfg2.csv"))
+    # measured DRAM traffic of the dominant kernel -> profiles/traffic.json (read by bench.py)
+    sf = os.path.join(G, "prof_final_cfg2_bwd.summary.txt")
+    if os.path.exists(sf):
+        vals = {}
+        for ln in open(sf):
+            parts = ln.split()
+            if len(parts) >= 2 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(parts[1])
+                unit = parts[2].lower() if len(parts) > 2 else "gbyte"      # ncu prints these two in Gbyte at this size
+                vals[parts[0]] = v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1e9)
+        if len(vals) == 2:
+            json.dump({l["config"]["workload"]: {"kernel": "k_rnn_bwd", "dram_bytes_per_launch": sum(vals.values()),
+                                                 "dram_read_bytes": vals["dram__bytes_read.sum"],
+                                                 "dram_write_bytes": vals["dram__bytes_write.sum"],
+                                                 "source": "profiles/r1_cfg2_summary.md (ncu --set full, dram__bytes_read.sum + "
+                                                           "dram__bytes_write.sum of k_rnn_bwd_s at T=784)"}},
+                      open(os.path.join(P, "traffic.json"), "w"), indent=1)
+            print("wrote traffic.json", vals)
     print("wrote r1_cfg2_summary.md")

@@ -22,11 +22,12 @@ want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "smsp__warp_issue_stalled_not_selected_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
         "smsp__warp_issue_stalled_dispatch_stall_per_warp_active.pct", "smsp__warp_issue_stalled_no_instruction_per_warp_active.pct",
         "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct"]
+units = rows[1]
 for r in rows[2:]:
     print("==", r[idx["Kernel Name"]][:70])
     for k in want:
         if k in idx and r[idx[k]] not in ("", "n/a"):
-            print("   %-78s %s" % (k, r[idx[k]]))
+            print("   %-78s %s %s" % (k, r[idx[k]], units[idx[k]]))
 if nsrc:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     print(src[:200])
