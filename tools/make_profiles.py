@@ -33,6 +33,19 @@ with open(os.path.join(P, "r1_all_configs.md"), "w") as f:
     f.write("\n".join(rows) + "\n\nRaw bench lines:\n\n")
     for l in raw:
         f.write("```json\n" + json.dumps(l) + "\n```\n")
+    sc = []
+    for c in (2, 3):
+        f8, f1 = os.path.join(G, "scale8_cfg%d.json" % c), os.path.join(G, "final_cfg%d.json" % c)
+        if os.path.exists(f8) and os.path.exists(f1):
+            a, b = line(f1), line(f8)
+            sc.append("| %d (%s, %s) | %.2f ms/step, %.3e/s | %.2f ms/step, %.3e/s | %.2fx |" % (
+                c, a["config"]["mode"], "one flat NCCL all-reduce of the TT-core gradients per step", a["ms_per_step"], a["value"],
+                b["ms_per_step"], b["value"], b["value"] / a["value"]))
+            raw.append(b)
+    if sc:
+        f.write("\nWeak scaling (fixed per-GPU batch; `gpurun --gpus 8`, torchrun, NCCL; max over ranks of device time):\n\n"
+                "| cfg | 1 GPU | 8 GPUs | scaling |\n|---|---|---|---:|\n" + "\n".join(sc) + "\n\n```json\n"
+                + "\n".join(json.dumps(x) for x in raw[-len(sc):]) + "\n```\n")
     rf = os.path.join(G, "final_reference_cfg2.json")
     if os.path.exists(rf):
         f.write("\nReference arm (`bench.py --impl reference`, oracle port of the reference's PyTorch path on the host cores):\n\n```json\n"
