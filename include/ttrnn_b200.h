@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TTRNN_ABI_VERSION 1
+#define TTRNN_ABI_VERSION 2   /* 2: + cell step, ih route query, static kernel table */
 #define TTRNN_MAX_CORES   6
 #define TTRNN_MAX_LAYERS  8
 

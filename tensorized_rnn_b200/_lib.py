@@ -10,6 +10,7 @@ import ctypes as C
 import os
 from typing import Optional, Sequence
 
+ABI_VERSION = 2
 MAX_CORES = 6
 MAX_LAYERS = 8
 CELL_LSTM, CELL_GRU = 0, 1
@@ -79,7 +80,7 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)          # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.ttrnn_abi_version() != 1:
+    if lib.ttrnn_abi_version() != ABI_VERSION:
         raise RuntimeError("tensorized_rnn_b200: ABI version mismatch between %s and the Python binding" % _LIB_PATH)
     for key, env in (("rows_per_cta", "TTRNN_ROWS_PER_CTA"), ("chunk_steps", "TTRNN_CHUNK_STEPS"),
                      ("chunk_bytes", "TTRNN_CHUNK_BYTES"), ("static_rows_fwd", "TTRNN_STATIC_ROWS_FWD"),

@@ -121,7 +121,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "library does not export %s" % name
     assert declared == set(_lib.SYMBOLS), "python binding and header disagree: %s" % (declared ^ set(_lib.SYMBOLS))
-    assert _lib.load().ttrnn_abi_version() == 1
+    assert _lib.load().ttrnn_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_struct_layout_matches_header():
