@@ -271,13 +271,19 @@ long long chain_macs(const ChainPlan &p) {
     return m;
 }
 // forward / recompute / dW^T all need: G*H % 128 == 0, I % 4 == 0
-bool dense_ih_ok(const ChainPlan &ih) {
+// `shape` (optional): when no statically specialised chain kernel is registered for it, the alternative to the
+// dense order is the ~5-10x slower runtime-shape kernel, so the dense order is allowed up to 4x the chain's MACs
+bool dense_ih_ok(const ChainPlan &ih, const ttrnn_tt_shape *shape = nullptr) {
     if (!g_opt_dense_ih.load()) return false;
     if (ih.n_out % ttg::BN != 0 || ih.n_in % 4 != 0 || ih.n_in < 4 || ih.n_in > 2048) return false;
-    return (long long)ih.n_in * ih.n_out * 100 <= chain_macs(ih) * g_opt_dense_ratio.load();
+    long long ratio = g_opt_dense_ratio.load();
+    if (shape && !(g_opt_static.load() && tts_find_ttl_fwd(shape, 1 << 20)) && ratio < 400) ratio = 400;
+    return (long long)ih.n_in * ih.n_out * 100 <= chain_macs(ih) * ratio;
 }
 // dX = delta * W additionally needs I % 128 == 0
-bool dense_ih_bwd_ok(const ChainPlan &ih, bool want_dx) { return dense_ih_ok(ih) && (!want_dx || ih.n_in % ttg::BN == 0); }
+bool dense_ih_bwd_ok(const ChainPlan &ih, bool want_dx, const ttrnn_tt_shape *shape = nullptr) {
+    return dense_ih_ok(ih, shape) && (!want_dx || ih.n_in % ttg::BN == 0);
+}
 
 struct DenseIh {
     float *eye, *wt, *w, *dwt, *dbias, *part, *pbias;
@@ -361,7 +367,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->f_aux = o; o += r4(GH) + 4;                       // rank-one input mode: dense W_ih column + a 1.0f
     long long dfw = 0, dbw = 0;                           // dense ih route: identity, W^T (+ W, dW^T, split partials)
     for (int l = 0; l < L; ++l)
-        if (dense_ih_ok(rp.layer[l].ih)) {
+        if (dense_ih_ok(rp.layer[l].ih, &d->ih[l])) {
             if (dense_fwd_floats(rp.layer[l].ih) > dfw) dfw = dense_fwd_floats(rp.layer[l].ih);
             if (dense_bwd_floats(rp.layer[l].ih) > dbw) dbw = dense_bwd_floats(rp.layer[l].ih);
         }
@@ -676,7 +682,7 @@ int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain
     if (chain_macs_per_row) *chain_macs_per_row = chain_macs(ih);
     if (dense_macs_per_row) *dense_macs_per_row = (int64_t)ih.n_in * ih.n_out;
     if (layer == 0 && desc->input_size == 1) return 2;
-    return dense_ih_ok(ih) ? 1 : 0;
+    return dense_ih_ok(ih, &desc->ih[layer]) ? 1 : 0;
 }
 
 int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc) {
@@ -734,7 +740,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
 
         // ---- batched ih projection of one time chunk: xg[b, t, :] = W_ih x[b, t0+t, :] + b_ih (+ b_hh for LSTM),
         // through the TT chain or, when that is the cheaper contraction order, through dense W_ih^T
-        const bool dense = dense_ih_ok(lp.ih) && !(l == 0 && d->input_size == 1);
+        const bool dense = dense_ih_ok(lp.ih, &d->ih[l]) && !(l == 0 && d->input_size == 1);
         DenseIh D;
         if (dense) {
             dense_carve(sc + lo.f_dense, lp.ih, false, &D);
@@ -889,7 +895,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
 
         // ---- ih projection (recompute) and its backward per time chunk: TT chain or dense route ---------
         const int mode = (l == 0 && d->input_size == 1 && !d_x) ? tts::MODE_RANK1 : tts::MODE_XG;
-        const bool dense = mode == tts::MODE_XG && dense_ih_bwd_ok(lp.ih, dlin != nullptr);
+        const bool dense = mode == tts::MODE_XG && dense_ih_bwd_ok(lp.ih, dlin != nullptr, &d->ih[l]);
         DenseIh D;
         if (dense) {
             dense_carve(sc + lo.b_dense, lp.ih, true, &D);

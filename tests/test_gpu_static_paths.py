@@ -28,6 +28,10 @@ CASES = [
     ("cfg4_shape", "lstm", 40, 256, 3, 4, 16, 5, 14, False, 0),
     ("cfg5_shape", "lstm", 256, 1024, 1, 4, 8, 4, 17, True, 0),
     ("cfg1_shape_xgrad", "lstm", 1, 256, 1, 2, 4, 8, 9, False, 0),     # x.requires_grad: XG-mode kernels
+    # row-by-row MNIST (pmnist_test.py without --permute: I = 28, T = 28): ih shape with no static chain kernel
+    # (dense route forward, chain route backward because dX is requested), XG-mode kept-gates BPTT kernels
+    ("rowmnist_lstm", "lstm", 28, 256, 1, 2, 4, 12, 28, False, 0),
+    ("rowmnist_gru_L2", "gru", 28, 256, 2, 2, 4, 9, 28, True, 0),
 ]
 
 
