@@ -277,8 +277,9 @@ TT_DEV void tt_stage_bwd_data(const StagePlan &s, int R, const float *__restrict
 // Backward-weight stage:  dW[kappa][n] += sum_m X[m][kappa] * dY[(i,m,a)]
 // accumulated into a shared-memory copy of the W layout (dWs, same strides).
 // Work item = (m-group, kappa-tile, n-tile); each item reduces its rows in
-// registers, then adds its TKxTN partial into shared memory (atomics when
-// several m-groups share an entry).
+// registers, then adds its TKxTN partial into shared memory.  When several m-groups share an
+// entry (mgroups > 1) the groups add one after the other between block barriers: a fixed summation
+// order, so the gradients are bit-reproducible (no atomics).  Must be called by every thread of the CTA.
 //   VX: K % 4 == 0  -> X read as float4 (TK = 4), else TK = 2 scalar
 //   VY: r % 4 == 0  -> dY read as float4 along a (TN = 4), else TN scalar loads
 // ---------------------------------------------------------------------------
@@ -293,7 +294,11 @@ TT_DEV void tt_stage_bwd_weight(const StagePlan &s, int R, const float *__restri
     const int NT = (s.N + TN - 1) / TN;
     const int items = KT * NT * mgroups;
     const int rows_per_group = (M + mgroups - 1) / mgroups;
-    for (int it = tid; it < items; it += nthr) {
+    // uniform trip count: every thread walks the same number of item rounds so that the serialised
+    // group adds below can sit between block barriers
+    for (int it0 = 0; it0 < items; it0 += nthr) {
+        const int it = it0 + tid;
+        const bool has = it < items;
         const int tn = it % NT;
         int t = it / NT;
         const int tk = t % KT;
@@ -316,7 +321,7 @@ TT_DEV void tt_stage_bwd_weight(const StagePlan &s, int R, const float *__restri
         }
         int bb = mbeg / s.Mrow;
         int mr = mbeg - bb * s.Mrow;
-        for (int m = mbeg; m < mend; ++m) {
+        for (int m = mbeg; has && m < mend; ++m) {
             const int hi = mr / s.Jp;
             const int lo = mr - hi * s.Jp;
             const float *yp = dY + bb * s.BSo + hi * s.KSo + lo * s.r;
@@ -341,14 +346,27 @@ TT_DEV void tt_stage_bwd_weight(const StagePlan &s, int R, const float *__restri
                 for (int b = 0; b < TN; ++b) acc[a][b] = fmaf(x[a], y[b], acc[a][b]);
             if (++mr == s.Mrow) { mr = 0; ++bb; }
         }
+        if (mgroups == 1) {
+            if (has) {
 #pragma unroll
-        for (int a = 0; a < TK; ++a)
+                for (int a = 0; a < TK; ++a)
 #pragma unroll
-            for (int b = 0; b < TN; ++b)
-                if (k0 + a < s.K && n0 + b < s.N) {
-                    if (mgroups == 1) dWs[(k0 + a) * s.NS + n0 + b] += acc[a][b];
-                    else atomicAdd(dWs + (k0 + a) * s.NS + n0 + b, acc[a][b]);
+                    for (int b = 0; b < TN; ++b)
+                        if (k0 + a < s.K && n0 + b < s.N) dWs[(k0 + a) * s.NS + n0 + b] += acc[a][b];
+            }
+        } else {
+            // the m-groups of one (kappa, n) tile add one after the other: fixed summation order
+            for (int gg = 0; gg < mgroups; ++gg) {
+                if (has && g == gg) {
+#pragma unroll
+                    for (int a = 0; a < TK; ++a)
+#pragma unroll
+                        for (int b = 0; b < TN; ++b)
+                            if (k0 + a < s.K && n0 + b < s.N) dWs[(k0 + a) * s.NS + n0 + b] += acc[a][b];
                 }
+                __syncthreads();
+            }
+        }
     }
 }
 
