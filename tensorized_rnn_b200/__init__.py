@@ -14,4 +14,6 @@ from .rnn import TTLSTM, TTLSTMCell, TTGRU, TTGRUCell, param_count
 
 __all__ = ["auto_shape", "tt_shape", "TensorTrain", "transpose", "glorot_initializer", "random_matrix",
            "matrix_with_random_cores", "TTLinear", "TTLinearSet", "ActivGradLogger", "av_norm", "TTLSTM", "TTLSTMCell", "TTGRU", "TTGRUCell", "param_count"]
-__version__ = "0.1.0"
+from . import compat  # noqa: E402,F401  (compat.patch_reference(): switch a reference checkout over)
+
+__version__ = "0.2.0"

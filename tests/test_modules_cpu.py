@@ -158,3 +158,39 @@ def test_every_registered_static_kernel_fits_shared_memory():
     too_big = [r for r in rows if r[4] != "1"]
     assert not too_big, too_big
     assert {r[0] for r in rows} == {"rnn_fwd", "rnn_bwd", "ttl_fwd", "ttl_bwd"}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tensorized_rnn"), reason="needs the reference checkout (build container only)")
+def test_patch_reference_switches_the_callers_over():
+    """compat.patch_reference(): the reference's MNIST_Classifier then builds the B200 modules, with the
+    reference's own state_dict layout (keys and shapes identical to an unpatched build)."""
+    import io
+    import sys
+    from contextlib import redirect_stdout
+    import tensorized_rnn_b200.compat as compat
+    sys.path.insert(0, "/root/reference")
+    sys.path.insert(0, "/root/reference/experiments/digit_classification")
+    try:
+        import mnist_classifier as mc
+        with redirect_stdout(io.StringIO()):
+            torch.manual_seed(0)
+            ref = mc.MNIST_Classifier(28, 10, 64, 1, torch.device("cpu"), tt=True, gru=False, n_cores=2, tt_rank=2)
+            n = compat.patch_reference()
+            assert n >= 4
+            torch.manual_seed(0)
+            ours = mc.MNIST_Classifier(28, 10, 64, 1, torch.device("cpu"), tt=True, gru=False, n_cores=2, tt_rank=2)
+        assert isinstance(ours.rnn, tr.TTLSTM) and not isinstance(ref.rnn, tr.TTLSTM)
+        assert isinstance(ours.linear, tr.TTLinear)
+        sd_ref, sd = ref.state_dict(), ours.state_dict()
+        assert list(sd.keys()) == list(sd_ref.keys())
+        for k in sd:
+            assert tuple(sd[k].shape) == tuple(sd_ref[k].shape), k
+            assert torch.equal(sd[k], sd_ref[k].contiguous()), k      # same RNG stream -> identical parameters
+        ours.load_state_dict(sd_ref)
+    finally:
+        compat.unpatch_reference()
+        for p in ("/root/reference/experiments/digit_classification", "/root/reference"):
+            if p in sys.path:
+                sys.path.remove(p)
+    import tensorized_rnn.tt_lstm as ref_tt
+    assert ref_tt.TTLSTM is not tr.TTLSTM
