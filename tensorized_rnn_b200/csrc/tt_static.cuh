@@ -1181,15 +1181,16 @@ struct RnnBwdSArgs {
     long long u_bstride;
 };
 
-template <class S, int R, class TB, int k, bool DWI = true>
+// LASTSYNC = false: no barrier after stage 1 (the caller's next phase does not read X_0 and ends with a barrier)
+template <class S, int R, class TB, int k, bool DWI = true, bool LASTSYNC = true>
 TTS_DEV void fwd_chain_keep(float *xs, const float *hcur, const float *wsm, int tid) {
     if constexpr (k >= 1) {
         using SM = BwdSmem<S, R, TB, DWI>;
         using TU = typename TB::F;
         const float *X = (k == S::D - 1) ? hcur : xs + SM::template XOff<k>::v;
         fwd_stage<S, k, R, TU::TMr[k], TU::TN[k]>(X, wsm + WOff<S, k>::v, xs + SM::template XOff<k - 1>::v, tid);
-        __syncthreads();
-        fwd_chain_keep<S, R, TB, k - 1, DWI>(xs, hcur, wsm, tid);
+        if constexpr (k > 1 || LASTSYNC) __syncthreads();
+        fwd_chain_keep<S, R, TB, k - 1, DWI, LASTSYNC>(xs, hcur, wsm, tid);
     }
 }
 
@@ -1447,7 +1448,10 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                                        t / XW - 1, tid);
             }
             // ---- recompute the hh chain keeping every X_k
-            if constexpr (!SAVED) fwd_chain_keep<S, R, TB, S::D - 1, DWI>(xs, hcur, wsm, tid);
+            // kept-gates kernels: the gate phase below reads neither X_0 nor anything stage 1 writes, so there is
+            // no barrier between them -- warps still in stage 1 (FFMA2-bound) overlap with warps already in the
+            // latency-bound gate phase; the barrier after the gate phase orders X_0 / dY_0 for the backward chain
+            if constexpr (!SAVED) fwd_chain_keep<S, R, TB, S::D - 1, DWI, !SAVEU>(xs, hcur, wsm, tid);
             if constexpr (!SAVEU) {
                 float acc[R][FM::TMr][FM::TI][4];
                 final_partial<S, R, FM>((S::D == 1) ? hcur : xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg,
