@@ -34,6 +34,11 @@ std::atomic<long long> g_opt_save_u_bytes{16LL << 30};
 // multiply-adds per row (and the shape fits the GEMM tiles); 0 disables
 std::atomic<long long> g_opt_row_plan{1};      // two-phase row plans of the static BPTT kernels
 std::atomic<long long> g_opt_dense_ih{1};
+// split backward (cfg5-class chains): accumulate the hh core gradients through the dense order
+// dW_hh^T = H_prev^T delta (one GEMM pass, then an H-row projection onto the cores) instead of a second
+// chain pass per row (recompute + dX chain + dW chain): 4.2 M vs 3.5 M multiply-adds per row at H = 1024,
+// but in GEMM form (measured ~67 % vs ~50 % of the FFMA peak)
+std::atomic<long long> g_opt_dense_hh{1};
 std::atomic<long long> g_opt_dense_ratio{130};
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
@@ -285,6 +290,10 @@ bool dense_ih_bwd_ok(const ChainPlan &ih, bool want_dx, const ttrnn_tt_shape *sh
     return dense_ih_ok(ih, shape) && (!want_dx || ih.n_in % ttg::BN == 0);
 }
 
+bool dense_hh_dw_ok(const ChainPlan &hh) {
+    return g_opt_dense_hh.load() && hh.n_out % ttg::BN == 0 && hh.n_in % 4 == 0 && hh.n_in <= 2048;
+}
+
 struct DenseIh {
     float *eye, *wt, *w, *dwt, *dbias, *part, *pbias;
 };
@@ -303,7 +312,7 @@ struct RnnLayout {
     // fwd scratch (floats)
     long long f_xg = 0, f_sh = 0, f_sc = 0, f_hs = 0, f_aux = 0, f_dense = 0, f_total = 0;
     // bwd scratch (floats)
-    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_dense = 0, b_total = 0;
+    long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_dense = 0, b_dense_hh = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
     int nslots = 0;
     // kept chain activations (two-core static chains, within the save_bytes budget): per layer offsets into `saved`
@@ -403,6 +412,14 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->b_spill = o; o += r4(spill) * lo->nslots;
     lo->b_aux = o; o += 2 * r4(GH) + 4;                   // rank-one input mode: W_ih column, its gradient, a 1.0f
     lo->b_dense = o; o += dbw;
+    long long dhh = 0;                                    // split backward: dense accumulation of the hh core gradients
+    if (g_opt_static.load())
+        for (int l = 0; l < L; ++l) {
+            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)g_opt_srows_bwd.load(), 0);
+            if (be && be->split && dense_hh_dw_ok(rp.layer[l].hh) && dense_bwd_floats(rp.layer[l].hh) > dhh)
+                dhh = dense_bwd_floats(rp.layer[l].hh);
+        }
+    lo->b_dense_hh = o; o += dhh;
     lo->b_total = o;
     return 0;
 }
@@ -664,6 +681,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
     if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
     if (!strcmp(key, "row_plan")) { g_opt_row_plan.store(value); return 0; }
+    if (!strcmp(key, "dense_hh_dw")) { g_opt_dense_hh.store(value); return 0; }
     if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
     return 1;
@@ -1023,6 +1041,15 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             float *aux_g = aux + r4(GH);
             float *one = aux_g + r4(GH);
             int ih_used = 0;
+            const bool dense_hh = be->split && dense_hh_dw_ok(lp.hh);
+            DenseIh DH;
+            int hh_dense_calls = 0;
+            if (dense_hh) {
+                dense_carve(sc + lo.b_dense_hh, lp.hh, true, &DH);
+                ttg::k_eye<<<1024, 256, 0, st>>>(DH.eye, H);
+                ++g_launches;
+                CU_CHECK(cudaGetLastError());
+            }
             if (mode == tts::MODE_RANK1) {
                 k_fill<<<1, 32, 0, st>>>(one, 1.0f, 1);
                 ++g_launches;
@@ -1052,8 +1079,17 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     sa.dh_out = sdh; sa.dc_out = sdc;
                     if (launch_plan(sa)) return 1;
                     if (be->split) {
-                        // hh core gradients: batched TT-matvec backward over rows (h_{t-1}, delta_t) of this chunk
+                        // hh core gradients over rows (h_{t-1}, delta_t) of this chunk: dense accumulation of
+                        // dW_hh^T = H_prev^T delta (projected onto the cores after the last chunk), or a batched
+                        // TT-matvec backward (second chain pass) when the dense order is disabled / does not fit
                         auto hh_dw = [&](const float *xp, long long xbs, const float *dyp, long long rows, int rpb) {
+                            if (dense_hh) {
+                                if (dense_dw(dv, rows, rpb, xp, xbs, H, dyp, (long long)tc * GH, GH, DH, hh_dense_calls > 0,
+                                             false, st))
+                                    return 1;
+                                ++hh_dense_calls;
+                                return 0;
+                            }
                             return launch_ttlinear_bwd(lp.hh, dv, rows, rpb, xp, xbs, params + lp.off_hh_cores, dyp,
                                                        (long long)tc * GH, nullptr, 0, part_hh, lo.nslots,
                                                        sc + lo.b_spill, 0, st, &hh_used, &d->hh[l]);
@@ -1068,6 +1104,12 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     if (project_bwd(t0, tc, &ih_used)) return 1;
                 }
                 if (project_finish(&ih_used)) return 1;
+                if (dense_hh && hh_dense_calls > 0) {
+                    // dense dW_hh^T -> TT cores: H-row TT-matvec backward with the identity as input
+                    if (launch_ttlinear_bwd(lp.hh, dv, H, H, DH.eye, 0, params + lp.off_hh_cores, DH.dwt, 0, nullptr, 0,
+                                            part_hh, lo.nslots, sc + lo.b_spill, 0, st, &hh_used, &d->hh[l]))
+                        return 1;
+                }
             }
             // fold the per-CTA slots into the gradient blob
             const long long cf = lp.hh.core_floats;

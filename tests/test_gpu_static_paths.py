@@ -201,6 +201,34 @@ def test_dense_route_split_reduction_and_chunk_accumulation():
         assert rel_err(a, b) <= GRAD_TOL
 
 
+def test_split_backward_dense_and_chain_core_gradients_agree():
+    """cfg5-class chain (H = 1024, d4 r8: split backward).  The hh core gradients accumulated densely
+    (dW_hh^T = H_prev^T delta, then projected onto the cores) must equal the second-chain-pass route."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    torch.manual_seed(47)
+    m = quiet(tr.TTLSTM, 256, 1024, 1, torch.device("cpu"), n_cores=4, tt_rank=8).to(dev)
+    x = torch.rand(70, 9, 256, device=dev)
+    h0 = 0.2 * torch.randn(70, 1024, device=dev)
+    c0 = 0.2 * torch.randn(70, 1024, device=dev)
+    w = torch.randn(70, 9, 1024, device=dev)
+    res = []
+    for flag, chunk in ((1, 4), (0, 0)):
+        lib.ttrnn_set_option(b"dense_hh_dw", flag)
+        lib.ttrnn_set_option(b"chunk_steps", chunk)
+        try:
+            for p in m.parameters():
+                p.grad = None
+            out, (h, c) = m(x, (h0, c0))
+            ((out * w).sum() + c.sum()).backward()
+            res.append([p.grad.clone() for p in m.parameters()])
+        finally:
+            lib.ttrnn_set_option(b"dense_hh_dw", 1)
+            lib.ttrnn_set_option(b"chunk_steps", 0)
+    for a, b in zip(res[0], res[1]):
+        assert rel_err(a, b) <= GRAD_TOL
+
+
 def test_two_phase_row_plan_matches_single_variant():
     """A batch that does not fill whole waves of the best BPTT variant runs in two phases (tail rows on a variant
     with fewer rows per CTA, row-offset pointers, shared gradient slots).  Must equal the one-variant launch."""
