@@ -1130,7 +1130,7 @@ struct TuneB {
 // DWI = false: X_k slots ping-pong like the forward kernel; the kernel only propagates dh/dc and writes
 //              delta; the core gradients come from a batched TT-matvec backward over (h_{t-1}, delta)
 //              ("split" backward, for chains whose kept slots exceed shared memory)
-template <class S, int R, class TB, bool DWI = true>
+template <class S, int R, class TB, bool DWI = true, int SV = 0>
 struct BwdSmem {
     static constexpr int D = S::D;
     using TU = typename TB::F;
@@ -1154,8 +1154,8 @@ struct BwdSmem {
     static constexpr int DHC = cr4(R * St<S, D - 1>::BS);
     static constexpr int XCH = cmax(FM::XCH_FLOATS, BdMap<S, D - 1, R, TB::BTM[D - 1], TB::BSP>::XCH_FLOATS);
     static constexpr int H2 = cr4(R * St<S, D - 1>::BS);          // second h_{t-1} slot (cp.async double buffer)
-    static constexpr int X1W = DWI ? 2 * R * XW : 0;              // rank-one input windows (kept-gates kernels)
-    static constexpr int DHO = DWI ? cr4(R * n_in<S>()) : 0;      // upstream-gradient tile dOut[:, t, :] (kept-gates kernels)
+    static constexpr int X1W = (SV != 0) ? 2 * R * XW : 0;        // rank-one input windows (kept-gates kernels)
+    static constexpr int DHO = (SV != 0) ? cr4(R * n_in<S>()) : 0; // upstream-gradient tile dOut[:, t, :] (kept-gates kernels)
     static constexpr int TOTAL = W + WT + XALL + DY + DHC + XCH + H2 + X1W + DHO;
     static constexpr size_t BYTES = (size_t)TOTAL * 4;
 };
@@ -1242,9 +1242,12 @@ template <class S, int CELL, int R, int MODE, class TB, bool DWI = true, int SV 
 __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
     constexpr bool SAVED = (SV == 1), SAVEU = (SV != 0);
     static_assert(!SAVED || (S::D == 2 && DWI), "saved-activation backward is implemented for two-core chains");
-    static_assert(!SAVEU || DWI, "kept pre-activations need the fused backward");
+    // DWI = false with kept gates: nothing of the forward chain is needed (gates come from the forward pass, the
+    // core gradients from the dense accumulation outside): the kernel runs the gate gradients and the dX chain only
+    constexpr bool RECOMPUTE = !SAVED && (DWI || !SAVEU);
+    constexpr bool NEED_H = DWI || !SAVEU || (CELL != TTRNN_CELL_LSTM);
     extern __shared__ __align__(16) float smem[];
-    using SM = BwdSmem<S, R, TB, DWI>;
+    using SM = BwdSmem<S, R, TB, DWI, SV>;
     static_assert(DWI || (CELL == TTRNN_CELL_LSTM && MODE == MODE_XG),
                   "split backward: delta_hh must equal delta_ih (LSTM) and be written to the xg buffer");
     using FM = typename SM::FM;
@@ -1387,7 +1390,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
                 }
             }
         };
-        fetch_h(smem + (((a.steps - 1) & 1) ? HOFF1 : HOFF0), a.t0 + a.steps - 1);
+        if constexpr (NEED_H) fetch_h(smem + (((a.steps - 1) & 1) ? HOFF1 : HOFF0), a.t0 + a.steps - 1);
         if constexpr (SAVEU) {
             fetch_dho(a.t0 + a.steps - 1);
             if (MODE == MODE_RANK1) {
@@ -1438,7 +1441,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             }
             // request the operands of step t-1 now; they land while this step computes
             if (t > 0) {
-                fetch_h(smem + (((t - 1) & 1) ? HOFF1 : HOFF0), tg - 1);
+                if constexpr (NEED_H) fetch_h(smem + (((t - 1) & 1) ? HOFF1 : HOFF0), tg - 1);
                 if constexpr (!SAVEU) fetch_regs(t - 1);
             }
             if constexpr (SAVEU) {
@@ -1451,7 +1454,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             // kept-gates kernels: the gate phase below reads neither X_0 nor anything stage 1 writes, so there is
             // no barrier between them -- warps still in stage 1 (FFMA2-bound) overlap with warps already in the
             // latency-bound gate phase; the barrier after the gate phase orders X_0 / dY_0 for the backward chain
-            if constexpr (!SAVED) fwd_chain_keep<S, R, TB, S::D - 1, DWI, !SAVEU>(xs, hcur, wsm, tid);
+            if constexpr (RECOMPUTE) fwd_chain_keep<S, R, TB, S::D - 1, DWI, !SAVEU>(xs, hcur, wsm, tid);
             if constexpr (!SAVEU) {
                 float acc[R][FM::TMr][FM::TI][4];
                 final_partial<S, R, FM>((S::D == 1) ? hcur : xs + SM::template XOff<0>::v, wsm + WOff<S, 0>::v, mt, itg,

@@ -35,15 +35,17 @@ struct TtsRnnBwdEntry {
     int (*launch)(const tts::RnnBwdSArgs *args, int grid, cudaStream_t st);
     int (*prepare)(int *max_blocks_per_sm);
 };
+// split_kept_ok: with saved == 2, prefer the split variants (gate gradients + dX chain only) when registered;
+// the caller then accumulates the hh core gradients in the dense order
 const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms,
-                                       int prefer_R = 0, int saved = 0);
+                                       int prefer_R = 0, int saved = 0, int split_kept_ok = 0);
 
 // Row plan of one BPTT launch: up to two phases (kernel variant, first row, row count).  When the batch does
 // not fill whole waves of the best variant, the tail runs on a variant with fewer rows per CTA instead of
 // a mostly idle second wave (cfg3: 640 rows = one wave of 148 x 3 rows + one wave of 98 x 2 rows).
 // Returns the number of phases (0 = no registered kernel).
 int tts_plan_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R, int saved,
-                     const TtsRnnBwdEntry *entry[2], long long row0[2], long long rows[2]);
+                     int split_kept_ok, const TtsRnnBwdEntry *entry[2], long long row0[2], long long rows[2]);
 
 struct TtsTtlFwdEntry {
     const char *name;

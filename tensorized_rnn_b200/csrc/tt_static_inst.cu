@@ -82,15 +82,15 @@ const TtsRnnFwdEntry kFwd[] = {
 
 template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0>
 int launch_bwd(const tts::RnnBwdSArgs *a, int grid, cudaStream_t st) {
-    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES, st>>>(*a);
+    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI, SV>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
 template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0>
 int prepare_bwd(int *occ) {
     auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB, DWI>::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB, DWI, SV>::BYTES);
     if (e != cudaSuccess) return (int)e;
-    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB, DWI>::BYTES);
+    return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB, DWI, SV>::BYTES);
 }
 template <class S>
 constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * tts::n_in<S>(); }
@@ -99,17 +99,23 @@ constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * 
     {#S, CELL, MODE, R, 0, 0, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(), &match_shape<S>, \
      &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true>, &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true>}
 #define TTS_BWD_SAVED(S, CELL, R, MODE, ...)                                                                \
-    {#S "(saved)", CELL, MODE, R, 0, 1, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(),      \
+    {#S "(saved)", CELL, MODE, R, 0, 1, tts::BwdSmem<S, R, __VA_ARGS__, true, 1>::BYTES, slot_floats<S>(),   \
      &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 1>,                                   \
      &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 1>}
 #define TTS_BWD_SAVEU(S, CELL, R, MODE, ...)                                                                \
-    {#S "(kept u)", CELL, MODE, R, 0, 2, tts::BwdSmem<S, R, __VA_ARGS__, true>::BYTES, slot_floats<S>(),     \
+    {#S "(kept u)", CELL, MODE, R, 0, 2, tts::BwdSmem<S, R, __VA_ARGS__, true, 2>::BYTES, slot_floats<S>(),  \
      &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 2>,                                   \
      &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, true, 2>}
 #define TTS_BWD_SPLIT(S, CELL, R, MODE, ...)                                                                \
     {#S "(split)", CELL, MODE, R, 1, 0, tts::BwdSmem<S, R, __VA_ARGS__, false>::BYTES, slot_floats<S>(),     \
      &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false>,                                     \
      &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, false>}
+
+// kept gates + split: gate gradients and the dX chain only (no recompute, no in-kernel core gradients)
+#define TTS_BWD_SPLIT_SAVEU(S, CELL, R, MODE, ...)                                                          \
+    {#S "(split, kept u)", CELL, MODE, R, 1, 2, tts::BwdSmem<S, R, __VA_ARGS__, false, 2>::BYTES, slot_floats<S>(), \
+     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false, 2>,                                  \
+     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, false, 2>}
 
 // TuneB<forward Tune, BTM0..3 (rows per thread of bwd-data stage k), BSP (split of the last bwd-data
 // stage), WTK0..3 (kappa rows of the register tile of bwd-weight stage k)>
@@ -146,6 +152,8 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
 };
 
 
@@ -231,17 +239,29 @@ const TtsTtlBwdEntry *tts_find_ttl_bwd(const ttrnn_tt_shape *s, long long rows, 
     return nullptr;
 }
 
+// kept gates (saved == 2): a "split" variant (gate gradients + dX chain only; core gradients by the dense
+// accumulation outside) does a third of the work per row of the fused variant and is preferred when the caller
+// can run the dense accumulation (split_kept_ok)
+static bool use_split_kept(const ttrnn_tt_shape *hh, int cell, int mode, int saved, int split_kept_ok) {
+    if (saved != 2 || !split_kept_ok) return false;
+    for (const auto &e : kBwd)
+        if (e.cell == cell && e.mode == mode && e.saved == 2 && e.split && e.match(hh) && e.smem <= kMaxSmem) return true;
+    return false;
+}
+
 const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R,
-                                       int saved) {
+                                       int saved, int split_kept_ok) {
     const TtsRnnBwdEntry *best = nullptr;
+    const bool only_split = use_split_kept(hh, cell, mode, saved, split_kept_ok);
     if (prefer_R > 0)
         for (const auto &e : kBwd)
             if (e.cell == cell && e.mode == mode && e.saved == saved && e.match(hh) && e.smem <= kMaxSmem &&
-                e.R == prefer_R)
+                e.R == prefer_R && (saved != 2 || (e.split != 0) == only_split))
                 return &e;
     long long best_cost = 0;
     for (const auto &e : kBwd) {
         if (e.cell != cell || e.mode != mode || e.saved != saved || !e.match(hh) || e.smem > kMaxSmem) continue;
+        if (saved == 2 && (e.split != 0) != only_split) continue;
         const long long tiles = (B + e.R - 1) / e.R;
         const long long waves = (tiles + sms - 1) / sms;
         const long long cost = waves * e.R;
@@ -254,16 +274,18 @@ const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int m
 }
 
 int tts_plan_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int mode, long long B, int sms, int prefer_R, int saved,
-                     const TtsRnnBwdEntry *entry[2], long long row0[2], long long rows[2]) {
+                     int split_kept_ok, const TtsRnnBwdEntry *entry[2], long long row0[2], long long rows[2]) {
     entry[0] = entry[1] = nullptr;
     row0[0] = row0[1] = rows[0] = rows[1] = 0;
     if (prefer_R > 0) {
-        entry[0] = tts_find_rnn_bwd(hh, cell, mode, B, sms, prefer_R, saved);
+        entry[0] = tts_find_rnn_bwd(hh, cell, mode, B, sms, prefer_R, saved, split_kept_ok);
         rows[0] = B;
         return entry[0] ? 1 : 0;
     }
+    const bool only_split = use_split_kept(hh, cell, mode, saved, split_kept_ok);
     auto ok = [&](const TtsRnnBwdEntry &e) {
-        return e.cell == cell && e.mode == mode && e.saved == saved && e.match(hh) && e.smem <= kMaxSmem;
+        return e.cell == cell && e.mode == mode && e.saved == saved && e.match(hh) && e.smem <= kMaxSmem &&
+               (saved != 2 || (e.split != 0) == only_split);
     };
     // cost of a wave of R rows per CTA ~ (1 + R): one unit of per-step overhead (barriers, gate phase) per row of work
     auto wave_cost = [&](const TtsRnnBwdEntry &e, long long nrows) {

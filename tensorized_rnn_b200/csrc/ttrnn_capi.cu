@@ -39,6 +39,7 @@ std::atomic<long long> g_opt_dense_ih{1};
 // chain pass per row (recompute + dX chain + dW chain): 4.2 M vs 3.5 M multiply-adds per row at H = 1024,
 // but in GEMM form (measured ~67 % vs ~50 % of the FFMA peak)
 std::atomic<long long> g_opt_dense_hh{1};
+std::atomic<long long> g_opt_split_kept{1};    // kept gates: prefer the dX-only BPTT variants + dense hh core gradients
 std::atomic<long long> g_opt_dense_ratio{130};
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
@@ -415,8 +416,11 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     long long dhh = 0;                                    // split backward: dense accumulation of the hh core gradients
     if (g_opt_static.load())
         for (int l = 0; l < L; ++l) {
+            const bool okd = dense_hh_dw_ok(rp.layer[l].hh);
+            const int oks = (okd && g_opt_split_kept.load()) ? 1 : 0;
             const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)g_opt_srows_bwd.load(), 0);
-            if (be && be->split && dense_hh_dw_ok(rp.layer[l].hh) && dense_bwd_floats(rp.layer[l].hh) > dhh)
+            const TtsRnnBwdEntry *b2 = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)g_opt_srows_bwd.load(), 2, oks);
+            if (okd && ((be && be->split) || (b2 && b2->split)) && dense_bwd_floats(rp.layer[l].hh) > dhh)
                 dhh = dense_bwd_floats(rp.layer[l].hh);
         }
     lo->b_dense_hh = o; o += dhh;
@@ -681,6 +685,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
     if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
     if (!strcmp(key, "row_plan")) { g_opt_row_plan.store(value); return 0; }
+    if (!strcmp(key, "split_kept")) { g_opt_split_kept.store(value); return 0; }
     if (!strcmp(key, "dense_hh_dw")) { g_opt_dense_hh.store(value); return 0; }
     if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
@@ -959,7 +964,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
         if (be && lo.save_mode[l] != 0 && sv) {
             // forward kept (X_0 and) the hh pre-activations of this layer: use the kernel that consumes them
             if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(),
-                                                            lo.save_mode[l]))
+                                                            lo.save_mode[l], dense_hh_dw_ok(lp.hh) && g_opt_split_kept.load()))
                 be = bs;
         }
         if (be) {
@@ -968,11 +973,11 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
             long long ph_row0[2] = {0, 0}, ph_rows[2] = {B, 0};
             int ph_grid[2] = {0, 0};
             int nph = 1;
-            if (!be->split && g_opt_row_plan.load()) {
+            if ((!be->split || be->saved == 2) && g_opt_row_plan.load()) {
                 const TtsRnnBwdEntry *pe[2];
                 long long pr0[2], pr[2];
                 const int np = tts_plan_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), be->saved,
-                                                pe, pr0, pr);
+                                                be->split && be->saved == 2, pe, pr0, pr);
                 if (np >= 1) {
                     nph = np;
                     for (int q = 0; q < np; ++q) { ph_e[q] = pe[q]; ph_row0[q] = pr0[q]; ph_rows[q] = pr[q]; }

@@ -229,6 +229,36 @@ def test_split_backward_dense_and_chain_core_gradients_agree():
         assert rel_err(a, b) <= GRAD_TOL
 
 
+def test_split_kept_gates_backward_matches_fused():
+    """d3r8 LSTM chain with kept gates: the dX-only recurrent kernel + dense accumulation of the hh core gradients
+    (`split_kept`, default) against the fused BPTT kernel that accumulates the core gradients in registers."""
+    dev = torch.device("cuda:0")
+    lib = _lib.load()
+    torch.manual_seed(53)
+    m = quiet(tr.TTLSTM, 40, 256, 2, torch.device("cpu"), n_cores=3, tt_rank=8).to(dev)
+    x = torch.rand(37, 11, 40, device=dev, requires_grad=True)
+    h0 = 0.2 * torch.randn(37, 256, device=dev)
+    c0 = 0.2 * torch.randn(37, 256, device=dev)
+    w = torch.randn(37, 11, 256, device=dev)
+    res = []
+    for flag, chunk in ((1, 4), (0, 0)):
+        lib.ttrnn_set_option(b"split_kept", flag)
+        lib.ttrnn_set_option(b"chunk_steps", chunk)
+        try:
+            for p in m.parameters():
+                p.grad = None
+            x.grad = None
+            h0r, c0r = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+            out, (h, c) = m(x, (h0r, c0r))
+            ((out * w).sum() + 2 * h.sum() + c.sum()).backward()
+            res.append([x.grad.clone(), h0r.grad.clone(), c0r.grad.clone()] + [p.grad.clone() for p in m.parameters()])
+        finally:
+            lib.ttrnn_set_option(b"split_kept", 1)
+            lib.ttrnn_set_option(b"chunk_steps", 0)
+    for a, b in zip(res[0], res[1]):
+        assert rel_err(a, b) <= GRAD_TOL
+
+
 def test_two_phase_row_plan_matches_single_variant():
     """A batch that does not fill whole waves of the best BPTT variant runs in two phases (tail rows on a variant
     with fewer rows per CTA, row-offset pointers, shared gradient slots).  Must equal the one-variant launch."""
