@@ -1135,7 +1135,8 @@ struct BwdSmem {
     static constexpr int D = S::D;
     using TU = typename TB::F;
     using FM = FinMap<S, R, TU::FTMr, TU::FTI, TU::FSK>;
-    static constexpr int W = w_floats<S>();
+    // forward-layout cores are only staged by the kernels that recompute (part of) the chain
+    static constexpr int W = (SV == 1 || (!DWI && SV != 0)) ? 0 : w_floats<S>();
     static constexpr int WT = wt_floats<S>();
     static constexpr int stage_bs(int k) { return slot_floats_of<S>(k); }
     static constexpr int HS0 = cr4(R * stage_bs(S::D - 1));
@@ -1269,7 +1270,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
     float *xw1 = smem + HOFF1 + SM::H2;
     float *dho_s = xw1 + SM::X1W;
 
-    stage_weights_k<S, 0>(a.cores, wsm, tid);
+    if constexpr (SM::W > 0) stage_weights_k<S, 0>(a.cores, wsm, tid);
     stage_weights_t<S, 0>(a.cores, wt, tid);
     for (int e = tid; e < SM::DY; e += NTHR) dy0[e] = 0.f;       // padded gate column stays zero
 

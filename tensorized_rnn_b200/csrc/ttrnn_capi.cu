@@ -355,7 +355,8 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
                 lo->x0f[l] = se->x0_floats;
                 extra1 += r4(B * T * se->x0_floats) + r4(B * T * 4 * H);
             }
-            if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 2)) {
+            const int oks = (dense_hh_dw_ok(rp.layer[l].hh) && g_opt_split_kept.load()) ? 1 : 0;
+            if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 2, oks)) {
                 mode2[l] = 1;
                 extra2 += r4(B * T * 4 * H);
             }
@@ -961,7 +962,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
 
         // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
         const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load()) : nullptr;
-        if (be && lo.save_mode[l] != 0 && sv) {
+        if (g_opt_static.load() && lo.save_mode[l] != 0 && sv) {
             // forward kept (X_0 and) the hh pre-activations of this layer: use the kernel that consumes them
             if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(),
                                                             lo.save_mode[l], dense_hh_dw_ok(lp.hh) && g_opt_split_kept.load()))
