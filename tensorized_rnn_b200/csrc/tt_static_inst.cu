@@ -126,6 +126,9 @@ using TB_d3_R2 = TuneB<Tune<1, 1, 1, 2, 8, 2, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
 // cfg5: split backward (recurrent kernel propagates dh/dc only); last bwd-data stage split 4 ways
 using TB_h1024_split = TuneB<Tune<8, 1, 2, 8, 8, 4, 8, 4, 8>, 8, 4, 4, 2, 4, 4, 4, 4, 4>;
 using TB_d3_R3 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
+// dX-only kernels of the d3r8 chain: no core-gradient registers, so two rows per thread in the bwd-data stages
+using TB_d3_split_R2 = TuneB<Tune<1, 1, 1, 2, 8, 2, 8>, 2, 2, 1, 1, 8, 4, 8, 4, 4>;
+using TB_d3_split_R3 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 2, 2, 1, 1, 8, 4, 8, 4, 4>;
 // d4 r16 (cfg4 shape) training: dX-only kernel with kept gates; last bwd-data stage split 4 ways
 using TB_d4r16_split = TuneB<Tune<4, 1, 4, 8, 8, 8, 8, 4, 8>, 8, 8, 4, 1, 4, 4, 4, 4, 4>;
 const TtsRnnBwdEntry kBwd[] = {
@@ -155,8 +158,8 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d4r16_split),
-    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_R2),
-    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_split_R2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_split_R3),
 };
 
 
