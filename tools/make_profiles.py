@@ -112,3 +112,53 @@ if os.path.exists(lf):
                       open(os.path.join(P, "traffic.json"), "w"), indent=1)
             print("wrote traffic.json", vals)
     print("wrote r1_cfg2_summary.md")
+
+
+def config_summary(cfg_no, title, kernels):
+    """profiles/r1_cfg<N>_summary.md from final_launches_cfg<N>.csv + prof_final_cfg<N>_*.summary.txt"""
+    lf = os.path.join(G, "final_launches_cfg%d.csv" % cfg_no)
+    if not os.path.exists(lf):
+        return
+    txt = [ln for ln in open(lf) if ln.startswith('"')]
+    rd = list(csv.reader(txt))
+    hdr = rd[0]
+    ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+    agg = collections.OrderedDict()
+    for r in rd[1:]:
+        try:
+            v = float(r[vi].replace(",", ""))
+        except ValueError:
+            continue
+        name = r[ki].split("<")[0].split("(")[0].replace("void ", "")
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1; a[1] += v
+    unit = rd[1][hdr.index("Metric Unit")] if len(rd) > 1 else "ns"
+    scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(unit, 1e-3)
+    tot = sum(a[1] for a in agg.values())
+    with open(os.path.join(P, "r1_cfg%d_summary.md" % cfg_no), "w") as f:
+        f.write("# Round 1 (final build) - %s on 1 x B200\n\n" % title)
+        f.write("Command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv python bench.py --config %d --steps 2 --warmup 1 --no-cpu-baseline`\n"
+                "(full launch list: `r1_launches_cfg%d.csv`; durations under ncu are serialised/cold-cache: compare SHARES; `k_ffma_probe` is the peak probe of bench.py)\n\n" % (cfg_no, cfg_no))
+        f.write("## Launch list (all launches of the command, ncu durations)\n\n| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
+        for name, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write("| %s | %d | %.1f | %.1f %% |\n" % (name, n, v * scale, 100 * v / tot))
+        bf = os.path.join(G, "final_cfg%d.json" % cfg_no)
+        if os.path.exists(bf):
+            l = line(bf)
+            f.write("\n## bench.py line of the same build (CUDA events, not under ncu)\n\n```json\n" + json.dumps(l) + "\n```\n\n")
+        for tag, ktitle in kernels:
+            sf = os.path.join(G, "prof_%s.summary.txt" % tag)
+            if os.path.exists(sf):
+                f.write("## %s, ncu --set full --clock-control none\n\n```\n%s```\n\n" % (ktitle, open(sf).read()))
+            cf = os.path.join(G, "prof_%s.cudasass.csv.gz" % tag)
+            if os.path.exists(cf):
+                out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), cf, "10"], capture_output=True, text=True).stdout
+                f.write("Stall samples by phase / source line (`tools/ncu_lines.py`):\n\n```\n" + out + "```\n\n")
+    import shutil
+    shutil.copy(lf, os.path.join(P, "r1_launches_cfg%d.csv" % cfg_no))
+    print("wrote r1_cfg%d_summary.md" % cfg_no)
+
+
+config_summary(3, "cfg3 (GE2E speaker encoder, 3 x TT-LSTM d3 r8, B=640, T=160, fwd+bwd)",
+               [("final_cfg3_bwd", "k_rnn_bwd_s (dX-only, kept gates)"), ("final_cfg3_fwd", "k_rnn_fwd_s"),
+                ("final_cfg3_red", "k_gemm_red (dense core-gradient accumulation)"), ("final_cfg3_rows", "k_gemm_rows (dense ih projection / dX)")])
