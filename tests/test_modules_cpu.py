@@ -194,3 +194,37 @@ def test_patch_reference_switches_the_callers_over():
                 sys.path.remove(p)
     import tensorized_rnn.tt_lstm as ref_tt
     assert ref_tt.TTLSTM is not tr.TTLSTM
+
+
+def test_ih_route_selection_is_host_logic():
+    """Contraction order of the batched ih projection per layer (ttrnn_rnn_ih_route): rank-one for I = 1, dense where
+    I*G*H is at most 1.3x the chain's multiply-adds (4x when no static chain kernel exists), else the TT chain.
+    Pure host logic: runs without a GPU."""
+    import ctypes
+    from tensorized_rnn_b200 import _lib
+    lib = _lib.load()
+
+    def routes(cls, I, H, L, d, r):
+        m = quiet(cls, I, H, L, torch.device("cpu"), n_cores=d, tt_rank=r)
+        desc = m.spec().desc(8, 16)
+        out = []
+        for l in range(L):
+            cm, dm = ctypes.c_int64(0), ctypes.c_int64(0)
+            out.append((lib.ttrnn_rnn_ih_route(ctypes.byref(desc), l, ctypes.byref(cm), ctypes.byref(dm)), cm.value, dm.value))
+        return out
+
+    assert [r[0] for r in routes(tr.TTGRU, 1, 256, 1, 2, 4)] == [2]                       # cfg2: rank-one input
+    r3 = routes(tr.TTLSTM, 40, 256, 3, 3, 8)                                              # cfg3
+    assert [r[0] for r in r3] == [1, 1, 1]
+    assert r3[0][1:] == (87040, 40960) and r3[1][1:] == (327680, 262144)                  # SURVEY 8a-5 / DESIGN 4.5
+    r4 = routes(tr.TTLSTM, 40, 256, 3, 4, 16)                                             # cfg4
+    assert [r[0] for r in r4] == [1, 1, 1] and r4[1][1:] == (2195456, 262144)
+    r5 = routes(tr.TTLSTM, 256, 1024, 1, 4, 8)                                            # cfg5
+    assert r5 == [(1, 933888, 1048576)]
+    assert [r[0] for r in routes(tr.TTLSTM, 30, 50, 1, 3, 4)] == [0]                      # G*H = 200: not a multiple of 128
+    lib.ttrnn_set_option(b"dense_ih", 0)
+    try:
+        assert [r[0] for r in routes(tr.TTLSTM, 40, 256, 3, 3, 8)] == [0, 0, 0]
+    finally:
+        lib.ttrnn_set_option(b"dense_ih", 1)
+    assert lib.ttrnn_set_option(b"no_such_option", 1) != 0
