@@ -175,6 +175,7 @@ int ttrnn_static_kernel_table(char *buf, int32_t cap);
  *                   backward skips the final stage of the chain recompute (default 16 GiB; 0 = recompute)
  *   "row_plan"      0 = one kernel variant per BPTT launch (default 1: a tail variant with fewer rows per
  *                   CTA may run the rows that do not fill a whole wave)
+ *   "gemm_wide"     1 = 128 x 256 CTA tiles for the dense-route row GEMMs (default 0: measured slower)
  *   "split_kept"    kept gates: 0 = never use the dX-only BPTT variants (gate gradients + dX chain in the recurrent
  *                   kernel, hh core gradients accumulated densely outside); default 1 where registered (cfg3 shape)
  *   "dense_hh_dw"   split backward only: 0 = hh core gradients by a second chain pass per row instead of the dense

@@ -51,11 +51,11 @@ __device__ __forceinline__ const float *rag_row(const Rag &g, unsigned r) {
     return g.p + (long long)b * g.bstride + (long long)(r - b * (unsigned)g.rpb) * g.ld;
 }
 
-// one k-step of the register tile: acc[i][jp] += a[i] * b[jp]
-template <int TM>
+// one k-step of the register tile: acc[i][jp] += a[i] * b[jp];  NG float4 column groups (64 columns apart) per thread
+template <int TM, int NG = 2>
 __device__ __forceinline__ void tile_step(const float *__restrict__ As, const float *__restrict__ Bs, int ty, int tx,
-                                          f32x2 (&acc)[TM][4]) {
-    constexpr int BM = 16 * TM;
+                                          f32x2 (&acc)[TM][2 * NG]) {
+    constexpr int BM = 16 * TM, BNV = 64 * NG;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
         float a[TM];
@@ -67,16 +67,17 @@ __device__ __forceinline__ void tile_step(const float *__restrict__ As, const fl
             const float4 t = *reinterpret_cast<const float4 *>(As + kk * BM + 64 + ty * 4);
             a[4] = t.x; a[5] = t.y; a[6] = t.z; a[7] = t.w;
         }
-        const float4 b0 = *reinterpret_cast<const float4 *>(Bs + kk * BN + tx * 4);
-        const float4 b1 = *reinterpret_cast<const float4 *>(Bs + kk * BN + 64 + tx * 4);
-        const f32x2 w0 = pk2(b0.x, b0.y), w1 = pk2(b0.z, b0.w), w2 = pk2(b1.x, b1.y), w3 = pk2(b1.z, b1.w);
+        f32x2 w[2 * NG];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) {
-            ffma2(acc[i][0], a[i], w0);
-            ffma2(acc[i][1], a[i], w1);
-            ffma2(acc[i][2], a[i], w2);
-            ffma2(acc[i][3], a[i], w3);
+        for (int h = 0; h < NG; ++h) {
+            const float4 b = *reinterpret_cast<const float4 *>(Bs + kk * BNV + h * 64 + tx * 4);
+            w[2 * h] = pk2(b.x, b.y);
+            w[2 * h + 1] = pk2(b.z, b.w);
         }
+#pragma unroll
+        for (int i = 0; i < TM; ++i)
+#pragma unroll
+            for (int j = 0; j < 2 * NG; ++j) ffma2(acc[i][j], a[i], w[j]);
     }
 }
 
@@ -99,16 +100,19 @@ struct GemmRowsArgs {
     Rag c;                   // rows x N (written)
 };
 
-template <int TM>
-__global__ void __launch_bounds__(NT, 2) k_gemm_rows(const __grid_constant__ GemmRowsArgs g) {
-    constexpr int BM = 16 * TM;
+// NG = 2: 128-column CTA tile, 8x8 thread tile, two CTAs per SM;  NG = 4: 256-column CTA tile, 8x16 thread tile,
+// one CTA per SM (operand floats per FMA drop from 0.25 to 0.19: the shared-memory pipe stops co-limiting)
+template <int TM, int NG = 2>
+__global__ void __launch_bounds__(NT, NG == 2 ? 2 : 1) k_gemm_rows(const __grid_constant__ GemmRowsArgs g) {
+    constexpr int BM = 16 * TM, BNV = 64 * NG;
     constexpr int AV = BM / 64;                  // float4 loads of A per thread per k-step
+    constexpr int F4R = BNV / 4, RPP = NT / F4R, NPASS = BK / RPP;   // B loader: float4 per row, rows per pass, passes
     __shared__ __align__(16) float As[2][BK * BM];
-    __shared__ __align__(16) float Bs[2][BK * BN];
+    __shared__ __align__(16) float Bs[2][BK * BNV];
     const int tid = threadIdx.x;
-    const int tiles_n = g.N / BN;
+    const int tiles_n = g.N / BNV;
     const unsigned tile_m = blockIdx.x / tiles_n;
-    const int n0 = (blockIdx.x % tiles_n) * BN;
+    const int n0 = (blockIdx.x % tiles_n) * BNV;
     const unsigned r0 = tile_m * BM;
     int ty, tx;
     thread_coords(tid, ty, tx);
@@ -117,10 +121,10 @@ __global__ void __launch_bounds__(NT, 2) k_gemm_rows(const __grid_constant__ Gem
     const int am = tid % BM, akq = tid / BM;     // BM = 128: akq in {0,1} (+2); BM = 64: akq in 0..3
     const bool arow_ok = r0 + am < g.rows;
     const float *arow = arow_ok ? rag_row(g.a, r0 + am) : g.a.p;
-    // B loader: rows bk, bk + 8; float4 column bn4
-    const int bk = tid >> 5, bn4 = tid & 31;
+    // B loader: rows bk + RPP * v; float4 column bn4
+    const int bk = tid / F4R, bn4 = tid % F4R;
 
-    float4 ra[AV], rb[2];
+    float4 ra[AV], rb[NPASS];
     auto load_g = [&](int k0) {
 #pragma unroll
         for (int v = 0; v < AV; ++v) {
@@ -128,8 +132,8 @@ __global__ void __launch_bounds__(NT, 2) k_gemm_rows(const __grid_constant__ Gem
             ra[v] = (arow_ok && k < g.K) ? ldg4(arow + k) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int v = 0; v < 2; ++v) {
-            const int k = k0 + bk + 8 * v;
+        for (int v = 0; v < NPASS; ++v) {
+            const int k = k0 + bk + RPP * v;
             rb[v] = (k < g.K) ? ldg4(g.b + (long long)k * g.ldb + n0 + bn4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
@@ -140,14 +144,14 @@ __global__ void __launch_bounds__(NT, 2) k_gemm_rows(const __grid_constant__ Gem
             d[0] = ra[v].x; d[BM] = ra[v].y; d[2 * BM] = ra[v].z; d[3 * BM] = ra[v].w;
         }
 #pragma unroll
-        for (int v = 0; v < 2; ++v) *reinterpret_cast<float4 *>(Bs[buf] + (bk + 8 * v) * BN + bn4 * 4) = rb[v];
+        for (int v = 0; v < NPASS; ++v) *reinterpret_cast<float4 *>(Bs[buf] + (bk + RPP * v) * BNV + bn4 * 4) = rb[v];
     };
 
-    f32x2 acc[TM][4];
+    f32x2 acc[TM][2 * NG];
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
+        for (int j = 0; j < 2 * NG; ++j) acc[i][j] = 0ull;
 
     load_g(0);
     store_s(0);
@@ -156,15 +160,15 @@ __global__ void __launch_bounds__(NT, 2) k_gemm_rows(const __grid_constant__ Gem
     for (int k0 = 0; k0 < g.K; k0 += BK) {
         const bool more = k0 + BK < g.K;
         if (more) load_g(k0 + BK);
-        tile_step<TM>(As[buf], Bs[buf], ty, tx, acc);
+        tile_step<TM, NG>(As[buf], Bs[buf], ty, tx, acc);
         if (more) store_s(buf ^ 1);
         __syncthreads();
         buf ^= 1;
     }
 
-    float4 bv[2];
+    float4 bv[NG];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < NG; ++h) {
         const int n = n0 + h * 64 + tx * 4;
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
         if (g.bias) { const float4 t = ldg4(g.bias + n); s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(NT, 2) k_gemm_rows(const __grid_constant__ Gem
         if (r >= g.rows) continue;
         float *crow = const_cast<float *>(rag_row(g.c, r)) + n0 + tx * 4;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < NG; ++h) {
             float4 v;
             upk2(acc[i][2 * h], v.x, v.y);
             upk2(acc[i][2 * h + 1], v.z, v.w);

@@ -38,6 +38,9 @@ std::atomic<long long> g_opt_dense_ih{1};
 // dW_hh^T = H_prev^T delta (one GEMM pass, then an H-row projection onto the cores) instead of a second
 // chain pass per row (recompute + dX chain + dW chain): 4.2 M vs 3.5 M multiply-adds per row at H = 1024,
 // but in GEMM form (measured ~67 % vs ~50 % of the FFMA peak)
+// dense-route row GEMMs: 128 x 256 CTA tiles (8 x 16 thread tiles, one CTA per SM) when N % 256 == 0.  Off: measured
+// 7 % slower than the 128 x 128 / two-CTA variant on cfg3 and cfg4 (8 warps per SM do not cover the LDS latency).
+std::atomic<long long> g_opt_gemm_wide{0};
 std::atomic<long long> g_opt_dense_hh{1};
 std::atomic<long long> g_opt_split_kept{1};    // kept gates: prefer the dX-only BPTT variants + dense hh core gradients
 std::atomic<long long> g_opt_dense_ratio{130};
@@ -587,11 +590,13 @@ int dense_rows_gemm(int kind, long long rows, int rpb, const float *a, long long
     g.a.p = a; g.a.bstride = a_bstride; g.a.rpb = rpb; g.a.ld = K;
     g.b = b; g.ldb = N; g.bias = bias; g.bias2 = bias2;
     g.c.p = c; g.c.bstride = c_bstride; g.c.rpb = rpb; g.c.ld = N;
-    const long long tiles = ((rows + 127) / 128) * (N / ttg::BN);
+    const bool wide = g_opt_gemm_wide.load() && N % 256 == 0;       // 128 x 256 CTA tile, 8 x 16 thread tile
+    const long long tiles = ((rows + 127) / 128) * (N / (wide ? 256 : ttg::BN));
     if (tiles > 0x7fffffffLL) return fail("dense ih projection: too many tiles");
     {
         KernelTimer tm(kind, st);
-        ttg::k_gemm_rows<8><<<(unsigned)tiles, ttg::NT, 0, st>>>(g);
+        if (wide) ttg::k_gemm_rows<8, 4><<<(unsigned)tiles, ttg::NT, 0, st>>>(g);
+        else ttg::k_gemm_rows<8, 2><<<(unsigned)tiles, ttg::NT, 0, st>>>(g);
     }
     ++g_launches;
     CU_CHECK(cudaGetLastError());
@@ -686,6 +691,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "static_rows_fwd")) { g_opt_srows_fwd.store(value); return 0; }
     if (!strcmp(key, "static_rows_bwd")) { g_opt_srows_bwd.store(value); return 0; }
     if (!strcmp(key, "row_plan")) { g_opt_row_plan.store(value); return 0; }
+    if (!strcmp(key, "gemm_wide")) { g_opt_gemm_wide.store(value); return 0; }
     if (!strcmp(key, "split_kept")) { g_opt_split_kept.store(value); return 0; }
     if (!strcmp(key, "dense_hh_dw")) { g_opt_dense_hh.store(value); return 0; }
     if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
