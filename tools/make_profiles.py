@@ -34,18 +34,27 @@ with open(os.path.join(P, "r1_all_configs.md"), "w") as f:
     for l in raw:
         f.write("```json\n" + json.dumps(l) + "\n```\n")
     sc = []
+    nraw = 0
     for c in (2, 3):
-        f8, f1 = os.path.join(G, "scale8_cfg%d.json" % c), os.path.join(G, "final_cfg%d.json" % c)
-        if os.path.exists(f8) and os.path.exists(f1):
-            a, b = line(f1), line(f8)
-            sc.append("| %d (%s, %s) | %.2f ms/step, %.3e/s | %.2f ms/step, %.3e/s | %.2fx |" % (
-                c, a["config"]["mode"], "one flat NCCL all-reduce of the TT-core gradients per step", a["ms_per_step"], a["value"],
-                b["ms_per_step"], b["value"], b["value"] / a["value"]))
-            raw.append(b)
+        f1 = os.path.join(G, "final_cfg%d.json" % c)
+        if not os.path.exists(f1):
+            continue
+        a = line(f1)
+        cells = ["%d (%s)" % (c, a["config"]["mode"]), "%.2f ms, %.3e/s" % (a["ms_per_step"], a["value"])]
+        for n in (2, 4, 8):
+            fn = os.path.join(G, "scale%d_cfg%d.json" % (n, c))
+            if os.path.exists(fn):
+                b = line(fn)
+                cells.append("%.2f ms, %.3e/s (%.2fx)" % (b["ms_per_step"], b["value"], b["value"] / a["value"]))
+                raw.append(b); nraw += 1
+            else:
+                cells.append("-")
+        sc.append("| " + " | ".join(cells) + " |")
     if sc:
-        f.write("\nWeak scaling (fixed per-GPU batch; `gpurun --gpus 8`, torchrun, NCCL; max over ranks of device time):\n\n"
-                "| cfg | 1 GPU | 8 GPUs | scaling |\n|---|---|---|---:|\n" + "\n".join(sc) + "\n\n```json\n"
-                + "\n".join(json.dumps(x) for x in raw[-len(sc):]) + "\n```\n")
+        f.write("\nWeak scaling (fixed per-GPU batch; `gpurun --gpus N`, torchrun, NCCL, one flat all-reduce of the TT-core gradients per\n"
+                "step; max over ranks of device time):\n\n"
+                "| cfg | 1 GPU | 2 GPUs | 4 GPUs | 8 GPUs |\n|---|---|---|---|---|\n" + "\n".join(sc) + "\n\n```json\n"
+                + "\n".join(json.dumps(x) for x in raw[-nraw:]) + "\n```\n")
     rf = os.path.join(G, "final_reference_cfg2.json")
     if os.path.exists(rf):
         f.write("\nReference arm (`bench.py --impl reference`, oracle port of the reference's PyTorch path on the host cores):\n\n```json\n"
