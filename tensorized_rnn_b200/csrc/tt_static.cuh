@@ -1437,8 +1437,6 @@ __global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ R
             float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE], pre[R][NE][4];
 #pragma unroll
             for (int b = 0; b < R; ++b) {
-                const long long row = row0 + b;
-                const bool ok = b < nvalid;
                 if constexpr (SAVEU) x1[b] = (MODE == MODE_RANK1) ? xw1[((t / XW) & 1) * R * XW + b * XW + (t % XW)] : 0.f;
                 else x1[b] = x1_n[b];
 #pragma unroll

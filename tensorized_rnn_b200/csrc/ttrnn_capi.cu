@@ -166,11 +166,6 @@ long long smem_rnn_bwd_fixed(const ChainPlan &p, int R, int H, int G) {
     return 2LL * p.w_floats + (G == 4 ? 0 : 2 * r4(G * H)) + (long long)R * (p.g_BS + p.in_BS) +
            r4((long long)R * G * H) + 3 * r4((long long)R * H);
 }
-// ... plus the shared-memory X_k slots (p.all_floats reflects the current placement)
-long long smem_ttlin_bwd(const ChainPlan &p, int R) { return smem_ttlin_bwd_fixed(p, R) + (long long)R * p.all_floats; }
-long long smem_rnn_bwd(const ChainPlan &p, int R, int H, int G) {
-    return smem_rnn_bwd_fixed(p, R, H, G) + (long long)R * p.all_floats;
-}
 
 template <class F>
 int pick_rows(F smem_floats, int smem_limit_bytes, int rmax, long long units, int sms, int want_ctas_per_sm) {
