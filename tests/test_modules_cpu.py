@@ -228,3 +228,26 @@ def test_ih_route_selection_is_host_logic():
     finally:
         lib.ttrnn_set_option(b"dense_ih", 1)
     assert lib.ttrnn_set_option(b"no_such_option", 1) != 0
+
+
+def test_header_is_valid_c_and_matches_the_binding():
+    """include/ttrnn_b200.h must compile as plain C99 (it is the drop-in boundary for non-C++ hosts) and declare
+    exactly the functions the ctypes binding knows."""
+    import shutil
+    import subprocess
+    import tempfile
+    from tensorized_rnn_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "ttrnn_b200.h")
+    gcc = shutil.which("gcc")
+    if gcc:
+        with tempfile.TemporaryDirectory() as td:
+            src = os.path.join(td, "t.c")
+            with open(src, "w") as f:
+                f.write('#include "ttrnn_b200.h"\nint main(void) { ttrnn_rnn_desc d; (void)d; return TTRNN_ABI_VERSION == 2 ? 0 : 1; }\n')
+            res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), src],
+                                 capture_output=True, text=True)
+            assert res.returncode == 0, res.stderr
+    text = open(hdr).read()
+    declared = set(re.findall(r"\b(ttrnn_[a-z0-9_]+)\s*\(", text))
+    assert declared == set(_lib.SYMBOLS), (declared ^ set(_lib.SYMBOLS))
