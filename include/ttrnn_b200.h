@@ -26,7 +26,8 @@
 extern "C" {
 #endif
 
-#define TTRNN_ABI_VERSION 2   /* 2: + cell step, ih route query, static kernel table */
+#define TTRNN_ABI_VERSION 3   /* 2: + cell step, ih route query, static kernel table; 3: execution plan carried by
+                                 ttrnn_rnn_workspace, GEMM probe, GE2E head, dense cells */
 #define TTRNN_MAX_CORES   6
 #define TTRNN_MAX_LAYERS  8
 
@@ -68,10 +69,17 @@ typedef struct ttrnn_rnn_desc {
     ttrnn_tt_shape hh[TTRNN_MAX_LAYERS];   /* (G*H) x H                      */
 } ttrnn_rnn_desc;
 
+#define TTRNN_PLAN_WORDS 24
 typedef struct ttrnn_rnn_workspace {
     int64_t saved_bytes;        /* forward -> backward activations (training only) */
     int64_t fwd_scratch_bytes;  /* scratch for one forward call                    */
     int64_t bwd_scratch_bytes;  /* scratch for one backward call                   */
+    /* Execution plan, written by ttrnn_rnn_workspace_bytes(): an opaque snapshot of every tuning option that
+     * decides a buffer layout or a kernel route (chunk length, kept-activation mode, ih route, rows per CTA ...).
+     * ttrnn_rnn_forward / ttrnn_rnn_backward run from THIS copy, never from the process-wide options, so
+     * changing an option between a forward and its backward cannot change how `saved` is interpreted.
+     * Pass the same struct to the forward and to its backward. */
+    int64_t plan[TTRNN_PLAN_WORDS];
 } ttrnn_rnn_workspace;
 
 int         ttrnn_abi_version(void);
@@ -84,9 +92,11 @@ int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *w
 
 /* Forward over the whole stack.  h0 / c0 may be NULL (zeros); one (h0, c0) seeds
  * every layer (lstm.py:120-121).  c0 / cT / d_c* are ignored for GRU.
+ * `ws` = the struct ttrnn_rnn_workspace_bytes() filled for this desc (sizes + execution plan).
  * `saved` NULL = inference (nothing kept for backward).  Returns outputs of the
  * last layer for every t, and (h_T, c_T) of the last layer (lstm.py:135). */
-int ttrnn_rnn_forward(const ttrnn_rnn_desc *desc, const float *x, const float *h0, const float *c0,
+int ttrnn_rnn_forward(const ttrnn_rnn_desc *desc, const ttrnn_rnn_workspace *ws,
+                      const float *x, const float *h0, const float *c0,
                       const float *params, float *out, float *hT, float *cT,
                       void *saved, void *scratch, void *stream);
 
@@ -95,7 +105,8 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *desc, const float *x, const float *h
  * NULL = zero).  d_params is OVERWRITTEN with the gradient blob.  d_x (B,T,I) may
  * be NULL.  d_h0 / d_c0 (B,H) may be NULL; they receive the SUM over layers
  * because every layer shares the same initial state. */
-int ttrnn_rnn_backward(const ttrnn_rnn_desc *desc, const float *x, const float *h0, const float *c0,
+int ttrnn_rnn_backward(const ttrnn_rnn_desc *desc, const ttrnn_rnn_workspace *ws,
+                       const float *x, const float *h0, const float *c0,
                        const float *params, const float *out, const void *saved,
                        const float *d_out, const float *d_hT, const float *d_cT,
                        float *d_params, float *d_x, float *d_h0, float *d_c0,
@@ -160,6 +171,14 @@ int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K
 int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row,
                        int64_t *dense_macs_per_row);
 
+/* Execution plan of `desc` under the current options, as text: first line "chunk_steps=.. sms=.. tc_gemm=..", then one
+ * line per layer of key=value pairs (ih_route, ih_fwd_tc / ih_dw_tc = tensor-core GEMMs used, fwd_kernel, fwd_rows =
+ * batch rows per CTA, save_mode, and with training != 0: bwd_kernel, bwd_rows, bwd_phase_rows, optional second phase,
+ * hh_dw, hh_dw_tc).  Needs a CUDA device (the plan depends on its SM count).  Returns characters written, < 0 on error. */
+int ttrnn_rnn_describe(const ttrnn_rnn_desc *desc, int32_t training, char *buf, int32_t cap);
+/* launches of the tcgen05 (tensor-core, 3xTF32) GEMM kernels since the last reset (subset of ttrnn_launch_count) */
+int64_t ttrnn_tc_launch_count(int32_t reset);
+
 /* Host-only: text table of the statically specialised kernels compiled into the library, one line per
  * kernel "kind|name|rows_per_cta|shared_memory_bytes|fits" (fits = 1 when it is within the 227 KB opt-in limit
  * and can be selected).  Returns the number of characters written, < 0 on a bad buffer. */
@@ -182,6 +201,8 @@ int ttrnn_static_kernel_table(char *buf, int32_t cap);
  *                   accumulation dW_hh^T = H_prev^T delta + projection onto the cores (default 1)
  *   "dense_ih"      0 = never take the dense route of the ih projection (default 1)
  *   "dense_ih_ratio" dense route allowed while I*G*H * 100 <= chain multiply-adds * ratio (default 130)
+ *   "tc_gemm"       1 (default) = the dense-route GEMMs run on the tensor cores (tcgen05.mma kind::tf32, error-compensated
+ *                   3xTF32 split, TMA-staged operands, TMEM accumulators) where the shape fits; 0 = FP32 FFMA kernels
  *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of
  *                   recomputing them (default 0 = recompute)
  * returns 0 if the key is known. */

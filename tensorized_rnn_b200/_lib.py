@@ -10,9 +10,10 @@ import ctypes as C
 import os
 from typing import Optional, Sequence
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CORES = 6
 MAX_LAYERS = 8
+PLAN_WORDS = 24
 CELL_LSTM, CELL_GRU = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libttrnn_b200.so")
@@ -34,7 +35,10 @@ class RnnDesc(C.Structure):
 
 
 class RnnWorkspace(C.Structure):
-    _fields_ = [("saved_bytes", C.c_int64), ("fwd_scratch_bytes", C.c_int64), ("bwd_scratch_bytes", C.c_int64)]
+    # `plan`: opaque execution plan stamped by ttrnn_rnn_workspace_bytes(); the same struct goes to the forward and
+    # to its backward so both interpret `saved` / scratch identically whatever happens to the options in between
+    _fields_ = [("saved_bytes", C.c_int64), ("fwd_scratch_bytes", C.c_int64), ("bwd_scratch_bytes", C.c_int64),
+                ("plan", C.c_int64 * PLAN_WORDS)]
 
 
 # every symbol include/ttrnn_b200.h declares: name -> (restype, argtypes)
@@ -44,8 +48,8 @@ SYMBOLS = {
     "ttrnn_last_error": (C.c_char_p, []),
     "ttrnn_rnn_param_count": (C.c_int64, [C.POINTER(RnnDesc)]),
     "ttrnn_rnn_workspace_bytes": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)]),
-    "ttrnn_rnn_forward": (C.c_int, [C.POINTER(RnnDesc)] + [_P] * 10),
-    "ttrnn_rnn_backward": (C.c_int, [C.POINTER(RnnDesc)] + [_P] * 15),
+    "ttrnn_rnn_forward": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)] + [_P] * 10),
+    "ttrnn_rnn_backward": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)] + [_P] * 15),
     "ttrnn_ttlinear_param_count": (C.c_int64, [C.POINTER(TTShape)]),
     "ttrnn_ttlinear_workspace_bytes": (C.c_int64, [C.POINTER(TTShape), C.c_int64]),
     "ttrnn_ttlinear_forward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 6),
@@ -54,6 +58,8 @@ SYMBOLS = {
     "ttrnn_cell_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 12),
     "ttrnn_rnn_ih_route": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ttrnn_static_kernel_table": (C.c_int, [C.c_char_p, C.c_int32]),
+    "ttrnn_rnn_describe": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.c_char_p, C.c_int32]),
+    "ttrnn_tc_launch_count": (C.c_int64, [C.c_int32]),
     "ttrnn_ffma_probe": (C.c_int, [C.c_int32, _P, C.POINTER(C.c_double), _P]),
     "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
     "ttrnn_kernel_timing": (C.c_int, [C.c_int32]),
@@ -88,11 +94,28 @@ def load() -> C.CDLL:
                      ("dense_ih", "TTRNN_DENSE_IH"), ("dense_ih_ratio", "TTRNN_DENSE_IH_RATIO"),
                      ("save_bytes", "TTRNN_SAVE_BYTES"), ("save_u_bytes", "TTRNN_SAVE_U_BYTES"),
                      ("row_plan", "TTRNN_ROW_PLAN"), ("gemm_wide", "TTRNN_GEMM_WIDE"), ("split_kept", "TTRNN_SPLIT_KEPT"),
-                     ("dense_hh_dw", "TTRNN_DENSE_HH_DW")):
+                     ("dense_hh_dw", "TTRNN_DENSE_HH_DW"), ("tc_gemm", "TTRNN_TC_GEMM")):
         if os.environ.get(env):
             lib.ttrnn_set_option(key.encode(), int(os.environ[env]))
     _lib = lib
     return lib
+
+
+def describe_plan(desc: "RnnDesc", training: bool = True) -> list:
+    """Execution plan of a descriptor (ttrnn_rnn_describe) as a list of dicts: [header, layer 0, layer 1, ...]."""
+    lib = load()
+    buf = C.create_string_buffer(8192)
+    n = lib.ttrnn_rnn_describe(C.byref(desc), 1 if training else 0, buf, 8192)
+    if n < 0:
+        raise RuntimeError("ttrnn_rnn_describe failed: " + last_error())
+    out = []
+    for line in buf.value.decode().strip().split("\n"):
+        ent = {}
+        for tok in line.split():
+            k, _, v = tok.partition("=")
+            ent[k] = int(v) if v.lstrip("-").isdigit() else v
+        out.append(ent)
+    return out
 
 
 def last_error() -> str:

@@ -12,6 +12,7 @@
 #include "tt_kernels.cuh"
 #include "tt_cell.cuh"
 #include "tt_gemm.cuh"
+#include "tt_tc.cuh"
 #include "tt_static.cuh"
 #include "tt_static_api.h"
 
@@ -19,6 +20,7 @@ namespace {
 
 thread_local std::string g_err = "";
 std::atomic<long long> g_launches{0};
+std::atomic<long long> g_tc_launches{0};      // launches of the tcgen05 GEMMs (tt_tc.cuh) among them
 std::atomic<long long> g_opt_rows{0};
 std::atomic<long long> g_opt_chunk{0};
 std::atomic<long long> g_opt_chunk_bytes{4LL << 30};
@@ -44,6 +46,40 @@ std::atomic<long long> g_opt_gemm_wide{0};
 std::atomic<long long> g_opt_dense_hh{1};
 std::atomic<long long> g_opt_split_kept{1};    // kept gates: prefer the dX-only BPTT variants + dense hh core gradients
 std::atomic<long long> g_opt_dense_ratio{130};
+// dense-route GEMMs on the tensor cores (tt_tc.cuh: tcgen05 3xTF32, TMA-staged) where the shape fits; 0 = FP32 FFMA kernels
+std::atomic<long long> g_opt_tc_gemm{1};
+
+// Snapshot of every option that decides a buffer layout or a kernel route.  ttrnn_rnn_workspace_bytes() takes it from the
+// process-wide options and stamps it into ttrnn_rnn_workspace.plan; forward and backward run from THAT copy, so a
+// ttrnn_set_option() between a forward and its backward (another model, another thread) cannot change how `saved` and
+// the scratch buffers are interpreted.  Helpers read the calling thread's current snapshot `t_opt`.
+struct Opts {
+    long long rows, chunk, chunk_bytes, stat, srows_fwd, srows_bwd, save_bytes, save_u_bytes, row_plan, dense_ih, gemm_wide,
+        dense_hh, split_kept, dense_ratio, tc_gemm;
+};
+constexpr int kOptFields = sizeof(Opts) / sizeof(long long);
+constexpr long long kPlanMagic = 0x7474726E6E706C33LL;          // "ttrnnpl3"
+static_assert(kOptFields + 1 <= TTRNN_PLAN_WORDS, "plan does not fit ttrnn_rnn_workspace.plan");
+thread_local Opts t_opt;
+
+Opts snapshot_options() {
+    Opts o;
+    o.rows = g_opt_rows.load(); o.chunk = g_opt_chunk.load(); o.chunk_bytes = g_opt_chunk_bytes.load();
+    o.stat = g_opt_static.load(); o.srows_fwd = g_opt_srows_fwd.load(); o.srows_bwd = g_opt_srows_bwd.load();
+    o.save_bytes = g_opt_save_bytes.load(); o.save_u_bytes = g_opt_save_u_bytes.load(); o.row_plan = g_opt_row_plan.load();
+    o.dense_ih = g_opt_dense_ih.load(); o.gemm_wide = g_opt_gemm_wide.load(); o.dense_hh = g_opt_dense_hh.load();
+    o.split_kept = g_opt_split_kept.load(); o.dense_ratio = g_opt_dense_ratio.load(); o.tc_gemm = g_opt_tc_gemm.load();
+    return o;
+}
+void plan_store(const Opts &o, int64_t *plan) {
+    plan[0] = kPlanMagic;
+    memcpy(plan + 1, &o, sizeof o);
+}
+bool plan_load(const int64_t *plan, Opts *o) {
+    if (!plan || plan[0] != kPlanMagic) return false;
+    memcpy(o, plan + 1, sizeof *o);
+    return true;
+}
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
 struct TimedLaunch { int kind; cudaEvent_t a, b; };
@@ -173,7 +209,7 @@ int pick_rows(F smem_floats, int smem_limit_bytes, int rmax, long long units, in
     for (int r = 1; r <= rmax; ++r)
         if (smem_floats(r) * 4 <= smem_limit_bytes) R = r;
     if (R == 0) return 0;
-    const long long opt = g_opt_rows.load();
+    const long long opt = t_opt.rows;
     if (opt > 0) return (int)(opt < R ? opt : R);
     while (R > 1 && (units + R - 1) / R < (long long)want_ctas_per_sm * sms) --R;
     return R;
@@ -278,10 +314,10 @@ long long chain_macs(const ChainPlan &p) {
 // `shape` (optional): when no statically specialised chain kernel is registered for it, the alternative to the
 // dense order is the ~5-10x slower runtime-shape kernel, so the dense order is allowed up to 4x the chain's MACs
 bool dense_ih_ok(const ChainPlan &ih, const ttrnn_tt_shape *shape = nullptr) {
-    if (!g_opt_dense_ih.load()) return false;
+    if (!t_opt.dense_ih) return false;
     if (ih.n_out % ttg::BN != 0 || ih.n_in % 4 != 0 || ih.n_in < 4 || ih.n_in > 2048) return false;
-    long long ratio = g_opt_dense_ratio.load();
-    if (shape && !(g_opt_static.load() && tts_find_ttl_fwd(shape, 1 << 20)) && ratio < 400) ratio = 400;
+    long long ratio = t_opt.dense_ratio;
+    if (shape && !(t_opt.stat && tts_find_ttl_fwd(shape, 1 << 20)) && ratio < 400) ratio = 400;
     return (long long)ih.n_in * ih.n_out * 100 <= chain_macs(ih) * ratio;
 }
 // dX = delta * W additionally needs I % 128 == 0
@@ -290,16 +326,18 @@ bool dense_ih_bwd_ok(const ChainPlan &ih, bool want_dx, const ttrnn_tt_shape *sh
 }
 
 bool dense_hh_dw_ok(const ChainPlan &hh) {
-    return g_opt_dense_hh.load() && hh.n_out % ttg::BN == 0 && hh.n_in % 4 == 0 && hh.n_in <= 2048;
+    return t_opt.dense_hh && hh.n_out % ttg::BN == 0 && hh.n_in % 4 == 0 && hh.n_in <= 2048;
 }
 
 struct DenseIh {
-    float *eye, *wt, *w, *dwt, *dbias, *part, *pbias;
+    float *eye, *wt, *w, *w_hi, *w_lo, *wt_hi, *wt_lo, *dwt, *dbias, *part, *pbias;
 };
-long long dense_fwd_floats(const ChainPlan &ih) { return r4((long long)ih.n_in * ih.n_in) + r4((long long)ih.n_in * ih.n_out); }
+// forward: identity, W^T (I x G*H), W (G*H x I) and its TF32 hi / lo split (tensor-core route)
+long long dense_fwd_floats(const ChainPlan &ih) { return r4((long long)ih.n_in * ih.n_in) + 4 * r4((long long)ih.n_in * ih.n_out); }
+// backward adds: hi / lo split of W^T (dX on the tensor cores), dW^T, dbias and the split partials
 long long dense_bwd_floats(const ChainPlan &ih) {
     const long long wn = r4((long long)ih.n_in * ih.n_out);
-    return r4((long long)ih.n_in * ih.n_in) + 3 * wn + r4(ih.n_out) + kDenseMaxSplit * (wn + r4(ih.n_out));
+    return dense_fwd_floats(ih) + 3 * wn + r4(ih.n_out) + kDenseMaxSplit * (wn + r4(ih.n_out));
 }
 // ---- workspace layout --------------------------------------------------------------------
 struct RnnLayout {
@@ -324,9 +362,9 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     const long long GH = (long long)rp.G * H;
     lo->BTH = B * T * H;
     lo->BH = B * H;
-    long long tc = g_opt_chunk.load();
+    long long tc = t_opt.chunk;
     if (tc <= 0) {
-        tc = g_opt_chunk_bytes.load() / (B * GH * 4);
+        tc = t_opt.chunk_bytes / (B * GH * 4);
         if (tc < 1) tc = 1;
     }
     if (tc > T) tc = T;
@@ -341,26 +379,26 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     //   mode 1 (two-core chains, "save_bytes" budget, off by default): X_0 tiles + gate activations
     //   mode 2 ("save_u_bytes" budget, default 16 GiB): gate activations only (4*H floats per row and step: LSTM
     //           i,f,g,o; GRU r,z,n,u_n) -- backward skips the final stage of the recompute and all gate math
-    if (g_opt_static.load()) {
+    if (t_opt.stat) {
         long long extra1 = 0, extra2 = 0;
         int mode1[TTRNN_MAX_LAYERS] = {}, mode2[TTRNN_MAX_LAYERS] = {};
         for (int l = 0; l < L; ++l) {
             const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
-            const TtsRnnFwdEntry *se = tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_fwd.load());
+            const TtsRnnFwdEntry *se = tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_fwd);
             if (!se) continue;
-            if (se->x0_floats > 0 && tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 1)) {
+            if (se->x0_floats > 0 && tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, 1)) {
                 mode1[l] = 1;
                 lo->x0f[l] = se->x0_floats;
                 extra1 += r4(B * T * se->x0_floats) + r4(B * T * 4 * H);
             }
-            const int oks = (dense_hh_dw_ok(rp.layer[l].hh) && g_opt_split_kept.load()) ? 1 : 0;
-            if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), 2, oks)) {
+            const int oks = (dense_hh_dw_ok(rp.layer[l].hh) && t_opt.split_kept) ? 1 : 0;
+            if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, 2, oks)) {
                 mode2[l] = 1;
                 extra2 += r4(B * T * 4 * H);
             }
         }
-        const bool use1 = extra1 > 0 && extra1 * 4 <= g_opt_save_bytes.load();
-        const bool use2 = !use1 && extra2 > 0 && extra2 * 4 <= g_opt_save_u_bytes.load();
+        const bool use1 = extra1 > 0 && extra1 * 4 <= t_opt.save_bytes;
+        const bool use2 = !use1 && extra2 > 0 && extra2 * 4 <= t_opt.save_u_bytes;
         for (int l = 0; l < L; ++l) {
             lo->save_mode[l] = (use1 && mode1[l]) ? 1 : ((use2 && mode2[l]) ? 2 : 0);
             if (lo->save_mode[l] == 1) { lo->sv_x0[l] = lo->sv_total; lo->sv_total += r4(B * T * lo->x0f[l]); }
@@ -413,12 +451,12 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->b_aux = o; o += 2 * r4(GH) + 4;                   // rank-one input mode: W_ih column, its gradient, a 1.0f
     lo->b_dense = o; o += dbw;
     long long dhh = 0;                                    // split backward: dense accumulation of the hh core gradients
-    if (g_opt_static.load())
+    if (t_opt.stat)
         for (int l = 0; l < L; ++l) {
             const bool okd = dense_hh_dw_ok(rp.layer[l].hh);
-            const int oks = (okd && g_opt_split_kept.load()) ? 1 : 0;
-            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)g_opt_srows_bwd.load(), 0);
-            const TtsRnnBwdEntry *b2 = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)g_opt_srows_bwd.load(), 2, oks);
+            const int oks = (okd && t_opt.split_kept) ? 1 : 0;
+            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)t_opt.srows_bwd, 0);
+            const TtsRnnBwdEntry *b2 = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)t_opt.srows_bwd, 2, oks);
             if (okd && ((be && be->split) || (b2 && b2->split)) && dense_bwd_floats(rp.layer[l].hh) > dhh)
                 dhh = dense_bwd_floats(rp.layer[l].hh);
         }
@@ -431,7 +469,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
 int launch_ttlinear_fwd(const ChainPlan &p, const DevInfo &dv, long long rows, int rows_per_b, const float *x,
                         long long x_bstride, const float *cores, const float *bias, const float *bias2, float *y,
                         long long y_bstride, cudaStream_t st, const ttrnn_tt_shape *shape = nullptr) {
-    if (shape && g_opt_static.load()) {
+    if (shape && t_opt.stat) {
         if (const TtsTtlFwdEntry *e = tts_find_ttl_fwd(shape, rows)) {
             int occ = 0;
             int rc = e->prepare(&occ);
@@ -479,7 +517,7 @@ int launch_ttlinear_bwd(const ChainPlan &p0, const DevInfo &dv, long long rows, 
                         long long x_bstride, const float *cores, const float *dy, long long dy_bstride, float *dx,
                         long long dx_bstride, float *partial, int nslots, float *spill, int want_dbias,
                         cudaStream_t st, int *slots_used, const ttrnn_tt_shape *shape = nullptr) {
-    if (shape && g_opt_static.load()) {
+    if (shape && t_opt.stat) {
         if (const TtsTtlBwdEntry *e = tts_find_ttl_bwd(shape, rows, dx != nullptr)) {
             int occ = 0;
             int rc = e->prepare(&occ);
@@ -549,43 +587,78 @@ void dense_carve(float *base, const ChainPlan &ih, bool bwd, DenseIh *D) {
     const long long wn = r4((long long)ih.n_in * ih.n_out);
     D->eye = base; base += r4((long long)ih.n_in * ih.n_in);
     D->wt = base; base += wn;
-    D->w = D->dwt = D->dbias = D->part = D->pbias = nullptr;
-    if (!bwd) return;
     D->w = base; base += wn;
+    D->w_hi = base; base += wn;
+    D->w_lo = base; base += wn;
+    D->wt_hi = D->wt_lo = D->dwt = D->dbias = D->part = D->pbias = nullptr;
+    if (!bwd) return;
+    D->wt_hi = base; base += wn;
+    D->wt_lo = base; base += wn;
     D->dwt = base; base += wn;
     D->dbias = base; base += r4(ih.n_out);
     D->part = base; base += kDenseMaxSplit * wn;
     D->pbias = base;
 }
 
-// W^T (I x G*H): the TT matvec applied to the rows of the identity; optionally W (G*H x I) as well
+// tensor-core route limits: the main TMEM accumulator of k_tc_rows chains K / 8 truncating adds (tt_tc.cuh)
+constexpr int kTcMaxKFwd = 512, kTcMaxKGrad = 2048;
+bool tc_rows_use(long long rows, int K, int N, bool grad) {
+    return t_opt.tc_gemm && ttc::tc_rows_ok(rows, K, N) && K <= (grad ? kTcMaxKGrad : kTcMaxKFwd);
+}
+
+int split_tf32(const float *src, float *hi, float *lo, long long n, cudaStream_t st) {
+    long long blocks = (n / 4 + 255) / 256;
+    if (blocks > 1184) blocks = 1184;
+    ttc::k_split_tf32<<<(unsigned)blocks, 256, 0, st>>>(src, hi, lo, n / 4);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// W^T (I x G*H): the TT matvec applied to the rows of the identity; optionally W (G*H x I) as well, and the TF32 hi / lo
+// splits the tensor-core GEMMs take as their weight operand (W for the forward projection, W^T for dX)
 int dense_prepare(const ChainPlan &ih, const ttrnn_tt_shape *shape, const DevInfo &dv, const float *cores, DenseIh &D,
-                  bool need_w, cudaStream_t st) {
+                  bool need_w, bool split_w, bool split_wt, cudaStream_t st) {
     const int I = ih.n_in, GH = ih.n_out;
     ttg::k_eye<<<(I * I + 255) / 256 > 1024 ? 1024 : (I * I + 255) / 256, 256, 0, st>>>(D.eye, I);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
     if (launch_ttlinear_fwd(ih, dv, I, I, D.eye, 0, cores, nullptr, nullptr, D.wt, 0, st, shape)) return 1;
-    if (need_w) {
+    if (need_w || split_w) {
         dim3 grid((GH + 31) / 32, (I + 31) / 32);
         ttg::k_transpose<<<grid, 256, 0, st>>>(D.wt, D.w, I, GH);
         ++g_launches;
         CU_CHECK(cudaGetLastError());
     }
+    const long long wn = r4((long long)I * GH);
+    if (split_w && split_tf32(D.w, D.w_hi, D.w_lo, wn, st)) return 1;
+    if (split_wt && split_tf32(D.wt, D.wt_hi, D.wt_lo, wn, st)) return 1;
     return 0;
 }
 
 // C[r, :] = A[r, :] * B (+ bias + bias2) over ragged rows (time-chunk views)
-int dense_rows_gemm(int kind, long long rows, int rpb, const float *a, long long a_bstride, int K, const float *b, int N,
-                    const float *bias, const float *bias2, float *c, long long c_bstride, cudaStream_t st) {
+int dense_rows_gemm(int kind, const DevInfo &dv, long long rows, int rpb, const float *a, long long a_bstride, int K,
+                    const float *b, const float *bt_hi, const float *bt_lo, int N, const float *bias, const float *bias2,
+                    float *c, long long c_bstride, bool grad, cudaStream_t st) {
     if (rows < 1 || rows > 0x7fffffffLL) return fail("dense ih projection: row count out of range");
+    if (bt_hi && bt_lo && tc_rows_use(rows, K, N, grad)) {
+        // tensor cores: tcgen05 3xTF32, Bt (N x K) pre-split into hi / lo
+        int rc;
+        {
+            KernelTimer tm(kind, st);
+            rc = ttc::launch_tc_rows(rows, rpb, a, a_bstride, K, bt_hi, bt_lo, N, bias, bias2, c, c_bstride, dv.sms, st);
+        }
+        if (rc == 0) { ++g_launches; ++g_tc_launches; return 0; }
+        if (rc > 0) return fail("k_tc_rows launch failed (code %d)", rc);
+        // rc < 0: the views cannot be described by a tensor map (alignment): FP32 FFMA kernel below
+    }
     ttg::GemmRowsArgs g;
     memset(&g, 0, sizeof g);
     g.rows = (unsigned)rows; g.K = K; g.N = N;
     g.a.p = a; g.a.bstride = a_bstride; g.a.rpb = rpb; g.a.ld = K;
     g.b = b; g.ldb = N; g.bias = bias; g.bias2 = bias2;
     g.c.p = c; g.c.bstride = c_bstride; g.c.rpb = rpb; g.c.ld = N;
-    const bool wide = g_opt_gemm_wide.load() && N % 256 == 0;       // 128 x 256 CTA tile, 8 x 16 thread tile
+    const bool wide = t_opt.gemm_wide && N % 256 == 0;       // 128 x 256 CTA tile, 8 x 16 thread tile
     const long long tiles = ((rows + 127) / 128) * (N / (wide ? 256 : ttg::BN));
     if (tiles > 0x7fffffffLL) return fail("dense ih projection: too many tiles");
     {
@@ -602,6 +675,29 @@ int dense_rows_gemm(int kind, long long rows, int rpb, const float *a, long long
 int dense_dw(const DevInfo &dv, long long rows, int rpb, const float *x, long long x_bstride, int I, const float *delta,
              long long d_bstride, int GH, DenseIh &D, bool accumulate, bool want_bias, cudaStream_t st) {
     if (rows < 1 || rows > 0x7fffffffLL) return fail("dense ih backward: row count out of range");
+    if (t_opt.tc_gemm && ttc::tc_red_ok(rows, I, GH)) {
+        // tensor cores: tcgen05 3xTF32 with the TMEM accumulator promoted into FP32 registers every 32 k-blocks
+        int ns = 0, rc;
+        {
+            KernelTimer tm(TTRNN_K_TTLINEAR_BWD, st);
+            rc = ttc::launch_tc_red(rows, rpb, x, x_bstride, I, delta, d_bstride, GH, D.part, want_bias ? D.pbias : nullptr,
+                                    dv.sms, kDenseMaxSplit, &ns, st);
+        }
+        if (rc > 0) return fail("k_tc_red launch failed (code %d)", rc);
+        if (rc == 0) {
+            ++g_launches;
+            ++g_tc_launches;
+            const long long wn = (long long)I * GH;
+            ttg::k_sum_splits<<<(unsigned)((wn / 4 + 255) / 256), 256, 0, st>>>(D.part, ns, wn, wn, D.dwt, accumulate ? 1 : 0);
+            ++g_launches;
+            if (want_bias) {
+                ttg::k_sum_splits<<<(unsigned)((GH / 4 + 255) / 256), 256, 0, st>>>(D.pbias, ns, GH, GH, D.dbias, accumulate ? 1 : 0);
+                ++g_launches;
+            }
+            CU_CHECK(cudaGetLastError());
+            return 0;
+        }
+    }
     const int TMsel = (I <= 64) ? 4 : 8;
     const int BM = 16 * TMsel;
     const int tiles = ((I + BM - 1) / BM) * (GH / ttg::BN);
@@ -691,6 +787,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "dense_hh_dw")) { g_opt_dense_hh.store(value); return 0; }
     if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
+    if (!strcmp(key, "tc_gemm")) { g_opt_tc_gemm.store(value); return 0; }
     return 1;
 }
 
@@ -700,6 +797,7 @@ int ttrnn_static_kernel_table(char *buf, int32_t cap) {
 }
 
 int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row, int64_t *dense_macs_per_row) {
+    t_opt = snapshot_options();
     RnnPlan rp;
     if (build_rnn_plan(desc, &rp)) return -1;
     if (layer < 0 || layer >= desc->num_layers) { fail("layer %d out of range", layer); return -1; }
@@ -710,6 +808,79 @@ int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain
     return dense_ih_ok(ih, &desc->ih[layer]) ? 1 : 0;
 }
 
+int64_t ttrnn_tc_launch_count(int32_t reset) {
+    long long v = g_tc_launches.load();
+    if (reset) g_tc_launches.store(0);
+    return v;
+}
+
+int ttrnn_rnn_describe(const ttrnn_rnn_desc *d, int32_t training, char *buf, int32_t cap) {
+    if (!buf || cap < 1) return -1;
+    t_opt = snapshot_options();
+    RnnPlan rp;
+    if (build_rnn_plan(d, &rp)) return -1;
+    DevInfo dv;
+    if (get_dev(&dv)) return -1;
+    RnnLayout lo;
+    if (build_layout(d, rp, dv, &lo)) return -1;
+    const long long B = d->batch;
+    const int GH = rp.G * d->hidden_size;
+    int n = 0;
+    auto put = [&](const char *fmt, ...) {
+        if (n >= cap) return;
+        va_list ap;
+        va_start(ap, fmt);
+        n += vsnprintf(buf + n, cap - n, fmt, ap);
+        va_end(ap);
+    };
+    // kernel names as single tokens
+    auto tok = [](const char *name) {
+        std::string t(name ? name : "none");
+        for (auto &c : t)
+            if (c == ' ') c = '_';
+        return t;
+    };
+    put("chunk_steps=%d sms=%d tc_gemm=%lld\n", lo.Tc, dv.sms, t_opt.tc_gemm);
+    for (int l = 0; l < d->num_layers; ++l) {
+        const LayerPlan &lp = rp.layer[l];
+        const bool rank1 = (l == 0 && d->input_size == 1);
+        const int mode = rank1 ? tts::MODE_RANK1 : tts::MODE_XG;
+        const bool dense = !rank1 && dense_ih_ok(lp.ih, &d->ih[l]);
+        const char *route = rank1 ? "rank_one" : (dense ? "dense" : "tt_chain");
+        const bool tc_f = dense && tc_rows_use(B * (long long)lo.Tc, lp.ih.n_in, GH, false);
+        const bool tc_r = dense && t_opt.tc_gemm && ttc::tc_red_ok(B * (long long)lo.Tc, lp.ih.n_in, GH);
+        const TtsRnnFwdEntry *se = t_opt.stat ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_fwd) : nullptr;
+        put("layer=%d ih_route=%s ih_fwd_tc=%d ih_dw_tc=%d fwd_kernel=%s fwd_rows=%d save_mode=%d", l, route, (int)tc_f, (int)tc_r,
+            se ? tok(se->name).c_str() : "runtime", se ? se->R : 0, lo.save_mode[l]);
+        if (training) {
+            const TtsRnnBwdEntry *be = t_opt.stat ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd) : nullptr;
+            if (t_opt.stat && lo.save_mode[l] != 0)
+                if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, lo.save_mode[l],
+                                                                dense_hh_dw_ok(lp.hh) && t_opt.split_kept))
+                    be = bs;
+            if (!be) {
+                put(" bwd_kernel=runtime bwd_rows=0");
+            } else {
+                const TtsRnnBwdEntry *pe[2] = {be, nullptr};
+                long long pr0[2] = {0, 0}, pr[2] = {B, 0};
+                int np = 1;
+                if ((!be->split || be->saved == 2) && t_opt.row_plan) {
+                    const int q = tts_plan_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, be->saved,
+                                                   be->split && be->saved == 2, pe, pr0, pr);
+                    if (q >= 1) np = q; else { pe[0] = be; pr[0] = B; }
+                }
+                put(" bwd_kernel=%s bwd_rows=%d bwd_phase_rows=%lld", tok(pe[0]->name).c_str(), pe[0]->R, pr[0]);
+                if (np == 2) put(" bwd_kernel2=%s bwd_rows2=%d bwd_phase_rows2=%lld", tok(pe[1]->name).c_str(), pe[1]->R, pr[1]);
+                const bool hh_dense = be->split && dense_hh_dw_ok(lp.hh);
+                put(" hh_dw=%s hh_dw_tc=%d", be->split ? (hh_dense ? "dense" : "tt_chain") : "fused",
+                    (int)(hh_dense && t_opt.tc_gemm && ttc::tc_red_ok(B * (long long)lo.Tc, d->hidden_size, GH)));
+            }
+        }
+        put("\n");
+    }
+    return n;
+}
+
 int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc) {
     RnnPlan rp;
     if (build_rnn_plan(desc, &rp)) return -1;
@@ -718,6 +889,7 @@ int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc) {
 
 int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
     if (!ws) return fail("null workspace struct");
+    t_opt = snapshot_options();
     RnnPlan rp;
     if (build_rnn_plan(desc, &rp)) return 1;
     DevInfo dv;
@@ -727,12 +899,16 @@ int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *w
     ws->saved_bytes = lo.sv_total * 4;
     ws->fwd_scratch_bytes = lo.f_total * 4;
     ws->bwd_scratch_bytes = lo.b_total * 4;
+    memset(ws->plan, 0, sizeof ws->plan);
+    plan_store(t_opt, ws->plan);
     return 0;
 }
 
-int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, const float *c0,
-                      const float *params, float *out, float *hT, float *cT, void *saved, void *scratch,
+int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                      const float *c0, const float *params, float *out, float *hT, float *cT, void *saved, void *scratch,
                       void *stream) {
+    if (!ws || !plan_load(ws->plan, &t_opt))
+        return fail("ttrnn_rnn_forward: `ws` must be the struct filled by ttrnn_rnn_workspace_bytes() for this descriptor");
     RnnPlan rp;
     if (build_rnn_plan(d, &rp)) return 1;
     if (!x || !params || !out || !scratch) return fail("x, params, out and scratch must be non-null");
@@ -740,6 +916,9 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
     if (get_dev(&dv)) return 1;
     RnnLayout lo;
     if (build_layout(d, rp, dv, &lo)) return 1;
+    if (lo.f_total * 4 != ws->fwd_scratch_bytes || lo.sv_total * 4 != ws->saved_bytes)
+        return fail("ttrnn_rnn_forward: workspace struct does not belong to this descriptor (scratch %lld vs %lld bytes)",
+                    (long long)lo.f_total * 4, (long long)ws->fwd_scratch_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const long long B = d->batch;
     const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = rp.G;
@@ -769,12 +948,14 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
         DenseIh D;
         if (dense) {
             dense_carve(sc + lo.f_dense, lp.ih, false, &D);
-            if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, false, st)) return 1;
+            if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, false,
+                              tc_rows_use(B * (long long)lo.Tc, nin, GH, false), false, st))
+                return 1;
         }
         auto project = [&](int t0, int tc) -> int {
             if (dense)
-                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
-                                       D.wt, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st);
+                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
+                                       D.wt, D.w_hi, D.w_lo, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, false, st);
             return launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                        params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
                                        &d->ih[l]);
@@ -782,7 +963,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
 
         // ---- statically specialised kernel for this hh shape, if one is registered -------------------
         const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
-        const TtsRnnFwdEntry *se = g_opt_static.load() ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_fwd.load()) : nullptr;
+        const TtsRnnFwdEntry *se = t_opt.stat ? tts_find_rnn_fwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_fwd) : nullptr;
         if (se) {
             int occ = 0;
             int rc = se->prepare(&occ);
@@ -883,10 +1064,12 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const float *x, const float *h0, 
     return 0;
 }
 
-int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0, const float *c0,
-                       const float *params, const float *out, const void *saved, const float *d_out,
+int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                       const float *c0, const float *params, const float *out, const void *saved, const float *d_out,
                        const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
                        void *scratch, void *stream) {
+    if (!ws || !plan_load(ws->plan, &t_opt))
+        return fail("ttrnn_rnn_backward: `ws` must be the struct the matching forward ran with");
     RnnPlan rp;
     if (build_rnn_plan(d, &rp)) return 1;
     if (!x || !params || !out || !scratch || !d_params) return fail("x, params, out, scratch, d_params must be non-null");
@@ -894,6 +1077,9 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
     if (get_dev(&dv)) return 1;
     RnnLayout lo;
     if (build_layout(d, rp, dv, &lo)) return 1;
+    if (lo.b_total * 4 != ws->bwd_scratch_bytes || lo.sv_total * 4 != ws->saved_bytes)
+        return fail("ttrnn_rnn_backward: workspace struct does not belong to this descriptor (scratch %lld vs %lld bytes)",
+                    (long long)lo.b_total * 4, (long long)ws->bwd_scratch_bytes);
     cudaStream_t st = (cudaStream_t)stream;
     const long long B = d->batch;
     const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = rp.G;
@@ -924,13 +1110,16 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
         DenseIh D;
         if (dense) {
             dense_carve(sc + lo.b_dense, lp.ih, true, &D);
-            if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, dlin != nullptr, st)) return 1;
+            if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, dlin != nullptr,
+                              tc_rows_use(B * (long long)lo.Tc, nin, GH, false),
+                              dlin != nullptr && tc_rows_use(B * (long long)lo.Tc, GH, nin, true), st))
+                return 1;
         }
         bool dense_first = true;
         auto project = [&](int t0, int tc) -> int {
             if (dense)
-                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
-                                       D.wt, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st);
+                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
+                                       D.wt, D.w_hi, D.w_lo, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, false, st);
             return launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                        params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
                                        &d->ih[l]);
@@ -943,8 +1132,8 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
                     return 1;
                 dense_first = false;
                 if (dlin)
-                    return dense_rows_gemm(TTRNN_K_TTLINEAR_BWD, B * tc, tc, xg, (long long)tc * GH, GH, D.w, nin, nullptr,
-                                           nullptr, dlin + (long long)t0 * nin, (long long)T * nin, st);
+                    return dense_rows_gemm(TTRNN_K_TTLINEAR_BWD, dv, B * tc, tc, xg, (long long)tc * GH, GH, D.w, D.wt_hi, D.wt_lo,
+                                           nin, nullptr, nullptr, dlin + (long long)t0 * nin, (long long)T * nin, true, st);
                 return 0;
             }
             return launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
@@ -962,23 +1151,26 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const float *x, const float *h0,
         };
 
         // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
-        const TtsRnnBwdEntry *be = g_opt_static.load() ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load()) : nullptr;
-        if (g_opt_static.load() && lo.save_mode[l] != 0 && sv) {
+        const TtsRnnBwdEntry *be = t_opt.stat ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd) : nullptr;
+        if (t_opt.stat && lo.save_mode[l] != 0 && sv) {
             // forward kept (X_0 and) the hh pre-activations of this layer: use the kernel that consumes them
-            if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(),
-                                                            lo.save_mode[l], dense_hh_dw_ok(lp.hh) && g_opt_split_kept.load()))
+            if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd,
+                                                            lo.save_mode[l], dense_hh_dw_ok(lp.hh) && t_opt.split_kept))
                 be = bs;
         }
+        if (be && be->split && !lstm)
+            return fail("internal: split BPTT variants compute the hh bias gradient from the ih side (LSTM only); %s is "
+                        "registered for a GRU", be->name);
         if (be) {
             // row plan: one phase, or two when a tail variant beats a mostly idle last wave
             const TtsRnnBwdEntry *ph_e[2] = {be, nullptr};
             long long ph_row0[2] = {0, 0}, ph_rows[2] = {B, 0};
             int ph_grid[2] = {0, 0};
             int nph = 1;
-            if ((!be->split || be->saved == 2) && g_opt_row_plan.load()) {
+            if ((!be->split || be->saved == 2) && t_opt.row_plan) {
                 const TtsRnnBwdEntry *pe[2];
                 long long pr0[2], pr[2];
-                const int np = tts_plan_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)g_opt_srows_bwd.load(), be->saved,
+                const int np = tts_plan_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, be->saved,
                                                 be->split && be->saved == 2, pe, pr0, pr);
                 if (np >= 1) {
                     nph = np;
@@ -1233,6 +1425,7 @@ int64_t ttrnn_ttlinear_param_count(const ttrnn_tt_shape *shape) {
 }
 
 int64_t ttrnn_ttlinear_workspace_bytes(const ttrnn_tt_shape *shape, int64_t rows) {
+    t_opt = snapshot_options();
     ChainPlan p;
     if (!shape || tt_build_plan(shape, &p)) { fail("malformed TT shape"); return -1; }
     DevInfo dv;
@@ -1246,6 +1439,7 @@ int64_t ttrnn_ttlinear_workspace_bytes(const ttrnn_tt_shape *shape, int64_t rows
 int ttrnn_ttlinear_forward(const ttrnn_tt_shape *shape, int64_t rows, const float *x, const float *cores,
                            const float *bias, float *y, void *scratch, void *stream) {
     (void)scratch;
+    t_opt = snapshot_options();
     ChainPlan p;
     if (!shape || tt_build_plan(shape, &p)) return fail("malformed TT shape");
     if (rows < 1) return fail("rows must be >= 1");
@@ -1258,6 +1452,7 @@ int ttrnn_ttlinear_forward(const ttrnn_tt_shape *shape, int64_t rows, const floa
 
 int ttrnn_ttlinear_backward(const ttrnn_tt_shape *shape, int64_t rows, const float *x, const float *cores,
                             const float *dy, float *d_x, float *d_cores, float *d_bias, void *scratch, void *stream) {
+    t_opt = snapshot_options();
     ChainPlan p;
     if (!shape || tt_build_plan(shape, &p)) return fail("malformed TT shape");
     if (rows < 1 || rows > 0x7fffffffLL) return fail("rows out of range");

@@ -67,9 +67,21 @@ def _bytes_to_floats(nbytes: int) -> int:
     return max(1, (int(nbytes) + 3) // 4)
 
 
+def _dense16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Contiguous and 16-byte aligned: the kernels read these buffers with float4 loads, 16-byte cp.async and TMA.
+    `.contiguous()` keeps a contiguous view whose storage offset is not a multiple of 4 floats (a slice of a flat
+    buffer); such a view is copied."""
+    if t is None:
+        return None
+    t = t.contiguous()
+    if t.data_ptr() % 16 != 0:
+        t = t.clone()
+    return t
+
+
 class _RnnFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, spec: RnnSpec, x, h0, c0, *params):
+    def forward(ctx, spec: RnnSpec, grad_enabled: bool, x, h0, c0, *params):
         lib = _lib.load()
         _require_cuda_f32("input", x)
         for i, p in enumerate(params):
@@ -85,9 +97,9 @@ class _RnnFunction(torch.autograd.Function):
                 _require_cuda_f32(name, s)
                 if tuple(s.shape) != (B, H):
                     raise ValueError("%s must have shape (%d, %d), got %s" % (name, B, H, tuple(s.shape)))
-        x = x.contiguous()
-        h0c = None if h0 is None else h0.contiguous()
-        c0c = None if c0 is None else c0.contiguous()
+        x = _dense16(x)
+        h0c = _dense16(h0)
+        c0c = _dense16(c0)
         desc = spec.desc(B, T)
         with torch.cuda.device(x.device):
             blob = torch.cat([p.detach().reshape(-1) for p in params])
@@ -98,7 +110,9 @@ class _RnnFunction(torch.autograd.Function):
                 raise RuntimeError("parameter blob has %d floats, descriptor expects %d" % (blob.numel(), want))
             ws = _lib.RnnWorkspace()
             _lib.check(lib.ttrnn_rnn_workspace_bytes(C.byref(desc), C.byref(ws)), "ttrnn_rnn_workspace_bytes")
-            training = any(ctx.needs_input_grad[1:])
+            # grad mode is always off inside Function.forward and needs_input_grad stays True for nn.Parameters under
+            # torch.no_grad(): the caller captures torch.is_grad_enabled() before .apply
+            training = bool(grad_enabled) and any(ctx.needs_input_grad[2:])
             out = torch.empty((B, T, H), device=x.device, dtype=torch.float32)
             hT = torch.empty((B, H), device=x.device, dtype=torch.float32)
             cT = torch.empty((B, H), device=x.device, dtype=torch.float32) if spec.cell == "lstm" else None
@@ -106,12 +120,13 @@ class _RnnFunction(torch.autograd.Function):
                 if training else None
             scratch = torch.empty(_bytes_to_floats(ws.fwd_scratch_bytes), device=x.device, dtype=torch.float32)
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(lib.ttrnn_rnn_forward(C.byref(desc), _ptr(x), _ptr(h0c), _ptr(c0c), _ptr(blob), _ptr(out),
+            _lib.check(lib.ttrnn_rnn_forward(C.byref(desc), C.byref(ws), _ptr(x), _ptr(h0c), _ptr(c0c), _ptr(blob), _ptr(out),
                                              _ptr(hT), _ptr(cT), _ptr(saved), _ptr(scratch), stream),
                        "ttrnn_rnn_forward")
         if training:
             ctx.spec = spec
             ctx.shapes = [tuple(p.shape) for p in params]
+            ctx.ws = ws                    # sizes + execution plan: backward runs from the same plan as this forward
             ctx.bwd_floats = _bytes_to_floats(ws.bwd_scratch_bytes)
             ctx.has_h0, ctx.has_c0 = h0 is not None, c0 is not None
             ctx.set_materialize_grads(False)
@@ -131,21 +146,19 @@ class _RnnFunction(torch.autograd.Function):
         B, T, _ = x.shape
         H = spec.hidden_size
         desc = spec.desc(B, T)
-        d_out = None if d_out is None else d_out.contiguous()
-        if d_out is not None and d_out.data_ptr() % 16 != 0:
-            d_out = d_out.clone()          # the BPTT kernels stage dOut tiles with 16-byte cp.async
-        d_hT = None if d_hT is None else d_hT.contiguous()
-        d_cT = None if d_cT is None else d_cT.contiguous()
+        d_out = _dense16(d_out)            # the BPTT kernels stage dOut tiles with 16-byte cp.async
+        d_hT = _dense16(d_hT)
+        d_cT = _dense16(d_cT)
         with torch.cuda.device(x.device):
             d_blob = torch.empty_like(blob)
-            d_x = torch.empty_like(x) if ctx.needs_input_grad[1] else None
+            d_x = torch.empty_like(x) if ctx.needs_input_grad[2] else None
             d_h0 = torch.empty((B, H), device=x.device, dtype=torch.float32) \
-                if (ctx.has_h0 and ctx.needs_input_grad[2]) else None
+                if (ctx.has_h0 and ctx.needs_input_grad[3]) else None
             d_c0 = torch.empty((B, H), device=x.device, dtype=torch.float32) \
-                if (spec.cell == "lstm" and ctx.has_c0 and ctx.needs_input_grad[3]) else None
+                if (spec.cell == "lstm" and ctx.has_c0 and ctx.needs_input_grad[4]) else None
             scratch = torch.empty(ctx.bwd_floats, device=x.device, dtype=torch.float32)
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(lib.ttrnn_rnn_backward(C.byref(desc), _ptr(x), _ptr(h0), _ptr(c0), _ptr(blob), _ptr(out),
+            _lib.check(lib.ttrnn_rnn_backward(C.byref(desc), C.byref(ctx.ws), _ptr(x), _ptr(h0), _ptr(c0), _ptr(blob), _ptr(out),
                                               _ptr(saved), _ptr(d_out), _ptr(d_hT), _ptr(d_cT), _ptr(d_blob),
                                               _ptr(d_x), _ptr(d_h0), _ptr(d_c0), _ptr(scratch), stream),
                        "ttrnn_rnn_backward")
@@ -155,9 +168,9 @@ class _RnnFunction(torch.autograd.Function):
             n = 1
             for v in shp:
                 n *= v
-            d_params.append(d_blob[off:off + n].view(shp) if ctx.needs_input_grad[4 + i] else None)
+            d_params.append(d_blob[off:off + n].view(shp) if ctx.needs_input_grad[5 + i] else None)
             off += n
-        return (None, d_x, d_h0, d_c0) + tuple(d_params)
+        return (None, None, d_x, d_h0, d_c0) + tuple(d_params)
 
 
 def rnn_sequence(spec: RnnSpec, x: torch.Tensor, h0: Optional[torch.Tensor], c0: Optional[torch.Tensor],
@@ -165,7 +178,7 @@ def rnn_sequence(spec: RnnSpec, x: torch.Tensor, h0: Optional[torch.Tensor], c0:
     """Run the whole stack over the whole sequence.  Returns (out, hT[, cT])."""
     if x.dim() != 3:
         raise ValueError("input must be (batch, seq_len, input_size), got shape %s" % (tuple(x.shape),))
-    return _RnnFunction.apply(spec, x, h0, c0, *params)
+    return _RnnFunction.apply(spec, torch.is_grad_enabled(), x, h0, c0, *params)
 
 
 class _TTLinearFunction(torch.autograd.Function):
@@ -179,7 +192,7 @@ class _TTLinearFunction(torch.autograd.Function):
             _require_cuda_f32("bias", bias)
         if x.dim() != 2 or x.shape[1] != n_in:
             raise ValueError("input must be (rows, %d), got %s" % (n_in, tuple(x.shape)))
-        x = x.contiguous()
+        x = _dense16(x)
         rows = x.shape[0]
         with torch.cuda.device(x.device):
             blob = torch.cat([p.detach().reshape(-1) for p in cores])
@@ -198,7 +211,7 @@ class _TTLinearFunction(torch.autograd.Function):
         lib = _lib.load()
         x, blob = ctx.saved_tensors
         rows = x.shape[0]
-        dy = dy.contiguous()
+        dy = _dense16(dy)
         with torch.cuda.device(x.device):
             nbytes = lib.ttrnn_ttlinear_workspace_bytes(C.byref(ctx.shape), rows)
             if nbytes < 0:

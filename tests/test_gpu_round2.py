@@ -1,0 +1,308 @@
+"""GPU tests added in round 2.
+
+* the tensor-core (tcgen05 3xTF32) dense-route GEMMs against the oracle, through the module API, at row counts
+  large enough to select them (B*T >= 256), with ragged time chunks;
+* the execution plan travels with the call: options changed between a forward and its backward do not change
+  how `saved` is read;
+* inference under torch.no_grad() takes the `saved == NULL` branch and matches the training forward;
+* full-size parity: rows taken out of a full-batch GPU run against the oracle on the same rows,
+  the rows-per-CTA variants the benchmark selects forced onto an oracle-sized batch, cfg3 at its full size, cfg5's
+  shape with >= 3 time chunks.
+
+Tolerances: 1e-5 forward, 1e-4 gradients, norm-wise relative (north_star).
+"""
+import io
+import os
+from contextlib import contextmanager, redirect_stdout
+
+import pytest
+import torch
+
+import tensorized_rnn_b200 as tr
+from tensorized_rnn_b200 import _lib
+from helpers import FWD_TOL, GRAD_TOL, oracle, quiet, rel_err
+from test_gpu_static_paths import _sd_from_layers
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@contextmanager
+def options(**kw):
+    """Set library options for the duration of a block; restore the defaults afterwards."""
+    defaults = {"chunk_steps": 0, "save_u_bytes": 16 << 30, "tc_gemm": 1, "static_rows_fwd": 0, "static_rows_bwd": 0,
+                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1}
+    lib = _lib.load()
+    for k, v in kw.items():
+        assert lib.ttrnn_set_option(k.encode(), int(v)) == 0, k
+    try:
+        yield lib
+    finally:
+        for k in kw:
+            lib.ttrnn_set_option(k.encode(), defaults[k])
+
+
+def make_pair(cell, I, H, L, d, r, seed=123, scale=1.5):
+    """Oracle layers and our module (on the GPU) with the same parameters."""
+    layers = oracle.random_layers(cell, I, H, L, d, r, bias=True, seed=seed, requires_grad=True, scale=scale)
+    cls = tr.TTLSTM if cell == "lstm" else tr.TTGRU
+    m = quiet(cls, I, H, L, torch.device("cpu"), n_cores=d, tt_rank=r)
+    m.load_state_dict(_sd_from_layers(layers))
+    return layers, m.to(DEV)
+
+
+def oracle_run(cell, layers, x, w_out=None, w_h=None):
+    for p in oracle.flat_params(layers):
+        p.grad = None
+    if cell == "lstm":
+        out, (h, _) = oracle.lstm_forward(layers, x)
+    else:
+        out, h = oracle.gru_forward(layers, x)
+    loss = (h * w_h).sum() if w_h is not None else h.sum()
+    if w_out is not None:
+        loss = loss + (out * w_out).sum()
+    loss.backward()
+    return out.detach(), h.detach(), [p.grad.clone() for p in oracle.flat_params(layers)]
+
+
+def gpu_run(cell, m, x, w_out=None, w_h=None):
+    for p in m.parameters():
+        p.grad = None
+    res = m(x.to(DEV))
+    out = res[0]
+    h = res[1][0] if cell == "lstm" else res[1]
+    loss = (h * w_h.to(DEV)).sum() if w_h is not None else h.sum()
+    if w_out is not None:
+        loss = loss + (out * w_out.to(DEV)).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+    return out.detach(), h.detach(), [p.grad.clone() for p in m.flat_parameters()]
+
+
+def assert_grads(got, ref, tol=GRAD_TOL):
+    bad = {}
+    for i, (a, b) in enumerate(zip(got, ref)):
+        e = rel_err(a, b)
+        if not e <= tol:
+            bad[(i, tuple(b.shape))] = e
+    assert not bad, "gradient rel err above %.0e: %s" % (tol, bad)
+
+
+# ---- tensor-core dense-route GEMMs ----------------------------------------------------------------------------
+TC_CASES = [
+    # name, cell, I, H, L, d, r, B, T, chunk_steps
+    ("cfg3_shape", "lstm", 40, 256, 3, 3, 8, 40, 24, 0),
+    ("cfg3_shape_chunks_of_10", "lstm", 40, 256, 3, 3, 8, 32, 25, 10),      # ragged views, short TMA boxes, tail chunk of 5
+    ("cfg5_shape", "lstm", 256, 1024, 1, 4, 8, 8, 40, 0),
+    ("cfg5_shape_chunks_of_48", "lstm", 256, 1024, 1, 4, 8, 6, 100, 48),    # rpb = 48 >= 32: partly out-of-bounds k-blocks
+    ("cfg4_shape_training", "lstm", 40, 256, 2, 4, 16, 24, 20, 0),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tensor_core_dense_route_matches_oracle(case):
+    name, cell, I, H, L, d, r, B, T, chunk = case
+    layers, m = make_pair(cell, I, H, L, d, r)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, T, I, generator=g)
+    w_out, w_h = torch.randn(B, T, H, generator=g), torch.randn(B, H, generator=g)
+    o_ref, h_ref, g_ref = oracle_run(cell, layers, x, w_out, w_h)
+    with options(chunk_steps=chunk, tc_gemm=1) as lib:
+        lib.ttrnn_tc_launch_count(1)
+        out, h, grads = gpu_run(cell, m, x, w_out, w_h)
+        n_tc = int(lib.ttrnn_tc_launch_count(0))
+    assert n_tc > 0, "the tcgen05 GEMMs were not selected at this size"
+    assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
+    assert_grads(grads, g_ref)
+    # and the FP32 FFMA route agrees (same call, tensor cores off)
+    with options(chunk_steps=chunk, tc_gemm=0) as lib:
+        lib.ttrnn_tc_launch_count(1)
+        out2, h2, grads2 = gpu_run(cell, m, x, w_out, w_h)
+        assert int(lib.ttrnn_tc_launch_count(0)) == 0
+    assert rel_err(out2, o_ref) <= FWD_TOL
+    assert_grads(grads2, g_ref)
+
+
+# ---- the plan travels with the call --------------------------------------------------------------------------
+@pytest.mark.parametrize("cell,I,H,L,d,r", [("lstm", 40, 256, 2, 3, 8), ("gru", 1, 256, 1, 2, 4)])
+def test_options_changed_between_forward_and_backward(cell, I, H, L, d, r):
+    layers, m = make_pair(cell, I, H, L, d, r)
+    g = torch.Generator().manual_seed(9)
+    B, T = 12, 16
+    x = torch.rand(B, T, I, generator=g)
+    w_out, w_h = torch.randn(B, T, H, generator=g), torch.randn(B, H, generator=g)
+    _, _, g_ref = oracle_run(cell, layers, x, w_out, w_h)
+    lib = _lib.load()
+    for p in m.parameters():
+        p.grad = None
+    with options(chunk_steps=5):
+        res = m(x.to(DEV))                               # forward: 4 chunks, gate activations kept
+    out = res[0]
+    h = res[1][0] if cell == "lstm" else res[1]
+    loss = (h * w_h.to(DEV)).sum() + (out * w_out.to(DEV)).sum()
+    # a different model / thread changes every layout-relevant option before this backward runs
+    with options(chunk_steps=3, save_u_bytes=0, static_kernels=0, dense_ih=0, tc_gemm=0):
+        loss.backward()
+        torch.cuda.synchronize()
+    assert_grads([p.grad for p in m.flat_parameters()], g_ref)
+
+
+def test_foreign_workspace_struct_is_rejected():
+    import ctypes as C
+    lib = _lib.load()
+    _, m = make_pair("lstm", 40, 64, 1, 3, 4)
+    desc = m.spec().desc(4, 6)
+    ws = _lib.RnnWorkspace()                             # never filled by ttrnn_rnn_workspace_bytes
+    x = torch.rand(4, 6, 40, device=DEV)
+    out = torch.empty(4, 6, 64, device=DEV)
+    blob = torch.cat([p.detach().reshape(-1) for p in m.flat_parameters()])
+    scratch = torch.empty(1 << 20, device=DEV)
+    rc = lib.ttrnn_rnn_forward(C.byref(desc), C.byref(ws), x.data_ptr(), None, None, blob.data_ptr(), out.data_ptr(),
+                               None, None, None, scratch.data_ptr(), None)
+    assert rc != 0 and "ttrnn_rnn_workspace_bytes" in _lib.last_error()
+
+
+# ---- inference branch ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cell,I,H,L,d,r,B,T", [("lstm", 40, 256, 3, 3, 8, 24, 20), ("gru", 1, 256, 1, 2, 4, 16, 30),
+                                                ("lstm", 40, 64, 2, 3, 4, 5, 7)])
+def test_no_grad_takes_the_inference_branch(cell, I, H, L, d, r, B, T):
+    _, m = make_pair(cell, I, H, L, d, r)
+    x = torch.rand(B, T, I, generator=torch.Generator().manual_seed(3)).to(DEV)
+    res_train = m(x)
+    torch.cuda.synchronize()
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    with torch.no_grad():
+        res_inf = m(x)
+    torch.cuda.synchronize()
+    peak_inf = torch.cuda.max_memory_allocated() - base
+    flat = lambda r: [r[0]] + (list(r[1]) if isinstance(r[1], tuple) else [r[1]])
+    for a, b in zip(flat(res_inf), flat(res_train)):
+        assert not a.requires_grad
+        assert rel_err(a, b) <= 1e-6                    # same arithmetic; the kept-gates stores are the only difference
+    # nothing is kept for backward: the call's peak stays below the training call's `saved` buffer alone
+    import ctypes as C
+    ws = _lib.RnnWorkspace()
+    _lib.check(_lib.load().ttrnn_rnn_workspace_bytes(C.byref(m.spec().desc(B, T)), C.byref(ws)), "workspace")
+    assert ws.saved_bytes > 0
+    if ws.saved_bytes > (4 << 20):
+        nparam = sum(p.numel() for p in m.parameters())
+        assert peak_inf < ws.fwd_scratch_bytes + 4 * (B * T * H + 2 * B * H + nparam) + (2 << 20), \
+            "inference call allocated %d bytes: the %d-byte `saved` buffer must not be among them" % (peak_inf, ws.saved_bytes)
+    # frozen parameters (requires_grad False) with grad mode on: inference branch as well
+    for p in m.parameters():
+        p.requires_grad_(False)
+    res_frozen = m(x)
+    assert not res_frozen[0].requires_grad
+    assert rel_err(res_frozen[0], res_train[0]) <= 1e-6
+
+
+def test_misaligned_views_are_copied():
+    """A contiguous view whose storage offset is not a multiple of 16 bytes must not fault."""
+    _, m = make_pair("lstm", 40, 64, 1, 3, 4)
+    B, T = 6, 9
+    flat = torch.rand(B * T * 40 + 1, device=DEV)
+    x_off = flat[1:].view(B, T, 40)                      # data_ptr % 16 == 4
+    assert x_off.data_ptr() % 16 != 0 and x_off.is_contiguous()
+    hbuf = torch.rand(2 * B * 64 + 1, device=DEV)
+    h0 = hbuf[1:1 + B * 64].view(B, 64)
+    c0 = hbuf[1 + B * 64:].view(B, 64)
+    out, (h, c) = m(x_off, (h0, c0))
+    out2, (h2, c2) = m(x_off.clone(), (h0.clone(), c0.clone()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2) and torch.equal(h, h2) and torch.equal(c, c2)
+
+
+# ---- full-size parity -------------------------------------------------------------------------------------------
+FULL = [
+    # name, cell, I, H, L, d, r, B_full, T, rows checked against the oracle
+    ("cfg1", "lstm", 1, 256, 1, 2, 4, 256, 784, 48),
+    ("cfg2", "gru", 1, 256, 1, 2, 4, 1024, 784, 48),
+]
+
+
+def digits(B, T, seed):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(B, T, 1, generator=g) - 0.1307) / 0.3081
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c[0] for c in FULL])
+def test_full_batch_rows_match_oracle(case):
+    """Outputs / h_T of rows taken out of the FULL benchmark batch (whatever rows-per-CTA variant and row plan the
+    library selects there) against the oracle run on those rows alone, over the full T = 784: batch rows are
+    independent, so the comparison is exact.  Rows are taken from the start, the middle and the ragged end."""
+    name, cell, I, H, L, d, r, B, T, nchk = case
+    layers, m = make_pair(cell, I, H, L, d, r, seed=1111, scale=1.0)
+    x = digits(B, T, 1111)
+    idx = torch.cat([torch.arange(0, nchk // 3), torch.arange(B // 2, B // 2 + nchk // 3),
+                     torch.arange(B - nchk // 3, B)])
+    with torch.no_grad():
+        if cell == "lstm":
+            o_ref, (h_ref, c_ref) = oracle.lstm_forward(layers, x[idx])
+        else:
+            o_ref, h_ref = oracle.gru_forward(layers, x[idx])
+    # training-mode forward (kept gates are written) and inference forward
+    res = m(x.to(DEV))
+    out = res[0].detach()
+    h = (res[1][0] if cell == "lstm" else res[1]).detach()
+    torch.cuda.synchronize()
+    assert rel_err(out[idx.to(DEV)], o_ref) <= FWD_TOL
+    assert rel_err(h[idx.to(DEV)], h_ref) <= FWD_TOL
+    with torch.no_grad():
+        res2 = m(x.to(DEV))
+    assert rel_err(res2[0][idx.to(DEV)], o_ref) <= FWD_TOL
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c[0] for c in FULL])
+def test_bench_row_variants_gradients_match_oracle(case):
+    """Every parameter gradient over the full T = 784 with the rows-per-CTA variants the benchmark selects at the full
+    batch (read from the library's plan) forced onto an oracle-sized batch (static_rows_fwd / static_rows_bwd)."""
+    name, cell, I, H, L, d, r, B_full, T, _ = case
+    Bs = 40
+    layers, m = make_pair(cell, I, H, L, d, r, seed=1111, scale=1.0)
+    plan = _lib.describe_plan(m.spec().desc(B_full, T), training=True)
+    lay = plan[1]
+    assert lay["fwd_kernel"] != "runtime" and lay["bwd_kernel"] != "runtime", plan
+    variants = {(lay["fwd_rows"], lay["bwd_rows"])}
+    if "bwd_rows2" in lay:
+        variants.add((lay["fwd_rows"], lay["bwd_rows2"]))
+    x = digits(Bs, T, 7)
+    w_h = torch.randn(Bs, H, generator=torch.Generator().manual_seed(8))
+    _, h_ref, g_ref = oracle_run(cell, layers, x, None, w_h)
+    for rf, rb in sorted(variants):
+        with options(static_rows_fwd=rf, static_rows_bwd=rb):
+            p2 = _lib.describe_plan(m.spec().desc(Bs, T), training=True)[1]
+            assert p2["fwd_rows"] == rf and p2["bwd_rows"] == rb, p2
+            _, h, grads = gpu_run(cell, m, x, None, w_h)
+        assert rel_err(h, h_ref) <= FWD_TOL
+        assert_grads(grads, g_ref)
+
+
+def test_cfg3_full_size_matches_oracle():
+    """BASELINE config 3 at its full size (3 x TT-LSTM d3 r8, B = 640, T = 160), gradient on h_T as the benchmark does:
+    outputs, h_T and every parameter gradient against the oracle (about 40 s of CPU)."""
+    cell, I, H, L, d, r, B, T = "lstm", 40, 256, 3, 3, 8, 640, 160
+    layers, m = make_pair(cell, I, H, L, d, r, seed=11, scale=1.0)
+    x = torch.rand(B, T, I, generator=torch.Generator().manual_seed(11))
+    torch.set_num_threads(os.cpu_count() or 1)
+    o_ref, h_ref, g_ref = oracle_run(cell, layers, x, None, None)
+    out, h, grads = gpu_run(cell, m, x, None, None)
+    assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
+    assert_grads(grads, g_ref)
+
+
+def test_cfg5_shape_three_chunks_matches_oracle():
+    """BASELINE config 5's shape (H = 1024, d4 r8, I = 256) at B = 8, T = 200 with the time axis cut into >= 3 chunks
+    (split backward, dense hh core gradients across chunk boundaries), dense upstream gradient as the benchmark uses."""
+    cell, I, H, L, d, r, B, T = "lstm", 256, 1024, 1, 4, 8, 8, 200
+    layers, m = make_pair(cell, I, H, L, d, r, seed=11, scale=1.0)
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(B, T, I, generator=g)
+    w_out, w_h = torch.rand(B, T, H, generator=g), torch.randn(B, H, generator=g)
+    o_ref, h_ref, g_ref = oracle_run(cell, layers, x, w_out, w_h)
+    with options(chunk_steps=72):
+        plan = _lib.describe_plan(m.spec().desc(B, T), training=True)
+        assert plan[0]["chunk_steps"] == 72
+        out, h, grads = gpu_run(cell, m, x, w_out, w_h)
+    assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
+    assert_grads(grads, g_ref)
