@@ -1,23 +1,26 @@
 #!/usr/bin/env python
 """Benchmark of the TT-LSTM / TT-GRU recurrence path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 1..5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--configs 1,2,3,4,5] [--headline 3]
 
-Metric (BASELINE.json): cell-steps/sec = batch x T / seconds of one forward(+backward) pass over
-the whole stack.  One "step" = one such pass over one batch of synthetic input of the config's
-shape.  Default workload = BASELINE.json configs[1] (permuted-MNIST TT-GRU, T=784, batch 1024,
-fwd+bwd).  Batch is per GPU (weak scaling): N GPUs process N x batch sequences; with N > 1 the
-TT-core gradients are all-reduced with NCCL inside the step.
+Metric (BASELINE.json): TT-LSTM cell-steps/sec = batch x T / seconds of one forward(+backward) pass over the whole
+stack.  One "step" = one such pass over one batch of synthetic input of the config's shape.
 
-Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events around each
-step, L2 flushed between steps, max over ranks); `e2e` = the same pass through the public module
-API from pinned HOST input with the H2D copy and a D2H read of the result inside the timed region;
-`roofline` = the dominant kernel against the FP32 FFMA peak measured live by an FFMA probe kernel
-(MEASURED_PEAKS.json carries no FP32 figure), in ALGORITHMIC FLOPs of the reference's core-by-core
-sweep (where the engine contracts the ih projection in the cheaper dense order it executes fewer
-FLOPs than credited; `roofline.ih_projection` lists both costs per layer); `cpu_baseline` = the CPU oracle (a restatement of the
-reference's PyTorch path; the reference itself cannot travel to the GPU box) timed on the host
-cores on a bounded sample.  `--impl reference` times that CPU path alone.
+ONE JSON line (rank 0).  Top level = the HEADLINE workload: BASELINE.json configs[2], the GE2E speaker-encoder
+training config (3 x TT-LSTM d3 r8, H 256, 40 mel, 64 speakers x 10 utterances = 640 sequences, T 160, fwd+bwd) --
+the config north_star's scaling target names.  `all_configs` carries one record per BASELINE config (1..5) measured
+in the same invocation: ms_per_step, value, e2e, per-kernel-group times, roofline, and at N = 1 a CPU baseline.
+
+Scaling: `--gpus N` splits each config's GLOBAL batch evenly over the N ranks -> "scaling": "strong";
+the weak-scaling figure (every rank runs the config's full batch) is measured beside it and reported as `weak`.
+Training steps all-reduce the TT-core / bias gradients with NCCL inside the timed region.
+
+`value` = device-resident throughput (CUDA events around each step, L2 flushed between steps, max over ranks);
+`e2e` = the same pass through the public module API from pinned HOST input, with the H2D copy and a D2H read of the
+result inside the timed region; `roofline` = the dominant kernel group against the FP32 FFMA peak measured live by an
+FFMA probe kernel (MEASURED_PEAKS.json has no FP32 figure), in ALGORITHMIC FLOPs of the reference's core-by-core
+sweep; `cpu_baseline` / `--impl reference` = the CPU oracle (a restatement of the reference's PyTorch path; the
+reference itself cannot travel to the GPU box) on the host cores, on a bounded sample whose batch is stated.
 """
 from __future__ import annotations
 
@@ -39,23 +42,27 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# name, cell, I, H, L, d, r, B (per GPU), T, mode, upstream gradient, input kind, seed
+# name, cell, I, H, L, d, r, GLOBAL batch B, T, mode, upstream gradient, input kind, seed
 CONFIGS = {
     1: dict(name="cfg1 sequential-MNIST TT-LSTM d2 r4", cell="lstm", I=1, H=256, L=1, d=2, r=4, B=256, T=784,
             mode="fwd+bwd", grad="out_last", inp="digits", seed=1111),
     2: dict(name="cfg2 permuted-MNIST TT-GRU d2 r4", cell="gru", I=1, H=256, L=1, d=2, r=4, B=1024, T=784,
             mode="fwd+bwd", grad="out_last", inp="digits_perm", seed=1111),
-    3: dict(name="cfg3 GE2E speaker encoder 3xTT-LSTM d3 r8", cell="lstm", I=40, H=256, L=3, d=3, r=8, B=640, T=160,
-            mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
-    4: dict(name="cfg4 speaker encoder inference 3xTT-LSTM d4 r16", cell="lstm", I=40, H=256, L=3, d=4, r=16,
-            B=2048, T=160, mode="fwd", grad=None, inp="uniform", seed=11),
+    3: dict(name="cfg3 GE2E speaker encoder 3xTT-LSTM d3 r8 (64 spk x 10 utt)", cell="lstm", I=40, H=256, L=3, d=3, r=8,
+            B=640, T=160, mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
+    4: dict(name="cfg4 speaker encoder inference 3xTT-LSTM d4 r16 (16k utterances)", cell="lstm", I=40, H=256, L=3, d=4,
+            r=16, B=16384, T=160, mode="fwd", grad=None, inp="uniform", seed=11),
     5: dict(name="cfg5 TT-LSTM H1024 d4 r8 sweep", cell="lstm", I=256, H=1024, L=1, d=4, r=8, B=4096, T=2000,
             mode="fwd+bwd", grad="dense", inp="uniform", seed=11),
+    # secondary point SURVEY.md 8(a) asks for: the reference's own default GE2E model (params_model.py: d2, r2)
+    6: dict(name="cfg3-alt GE2E speaker encoder 3xTT-LSTM d2 r2 (params_model.py defaults)", cell="lstm", I=40, H=256, L=3,
+            d=2, r=2, B=640, T=160, mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
 }
-# bounded CPU sample (batch) per config for the cpu_baseline / reference arm: T stays at the config
-# value (the reference's cost is dominated by per-step dispatch and its O(T^2) backward)
-CPU_SAMPLE_B = {1: 64, 2: 64, 3: 32, 4: 16, 5: 4}
-CPU_SAMPLE_T = {1: 784, 2: 784, 3: 160, 4: 160, 5: 200}
+# per-config caps on (warmup, steps): cfg5 moves ~100 GB per step
+STEP_CAP = {5: (3, 3), 4: (3, 5)}
+# CPU sample (batch, T) per config for the in-line cpu_baseline: about 5-15 s of CPU work each
+CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160)}
+KINDS = ["k_ttlinear_fwd", "k_rnn_fwd", "k_rnn_bwd", "k_ttlinear_bwd", "gemm_ih_fwd", "gemm_dx", "gemm_dw"]
 
 
 # ------------------------------------------------------------------------------------------
@@ -70,17 +77,15 @@ def chain_flops(in_modes, out_modes, ranks):
 
 
 def algorithmic_flops(cfg):
-    """Forward FLOPs per sequence-step for the whole stack, and for the hh chain of one layer."""
+    """Forward FLOPs per sequence-step: whole stack, hh chain of one layer, list of per-layer ih chains."""
     from tensorized_rnn_b200.shapes import tt_shape
     G = 4 if cfg["cell"] == "lstm" else 3
     H, d, r = cfg["H"], cfg["d"], cfg["r"]
     ranks = [1] + [r] * (d - 1) + [1]
-    total = 0
     hh = chain_flops(*tt_shape(H, H, d, G), ranks)
-    for l in range(cfg["L"]):
-        n_in = cfg["I"] if l == 0 else H
-        total += chain_flops(*tt_shape(n_in, H, d, G), ranks) + hh + 2 * G * H + 12 * H
-    return total, hh
+    ih = [chain_flops(*tt_shape(cfg["I"] if l == 0 else H, H, d, G), ranks) for l in range(cfg["L"])]
+    gate = 2 * G * H + 12 * H
+    return sum(ih) + cfg["L"] * (hh + gate), hh, ih, gate
 
 
 def make_input(cfg, B, device="cpu"):
@@ -105,53 +110,88 @@ def upstream(cfg, out, hT):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons sampled in-process through NVML for the whole run; `summary(windows)` keeps
+    the samples that fall inside the timed regions.  Falls back to an nvidia-smi subprocess when pynvml is missing."""
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index):
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.lines = []
+    def __init__(self, gpu_index, period=0.02):
+        self.idx, self.period = gpu_index, period
+        self.samples = []                    # (t, sm_mhz, max_mhz, power_w, reasons bitmask)
+        self.stop_ev = threading.Event()
+        self.thread = None
+        self.source = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "25", "-i", str(self.gpu_index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES: NVML indexes physical devices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = self.idx
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.idx < len(ids) and ids[self.idx].isdigit():
+                    phys = int(ids[self.idx])
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+
+            def loop():
+                while not self.stop_ev.is_set():
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1000.0
+                        try:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        except Exception:
+                            rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        self.samples.append((time.perf_counter(), float(sm), float(mx), pw, int(rs)))
+                    except Exception:
+                        pass
+                    time.sleep(self.period)
+            self.source = "nvml"
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "50",
+                                     "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = proc
+
+            def loop():
+                for ln in proc.stdout:
+                    p = [v.strip() for v in ln.split(",")]
+                    try:
+                        rs = 0
+                        for bit, v in zip((0x8, 0x40, 0x20, 0x4), p[3:7]):
+                            if v.lower().startswith("active"):
+                                rs |= bit
+                        self.samples.append((time.perf_counter(), float(p[0]), float(p[1]), float(p[2]), rs))
+                    except Exception:
+                        continue
+            self.source = "nvidia-smi"
+            self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.source = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 8:
-                continue
-            try:
-                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        self.stop_ev.set()
+        if getattr(self, "proc", None) is not None:
+            self.proc.terminate()
+
+    def summary(self, windows):
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        ins = [s for s in self.samples if any(a <= s[0] <= b for a, b in windows)]
+        reasons = sorted(k for k, bit in self.BAD.items() if any(s[4] & bit for s in ins))
+        return {"sm_mhz": statistics.median(s[1] for s in ins) if ins else None,
+                "sm_max_mhz": max(s[2] for s in ins) if ins else (self.samples[0][2] if self.samples else None),
+                "power_w_max": max(s[3] for s in ins) if ins else None, "samples": len(ins),
+                "samples_total": len(self.samples), "source": self.source, "reasons": reasons}
 
 
 # ------------------------------------------------------------------------------------------
@@ -193,238 +233,339 @@ def run_cpu_oracle(cfg, B, T, steps, warmup):
     return B * T / sec, sec
 
 
+def config_json(cfg, B_rank, world, scaling):
+    return {"workload": cfg["name"], "cell": cfg["cell"], "input_size": cfg["I"], "hidden_size": cfg["H"],
+            "num_layers": cfg["L"], "n_cores": cfg["d"], "tt_rank": cfg["r"], "batch_per_gpu": B_rank,
+            "global_batch": B_rank * world, "seq_len": cfg["T"], "mode": cfg["mode"], "upstream_grad": cfg["grad"],
+            "parallelism": "dp%d (batch-sharded replicas, %s scaling)" % (world, scaling),
+            "l2": "flushed between timed steps (256 MiB write)"}
+
+
+# ------------------------------------------------------------------------------------------
+class GpuBench(object):
+    def __init__(self, rank, world, local_rank):
+        import tensorized_rnn_b200 as tr
+        from tensorized_rnn_b200 import _lib
+        self.tr, self._lib = tr, _lib
+        self.rank, self.world = rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.lib = _lib.load()
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.windows = []                              # host-time windows of the timed regions (clock sampling)
+        self.peak = self.measure_ffma_peak()
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def measure_ffma_peak(self):
+        sink = torch.zeros(4, device=self.dev)
+        flops = C.c_double(0)
+        stream = torch.cuda.current_stream().cuda_stream
+        peak = 0.0
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            self._lib.check(self.lib.ttrnn_ffma_probe(4000, sink.data_ptr(), C.byref(flops), stream), "ttrnn_ffma_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            peak = max(peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return peak
+
+    def run(self, cid, cfg, B_rank, steps, warmup, scaling, with_e2e=True):
+        """One config at per-rank batch B_rank.  Returns the record (rank 0) or None."""
+        from tensorized_rnn_b200.dist import allreduce_gradients
+        lib, dev, dist = self.lib, self.dev, self.dist
+        torch.manual_seed(cfg["seed"])
+        cls = self.tr.TTLSTM if cfg["cell"] == "lstm" else self.tr.TTGRU
+        with redirect_stdout(io.StringIO()):
+            model = cls(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu"), n_cores=cfg["d"], tt_rank=cfg["r"]).to(dev)
+        params = [p for p in model.parameters()]
+        B, T, H = B_rank, cfg["T"], cfg["H"]
+        c_rank = dict(cfg)
+        c_rank["seed"] = cfg["seed"] + self.rank        # every rank owns different sequences
+        x_host = make_input(c_rank, B).pin_memory()
+        x_dev = x_host.to(dev)
+        train = cfg["mode"] != "fwd"
+        dense_dout = torch.rand(B, T, H, device=dev) if cfg["grad"] == "dense" else None
+
+        def one_pass(x):
+            if not train:
+                with torch.no_grad():
+                    res = model(x)
+                return res[1][0] if cfg["cell"] == "lstm" else res[1]
+            for p in params:
+                p.grad = None
+            res = model(x)
+            out = res[0]
+            hT = res[1][0] if cfg["cell"] == "lstm" else res[1]
+            if dense_dout is not None:
+                out.backward(dense_dout)
+                result = hT
+            else:
+                loss = upstream(cfg, out, hT)
+                loss.backward()
+                result = loss
+            if dist is not None:
+                allreduce_gradients(params)             # one flat NCCL all-reduce of every TT-core / bias gradient
+            return result
+
+        for _ in range(warmup):
+            one_pass(x_dev)
+        self.barrier()
+        # ---- value: device-resident, per-step CUDA events, L2 flushed between steps -------------
+        lib.ttrnn_launch_count(1)
+        lib.ttrnn_tc_launch_count(1)
+        lib.ttrnn_kernel_timing(1)
+        ev = []
+        self.barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            self.flush_buf.fill_(1)
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            one_pass(x_dev)
+            e1.record()
+            ev.append((e0, e1))
+        self.barrier()
+        self.windows.append((w0, time.perf_counter()))
+        lib.ttrnn_kernel_timing(0)
+        launches = int(lib.ttrnn_launch_count(0))
+        tc_launches = int(lib.ttrnn_tc_launch_count(0))
+        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        nk = len(KINDS)
+        kms = (C.c_double * nk)(*([0.0] * nk))
+        kcnt = (C.c_int64 * nk)(*([0] * nk))
+        lib.ttrnn_kernel_times(kms, kcnt)
+
+        # ---- e2e: pinned host input -> H2D -> module API -> D2H of the result, wall clock ----------
+        e2e_ms, d2h = 0.0, 0
+        if with_e2e:
+            x_stage = torch.empty_like(x_dev)
+            self.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                x_stage.copy_(x_host, non_blocking=True)
+                res = one_pass(x_stage)
+                host = res.detach().to("cpu")           # D2H read of the step's result (loss / final state)
+                d2h = host.numel() * host.element_size()
+            self.barrier()
+            e2e_ms = (time.perf_counter() - t0) * 1e3
+            self.windows.append((t0, time.perf_counter()))
+            del x_stage
+
+        tot = torch.tensor([total_ms, e2e_ms], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(tot[0]), float(tot[1])
+        rec = None
+        if self.rank == 0:
+            world = self.world
+            units = B * T * world * steps
+            fwd_flops, hh_flops, ih_list, gate = algorithmic_flops(cfg)
+            mult = 3 if train else 1
+            plan = self._lib.describe_plan(model.spec().desc(B, T), training=train)
+            layers = plan[1:]
+            kern = {KINDS[i]: {"ms_per_step": kms[i] / steps, "launches_per_step": kcnt[i] / steps} for i in range(nk)}
+            # algorithmic FLOPs credited to each kernel group per sequence-step (reference chain order; recomputed
+            # forward work is NOT credited; where the hh core gradients are accumulated densely outside the recurrent
+            # kernel the backward credit 2*F_hh is split half / half between k_rnn_bwd and gemm_dw)
+            cred = {k: 0.0 for k in KINDS}
+            for l, lay in enumerate(layers):
+                route = lay.get("ih_route")
+                ihf = ih_list[l]
+                if route == "rank_one":
+                    cred["k_rnn_fwd"] += ihf
+                    if train:
+                        cred["k_rnn_bwd"] += 2 * ihf
+                elif route == "dense":
+                    cred["gemm_ih_fwd"] += ihf
+                    if train:
+                        need_dx = l > 0
+                        cred["gemm_dw"] += ihf
+                        cred["gemm_dx" if need_dx else "gemm_dw"] += ihf
+                else:
+                    cred["k_ttlinear_fwd"] += ihf
+                    if train:
+                        cred["k_ttlinear_bwd"] += 2 * ihf
+                cred["k_rnn_fwd"] += hh_flops + gate
+                if train:
+                    if lay.get("hh_dw") == "dense":
+                        cred["k_rnn_bwd"] += hh_flops + 2 * gate
+                        cred["gemm_dw"] += hh_flops
+                    elif lay.get("hh_dw") == "tt_chain":
+                        cred["k_rnn_bwd"] += hh_flops + 2 * gate
+                        cred["k_ttlinear_bwd"] += hh_flops
+                    else:
+                        cred["k_rnn_bwd"] += 2 * (hh_flops + gate)
+            dom = max(range(nk), key=lambda i: kms[i])
+            dom_ms = kms[dom] / steps
+            achieved = cred[KINDS[dom]] * B * T / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+            for i in range(nk):
+                ms = kms[i] / steps
+                kern[KINDS[i]]["credited_tflops"] = cred[KINDS[i]] * B * T / (ms * 1e-3) / 1e12 if ms > 0 else None
+                kern[KINDS[i]]["frac_of_ffma_peak"] = (kern[KINDS[i]]["credited_tflops"] / self.peak
+                                                       if ms > 0 and self.peak else None)
+            whole = mult * fwd_flops * B * T * steps / (total_ms * 1e-3) / 1e12
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    ent = json.load(f).get(cfg["name"].split(" ")[0])
+                if ent and ent["kernel"] == KINDS[dom]:
+                    traffic = ent["dram_bytes_per_launch"]
+            except Exception:
+                traffic = None
+            rec = {
+                "config_id": cid, "config": config_json(cfg, B, world, scaling), "scaling": scaling,
+                "value": units / (total_ms * 1e-3), "unit": "cell-steps/s",
+                "layer_cell_steps_per_s": units * cfg["L"] / (total_ms * 1e-3),
+                "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+                "e2e": ({"value": units / (e2e_ms * 1e-3), "unit": "cell-steps/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                         "d2h_bytes_per_step": d2h} if with_e2e else None),
+                "gpu_launches": launches, "tc_gemm_launches": tc_launches,
+                "roofline": {"bound": "fp32_ffma", "kernel": KINDS[dom], "achieved": achieved, "peak": self.peak,
+                             "unit": "TFLOP/s", "frac": achieved / self.peak if self.peak else None, "traffic": traffic,
+                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
+                             "peak_source": "ttrnn_ffma_probe measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
+                             "algorithmic_flops_per_seqstep": cred[KINDS[dom]],
+                             "whole_step_tflops_per_gpu": whole, "whole_step_frac": whole / self.peak if self.peak else None,
+                             "fwd_flops_per_seqstep": fwd_flops, "kernels": kern, "plan": plan},
+            }
+        del model, params, x_dev, x_host, dense_dout
+        torch.cuda.empty_cache()
+        return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--headline", type=int, default=3, choices=sorted(CONFIGS))
+    ap.add_argument("--config", type=int, default=0, help="shorthand: headline = this config and run only it")
+    ap.add_argument("--configs", default="1,2,3,4,5,6", help="configs measured into all_configs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
-    ap.add_argument("--seq-len", type=int, default=0, help="override T (profiling only; not a bench number)")
+    ap.add_argument("--batch", type=int, default=0, help="override the global batch of the headline config (profiling)")
+    ap.add_argument("--seq-len", type=int, default=0, help="override T of the headline config (profiling only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling measurement")
     args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
+    if args.config:
+        args.headline, args.configs = args.config, str(args.config)
+    ids = [int(v) for v in args.configs.split(",") if v.strip()]
+    if args.headline not in ids:
+        ids.append(args.headline)
+    cfgs = {i: dict(CONFIGS[i]) for i in ids}
+    head = cfgs[args.headline]
     if args.batch:
-        cfg["B"] = args.batch
+        head["B"] = args.batch
     if args.seq_len:
-        cfg["T"] = args.seq_len
-        cfg["name"] += " [T overridden to %d: profiling run]" % args.seq_len
+        head["T"] = args.seq_len
+        head["name"] += " [T overridden to %d: profiling run]" % args.seq_len
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config_json = {"workload": cfg["name"], "cell": cfg["cell"], "input_size": cfg["I"], "hidden_size": cfg["H"],
-                   "num_layers": cfg["L"], "n_cores": cfg["d"], "tt_rank": cfg["r"], "batch_per_gpu": cfg["B"],
-                   "global_batch": cfg["B"] * world, "seq_len": cfg["T"], "mode": cfg["mode"],
-                   "upstream_grad": cfg["grad"], "parallelism": "dp%d (batch-sharded replicas)" % world,
-                   "l2": "flushed between timed steps (256 MiB write)"}
+    metric = "TT-%s cell-steps/sec (batch x T), %s" % ("LSTM" if head["cell"] == "lstm" else "GRU", head["mode"])
 
     # ---------------- reference arm: the CPU path on the host cores --------------------------
     if args.impl == "reference":
         if rank != 0:
             return 0
-        Bs, Ts = CPU_SAMPLE_B[args.config], CPU_SAMPLE_T[args.config]
-        val, sec = run_cpu_oracle(cfg, Bs, Ts, args.steps, args.warmup)
-        sample = "batch %d x T %d of the workload per step (T %s); oracle port of the reference PyTorch path" % (
-            Bs, Ts, "as configured" if Ts == cfg["T"] else "reduced from %d" % cfg["T"])
-        line = {"impl": "reference", "metric": "TT-RNN cell-steps/sec (batch x T), %s" % cfg["mode"], "value": val,
-                "unit": "cell-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": config_json,
-                "cpu_baseline": {"value": val, "unit": "cell-steps/s", "cores": torch.get_num_threads(),
-                                 "kind": "port", "sample": sample},
+        # batch of the bounded sample: a pilot pass at batch 32 sizes it so that (warmup + steps) passes take ~150 s;
+        # T stays at the config value (the reference's cost is per-step dispatch and its O(T^2) backward)
+        T = head["T"]
+        _, pilot = run_cpu_oracle(head, 32, T, 1, 0)
+        budget = 150.0 / (args.steps + args.warmup)
+        Bs = int(max(16, min(head["B"], 32 * budget / pilot)))
+        Bs = max(16, (Bs // 16) * 16) if Bs < head["B"] else head["B"]
+        val, sec = run_cpu_oracle(head, Bs, T, args.steps, args.warmup)
+        sample = "batch %d of the config's %d sequences x T %d per step (pilot pass at batch 32 took %.1f s); oracle port of " \
+                 "the reference PyTorch path, %d threads" % (Bs, head["B"], T, pilot, torch.get_num_threads())
+        cj = config_json(head, Bs, 1, "none")
+        cj["parallelism"] = "host CPU, %d threads" % torch.get_num_threads()
+        cj["sample_of_global_batch"] = head["B"]
+        line = {"impl": "reference", "metric": metric, "value": val, "unit": "cell-steps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cj,
+                "sample": sample,
+                "cpu_baseline": {"value": val, "unit": "cell-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                 "sample": sample, "batch": Bs, "seq_len": T},
                 "e2e": {"value": val, "unit": "cell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
         return 0
 
     # ---------------- our arm -----------------------------------------------------------------
-    import tensorized_rnn_b200 as tr
-    from tensorized_rnn_b200 import _lib
-    from tensorized_rnn_b200.dist import allreduce_gradients
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-    lib = _lib.load()
-
-    torch.manual_seed(cfg["seed"])
-    cls = tr.TTLSTM if cfg["cell"] == "lstm" else tr.TTGRU
-    with redirect_stdout(io.StringIO()):
-        model = cls(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu"), n_cores=cfg["d"], tt_rank=cfg["r"]).to(dev)
-    params = [p for p in model.parameters()]
-    B, T, H = cfg["B"], cfg["T"], cfg["H"]
-    c_rank = dict(cfg)
-    c_rank["seed"] = cfg["seed"] + rank               # every rank owns different sequences
-    x_host = make_input(c_rank, B).pin_memory()
-    x_dev = x_host.to(dev)
-    train = cfg["mode"] != "fwd"
-    dense_dout = None
-    if cfg["grad"] == "dense":
-        dense_dout = torch.rand(B, T, H, device=dev)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def one_pass(x):
-        if not train:
-            with torch.no_grad():
-                res = model(x)
-            return res[1][0] if cfg["cell"] == "lstm" else res[1]
-        for p in params:
-            p.grad = None
-        res = model(x)
-        out = res[0]
-        hT = res[1][0] if cfg["cell"] == "lstm" else res[1]
-        if dense_dout is not None:
-            out.backward(dense_dout)
-            result = hT
-        else:
-            loss = upstream(cfg, out, hT)
-            loss.backward()
-            result = loss
-        if dist is not None:
-            allreduce_gradients(params)                 # one flat NCCL all-reduce of every TT-core / bias gradient
-        return result
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # FP32 peak: FFMA probe, best of 5 (burst figure for a kernel timed alone)
-    sink = torch.zeros(4, device=dev)
-    flops = C.c_double(0)
-    stream = torch.cuda.current_stream().cuda_stream
-    peak = 0.0
-    for _ in range(6):
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        _lib.check(lib.ttrnn_ffma_probe(4000, sink.data_ptr(), C.byref(flops), stream), "ttrnn_ffma_probe")
-        e1.record()
-        torch.cuda.synchronize()
-        peak = max(peak, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
-
-    for _ in range(args.warmup):
-        one_pass(x_dev)
-    barrier()
-
-    # ---- value: device-resident, per-step CUDA events, L2 flushed between steps -------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.ttrnn_launch_count(1)
-    lib.ttrnn_kernel_timing(1)
-    ev = []
-    barrier()
-    for _ in range(args.steps):
-        flush_buf.fill_(1)
-        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-        e0.record()
-        one_pass(x_dev)
-        e1.record()
-        ev.append((e0, e1))
-    barrier()
-    lib.ttrnn_kernel_timing(0)
-    launches = int(lib.ttrnn_launch_count(0))
-    clocks = sampler.stop() if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = sum(step_ms)
-    kms = (C.c_double * 4)(0, 0, 0, 0)
-    kcnt = (C.c_int64 * 4)(0, 0, 0, 0)
-    lib.ttrnn_kernel_times(kms, kcnt)
+    gb = GpuBench(rank, world, local_rank)
 
-    # ---- e2e: pinned host input -> H2D -> module API -> D2H of the result, wall clock ----------
-    x_stage = torch.empty_like(x_dev)
-    barrier()
-    t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(args.steps):
-        x_stage.copy_(x_host, non_blocking=True)
-        res = one_pass(x_stage)
-        host = res.detach().to("cpu")                   # D2H read of the step's result (loss / final state)
-        d2h = host.numel() * host.element_size()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    def split(B):
+        return (B + world - 1) // world
 
-    tot = torch.tensor([total_ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-    if dist is not None:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(tot[0]), float(tot[1])
+    def steps_for(cid):
+        cw, cs = STEP_CAP.get(cid, (args.warmup, args.steps))
+        return min(args.warmup, cw), min(args.steps, cs)
+
+    records = []
+    head_rec, head_weak = None, None
+    order = [args.headline] + [i for i in ids if i != args.headline]
+    for cid in order:
+        cfg = cfgs[cid]
+        w, s = steps_for(cid)
+        rec = gb.run(cid, cfg, split(cfg["B"]), s, w, "strong")
+        weak = None
+        if world > 1 and not args.no_weak:
+            weak = gb.run(cid, cfg, cfg["B"], min(s, 5), min(w, 3), "weak", with_e2e=False)
+        if rank == 0:
+            if weak is not None:
+                rec["weak"] = {"value": weak["value"], "ms_per_step": weak["ms_per_step"], "batch_per_gpu": cfg["B"],
+                               "global_batch": cfg["B"] * world}
+            records.append(rec)
+            if cid == args.headline:
+                head_rec = rec
 
     if rank == 0:
-        units = B * T * world * args.steps
-        value = units / (total_ms * 1e-3)
-        fwd_flops, hh_flops = algorithmic_flops(cfg)
-        mult = 3 if train else 1
-        names = ["k_ttlinear_fwd", "k_rnn_fwd", "k_rnn_bwd", "k_ttlinear_bwd"]
-        share = {names[i]: {"ms_per_step": kms[i] / args.steps, "launches_per_step": kcnt[i] / args.steps}
-                 for i in range(4)}
-        dom = max(range(4), key=lambda i: kms[i])
-        # algorithmic FLOPs of the dominant kernel per step (recomputed forward work is NOT credited)
-        G = 4 if cfg["cell"] == "lstm" else 3
-        gate = 2 * G * H + 12 * H
-        ih_flops = fwd_flops - cfg["L"] * (hh_flops + gate)
-        per_seqstep = {0: ih_flops * (1 if train else 1), 1: cfg["L"] * (hh_flops + gate),
-                       2: 2 * cfg["L"] * (hh_flops + gate), 3: 2 * ih_flops}[dom]
-        dom_flops = per_seqstep * B * T
-        dom_ms = kms[dom] / args.steps
-        achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
-        whole = mult * fwd_flops * B * T * world * args.steps / (total_ms * 1e-3) / 1e12 / world
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                ent = json.load(f).get(cfg["name"])
-            if ent and ent["kernel"] == names[dom].replace("k_ttlinear", "k_ttlinear"):
-                traffic = ent["dram_bytes_per_launch"]
-        except Exception:
-            traffic = None
-        # contraction order the engine chose for each layer's batched ih projection (0 = TT chain, 1 = dense
-        # W_ih formed once per call, 2 = rank-one input): the roofline figures above always credit the
-        # reference's core-by-core sweep; where the dense order is cheaper the kernels execute
-        # FEWER multiply-adds than credited, so both costs are reported
-        routes = []
-        desc = model.spec().desc(B, T)
-        for l in range(cfg["L"]):
-            cm, dm = C.c_int64(0), C.c_int64(0)
-            rt = int(lib.ttrnn_rnn_ih_route(C.byref(desc), l, C.byref(cm), C.byref(dm)))
-            routes.append({"layer": l, "route": {0: "tt_chain", 1: "dense", 2: "rank_one"}.get(rt, str(rt)),
-                           "chain_macs_per_row": cm.value, "dense_macs_per_row": dm.value})
-        line = {
-            "metric": "TT-RNN cell-steps/sec (batch x T), %s" % cfg["mode"],
-            "value": value, "unit": "cell-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic (random-init TT cores, %s input)" % cfg["inp"],
-            "config": config_json,
-            "e2e": {"value": units / (e2e_ms * 1e-3), "unit": "cell-steps/s",
-                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"bound": "fp32_ffma", "kernel": names[dom], "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
-                         "peak_source": "ttrnn_ffma_probe measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
-                         "algorithmic_flops_per_seqstep": per_seqstep,
-                         "whole_step_tflops_per_gpu": whole, "whole_step_frac": whole / peak if peak else None,
-                         "fwd_flops_per_seqstep": fwd_flops, "kernels": share, "ih_projection": routes},
-        }
+        sampler.stop()
+        clocks = sampler.summary(gb.windows)
+        # CPU baseline (N = 1 only): bounded sample per config, batch stated
         if world == 1 and not args.no_cpu_baseline:
-            Bs, Ts = CPU_SAMPLE_B[args.config], CPU_SAMPLE_T[args.config]
-            val, sec = run_cpu_oracle(cfg, Bs, Ts, 1, 1 if sec_budget_ok(args.config) else 0)
-            line["cpu_baseline"] = {"value": val, "unit": "cell-steps/s", "cores": torch.get_num_threads(),
-                                    "kind": "port", "seconds": sec,
-                                    "sample": "batch %d x T %d of the workload, 1 pass, oracle port of the "
-                                              "reference PyTorch path" % (Bs, Ts)}
+            for rec in records:
+                cid = rec["config_id"]
+                Bs, Ts = CPU_SAMPLE[cid]
+                Ts = min(Ts, cfgs[cid]["T"])
+                val, sec = run_cpu_oracle(cfgs[cid], Bs, Ts, 1, 0)
+                rec["cpu_baseline"] = {"value": val, "unit": "cell-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                                       "seconds": sec, "batch": Bs, "seq_len": Ts,
+                                       "sample": "batch %d x T %d of the workload (global batch %d, T %d), 1 pass, oracle port "
+                                                 "of the reference PyTorch path" % (Bs, Ts, cfgs[cid]["B"], cfgs[cid]["T"])}
+        line = {
+            "metric": metric, "value": head_rec["value"], "unit": "cell-steps/s", "n_gpus": world,
+            "steps": head_rec["steps"], "warmup": head_rec["warmup"], "ms_per_step": head_rec["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (random-init TT cores, %s input)" % head["inp"],
+            "config": head_rec["config"], "e2e": head_rec["e2e"], "gpu_launches": head_rec["gpu_launches"],
+            "clocks": clocks, "roofline": head_rec["roofline"],
+        }
+        if "weak" in head_rec:
+            line["weak"] = head_rec["weak"]
+        if "cpu_baseline" in head_rec:
+            line["cpu_baseline"] = head_rec["cpu_baseline"]
+        line["all_configs"] = [{k: v for k, v in r.items() if k != "config_id"} | {"id": r["config_id"]} for r in records]
         print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    if gb.dist is not None:
+        gb.dist.destroy_process_group()
     return 0
-
-
-def sec_budget_ok(config):
-    return True
 
 
 if __name__ == "__main__":

@@ -152,7 +152,7 @@ int ttrnn_ffma_probe(int32_t iters, float *sink, double *flops_out, void *stream
 /* counts kernels launched by this library since the last reset (host counter) */
 int64_t ttrnn_launch_count(int32_t reset);
 /* Per-kernel device timing for the roofline report.  ttrnn_kernel_timing(1) makes every launch
- * of the four main kernels record a CUDA-event pair on its own stream (bounded pool; extra
+ * of the main kernel groups record a CUDA-event pair on its own stream (bounded pool; extra
  * launches are simply not recorded); ttrnn_kernel_timing(0) stops.  ttrnn_kernel_times()
  * synchronises the recorded events, adds their elapsed milliseconds into ms[kind] and the
  * number of recorded launches into count[kind], and clears the pool.  Kinds: */
@@ -160,7 +160,10 @@ int64_t ttrnn_launch_count(int32_t reset);
 #define TTRNN_K_RNN_FWD      1
 #define TTRNN_K_RNN_BWD      2
 #define TTRNN_K_TTLINEAR_BWD 3
-#define TTRNN_K_KINDS        4
+#define TTRNN_K_GEMM_FWD     4   /* dense-route ih projection (tensor-core or FFMA row GEMM)          */
+#define TTRNN_K_GEMM_DX      5   /* dense-route dX = delta * W                                         */
+#define TTRNN_K_GEMM_DW      6   /* dense-route core-gradient accumulation dW^T = X^T delta (ih and hh) */
+#define TTRNN_K_KINDS        7
 int ttrnn_kernel_timing(int32_t enable);
 int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K_KINDS]*/);
 

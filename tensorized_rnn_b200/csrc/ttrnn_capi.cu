@@ -679,7 +679,7 @@ int dense_dw(const DevInfo &dv, long long rows, int rpb, const float *x, long lo
         // tensor cores: tcgen05 3xTF32 with the TMEM accumulator promoted into FP32 registers every 32 k-blocks
         int ns = 0, rc;
         {
-            KernelTimer tm(TTRNN_K_TTLINEAR_BWD, st);
+            KernelTimer tm(TTRNN_K_GEMM_DW, st);
             rc = ttc::launch_tc_red(rows, rpb, x, x_bstride, I, delta, d_bstride, GH, D.part, want_bias ? D.pbias : nullptr,
                                     dv.sms, kDenseMaxSplit, &ns, st);
         }
@@ -715,7 +715,7 @@ int dense_dw(const DevInfo &dv, long long rows, int rpb, const float *x, long lo
     g.b.p = delta; g.b.bstride = d_bstride; g.b.rpb = rpb; g.b.ld = GH;
     g.part = D.part; g.pbias = want_bias ? D.pbias : nullptr;
     {
-        KernelTimer tm(TTRNN_K_TTLINEAR_BWD, st);
+        KernelTimer tm(TTRNN_K_GEMM_DW, st);
         if (TMsel == 4) ttg::k_gemm_red<4><<<(unsigned)(tiles * nsplit), ttg::NT, 0, st>>>(g);
         else ttg::k_gemm_red<8><<<(unsigned)(tiles * nsplit), ttg::NT, 0, st>>>(g);
     }
@@ -954,7 +954,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, co
         }
         auto project = [&](int t0, int tc) -> int {
             if (dense)
-                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
+                return dense_rows_gemm(TTRNN_K_GEMM_FWD, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
                                        D.wt, D.w_hi, D.w_lo, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, false, st);
             return launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                        params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
@@ -1118,7 +1118,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, c
         bool dense_first = true;
         auto project = [&](int t0, int tc) -> int {
             if (dense)
-                return dense_rows_gemm(TTRNN_K_TTLINEAR_FWD, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
+                return dense_rows_gemm(TTRNN_K_GEMM_FWD, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin,
                                        D.wt, D.w_hi, D.w_lo, GH, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, false, st);
             return launch_ttlinear_fwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                        params + lp.off_ih_cores, b_ih, lstm ? b_hh : nullptr, xg, (long long)tc * GH, st,
@@ -1132,7 +1132,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, c
                     return 1;
                 dense_first = false;
                 if (dlin)
-                    return dense_rows_gemm(TTRNN_K_TTLINEAR_BWD, dv, B * tc, tc, xg, (long long)tc * GH, GH, D.w, D.wt_hi, D.wt_lo,
+                    return dense_rows_gemm(TTRNN_K_GEMM_DX, dv, B * tc, tc, xg, (long long)tc * GH, GH, D.w, D.wt_hi, D.wt_lo,
                                            nin, nullptr, nullptr, dlin + (long long)t0 * nin, (long long)T * nin, true, st);
                 return 0;
             }
