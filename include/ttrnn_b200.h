@@ -144,6 +144,26 @@ int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, cons
                         float *da, float *du, float *dh_prev, float *dc_prev, float *dc_total,
                         void *stream);
 
+/* GE2E head on the device: the part of the speaker-encoder training step the reference runs on the CPU
+ * after every RNN pass (experiments/speaker_verification/encoder/main.py:279-280 moves the embeddings to `loss_device`).
+ *
+ * ttrnn_embed_forward: embeds = relu(x) / ||relu(x)||_2 per row (speaker_encoder.py:86-89); x, y (rows, E),
+ * inv_norm (rows) is kept for the backward.  ttrnn_embed_backward: dx from dy. */
+int ttrnn_embed_forward(int64_t rows, int32_t E, const float *x, float *y, float *inv_norm, void *stream);
+int ttrnn_embed_backward(int64_t rows, int32_t E, const float *x, const float *y, const float *inv_norm,
+                         const float *dy, float *dx, void *stream);
+/* GE2E softmax loss of `embeds` (S speakers, U utterances each, E features; row = s * U + u), training form of
+ * SpeakerEncoder.similarity_matrix / .loss (speaker_encoder.py:93-141, 143-156, enrollment_embeds = None): inclusive and
+ * exclusive centroids, sim[(s,u), j], logits = wb[0] * sim + wb[1], mean cross-entropy against the speaker index.
+ * wb: device pointer to {similarity_weight, similarity_bias}; loss: device scalar; sim_out (optional, S*U x S): the scaled
+ * similarity matrix wb[0] * sim + wb[1] that SpeakerEncoder.similarity_matrix returns (speaker_encoder.py:139).  `workspace` (ttrnn_ge2e_workspace_bytes) carries centroids / probabilities to the backward,
+ * which writes d_embeds (S*U x E) and d_wb[2] for an upstream gradient *dloss (device scalar). */
+int64_t ttrnn_ge2e_workspace_bytes(int32_t S, int32_t U, int32_t E);
+int ttrnn_ge2e_loss_forward(int32_t S, int32_t U, int32_t E, const float *embeds, const float *wb, float *loss,
+                            float *sim_out, void *workspace, void *stream);
+int ttrnn_ge2e_loss_backward(int32_t S, int32_t U, int32_t E, const float *embeds, const float *wb,
+                             const float *dloss, void *workspace, float *d_embeds, float *d_wb, void *stream);
+
 /* Measurement helpers (bench.py only).
  * ttrnn_ffma_probe: dependent-chain-free FP32 FFMA loop on every SM; writes the
  * number of FLOPs executed to *flops_out (host) and leaves a checksum in sink

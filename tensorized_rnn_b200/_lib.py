@@ -56,6 +56,11 @@ SYMBOLS = {
     "ttrnn_ttlinear_backward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 8),
     "ttrnn_cell_forward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 7),
     "ttrnn_cell_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 12),
+    "ttrnn_embed_forward": (C.c_int, [C.c_int64, C.c_int32] + [_P] * 4),
+    "ttrnn_embed_backward": (C.c_int, [C.c_int64, C.c_int32] + [_P] * 6),
+    "ttrnn_ge2e_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),
+    "ttrnn_ge2e_loss_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_P] * 6),
+    "ttrnn_ge2e_loss_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_int32] + [_P] * 7),
     "ttrnn_rnn_ih_route": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "ttrnn_static_kernel_table": (C.c_int, [C.c_char_p, C.c_int32]),
     "ttrnn_rnn_describe": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.c_char_p, C.c_int32]),

@@ -13,6 +13,7 @@
 #include "tt_cell.cuh"
 #include "tt_gemm.cuh"
 #include "tt_tc.cuh"
+#include "tt_ge2e.cuh"
 #include "tt_static.cuh"
 #include "tt_static_api.h"
 
@@ -1518,6 +1519,93 @@ int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, cons
     if (lstm) k_cell_bwd<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     else k_cell_bwd<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---- GE2E head ------------------------------------------------------------------------------------
+int ttrnn_embed_forward(int64_t rows, int32_t E, const float *x, float *y, float *inv_norm, void *stream) {
+    if (rows < 1 || E < 1) return fail("ttrnn_embed_forward: rows and E must be >= 1");
+    if (!x || !y || !inv_norm) return fail("ttrnn_embed_forward: null operand");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    ge2e::k_embed_fwd<<<(unsigned)((rows + 7) / 8), ge2e::NT, 0, (cudaStream_t)stream>>>(x, y, inv_norm, (int)rows, E);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ttrnn_embed_backward(int64_t rows, int32_t E, const float *x, const float *y, const float *inv_norm, const float *dy,
+                         float *dx, void *stream) {
+    if (rows < 1 || E < 1) return fail("ttrnn_embed_backward: rows and E must be >= 1");
+    if (!x || !y || !inv_norm || !dy || !dx) return fail("ttrnn_embed_backward: null operand");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    ge2e::k_embed_bwd<<<(unsigned)((rows + 7) / 8), ge2e::NT, 0, (cudaStream_t)stream>>>(x, y, inv_norm, dy, dx, (int)rows, E);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// workspace layout (floats): c_incl S*E | n_incl S | c_excl S*U*E | n_excl S*U | sim B*S | prob B*S | row B | dsim B*S | row_dw B | row_db B
+struct Ge2eWs {
+    float *c_incl, *n_incl, *c_excl, *n_excl, *sim, *prob, *row, *dsim, *row_dw, *row_db;
+    long long total;
+};
+static Ge2eWs ge2e_carve(float *base, long long S, long long U, long long E) {
+    Ge2eWs w;
+    const long long B = S * U;
+    long long o = 0;
+    auto take = [&](long long n) { float *p = base ? base + o : nullptr; o += r4(n); return p; };
+    w.c_incl = take(S * E); w.n_incl = take(S); w.c_excl = take(B * E); w.n_excl = take(B);
+    w.sim = take(B * S); w.prob = take(B * S); w.row = take(B); w.dsim = take(B * S); w.row_dw = take(B); w.row_db = take(B);
+    w.total = o;
+    return w;
+}
+static int ge2e_args_ok(int S, int U, int E) {
+    if (S < 2 || U < 2 || E < 1) return fail("GE2E loss needs >= 2 speakers, >= 2 utterances per speaker and E >= 1 (got %d, %d, %d)", S, U, E);
+    if ((long long)(E + S + 8) * 4 > 200 * 1024) return fail("GE2E loss: embedding size %d / %d speakers exceed the shared-memory staging", E, S);
+    return 0;
+}
+
+int64_t ttrnn_ge2e_workspace_bytes(int32_t S, int32_t U, int32_t E) {
+    if (ge2e_args_ok(S, U, E)) return -1;
+    return ge2e_carve(nullptr, S, U, E).total * 4;
+}
+
+int ttrnn_ge2e_loss_forward(int32_t S, int32_t U, int32_t E, const float *embeds, const float *wb, float *loss,
+                            float *sim_out, void *workspace, void *stream) {
+    if (ge2e_args_ok(S, U, E)) return 1;
+    if (!embeds || !wb || !loss || !workspace) return fail("ttrnn_ge2e_loss_forward: null operand");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    Ge2eWs w = ge2e_carve((float *)workspace, S, U, E);
+    const int B = S * U;
+    ge2e::k_centroids<<<S, ge2e::NT, (size_t)(E + 8) * 4, st>>>(embeds, w.c_incl, w.n_incl, w.c_excl, w.n_excl, U, E);
+    ge2e::k_sim_loss<<<B, ge2e::NT, (size_t)(E + S + 8) * 4, st>>>(embeds, w.c_incl, w.c_excl, wb, w.sim, w.prob, w.row, sim_out, S, U, E);
+    ge2e::k_mean<<<1, ge2e::NT, 0, st>>>(w.row, B, loss);
+    g_launches += 3;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int ttrnn_ge2e_loss_backward(int32_t S, int32_t U, int32_t E, const float *embeds, const float *wb, const float *dloss,
+                             void *workspace, float *d_embeds, float *d_wb, void *stream) {
+    if (ge2e_args_ok(S, U, E)) return 1;
+    if (!embeds || !wb || !dloss || !workspace || !d_embeds || !d_wb) return fail("ttrnn_ge2e_loss_backward: null operand");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    Ge2eWs w = ge2e_carve((float *)workspace, S, U, E);
+    const int B = S * U;
+    ge2e::k_bwd_rows<<<B, ge2e::NT, (size_t)S * 4, st>>>(w.c_incl, w.c_excl, wb, w.sim, w.prob, dloss, w.dsim, d_embeds, w.row_dw,
+                                                         w.row_db, S, U, E);
+    ge2e::k_bwd_centroids<<<S, ge2e::NT, (size_t)(E + 8) * 4, st>>>(embeds, w.c_incl, w.n_incl, w.c_excl, w.n_excl, w.dsim, d_embeds,
+                                                                 S, U, E);
+    ge2e::k_sum<<<1, ge2e::NT, 0, st>>>(w.row_dw, B, d_wb);
+    ge2e::k_sum<<<1, ge2e::NT, 0, st>>>(w.row_db, B, d_wb + 1);
+    g_launches += 4;
     CU_CHECK(cudaGetLastError());
     return 0;
 }

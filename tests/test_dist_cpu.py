@@ -81,3 +81,32 @@ def test_single_flat_allreduce_world2(tmp_path):
             assert torch.allclose(res[r]["grads"][i], want, atol=1e-6), (i, r)
     full = torch.arange(10 * 3 * 2, dtype=torch.float32).view(10, 3, 2)
     assert torch.equal(torch.cat([res[0]["shard"], res[1]["shard"]]), full)
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tensorized_rnn_b200.ge2e import _AllGatherRows
+    # each rank owns 3 speakers x 2 utterances x 4 features of a global batch of 6 speakers
+    x = (torch.arange(3 * 2 * 4, dtype=torch.float32).view(3, 2, 4) + 100 * rank).requires_grad_(True)
+    full = _AllGatherRows.apply(x, None)
+    weight = torch.arange(full.numel(), dtype=torch.float32).view_as(full)
+    (full * weight).sum().backward()             # every rank evaluates the same global loss
+    torch.save({"full": full.detach().clone(), "grad": x.grad.clone()}, os.path.join(out_dir, "g%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_ge2e_embedding_all_gather_world2(tmp_path):
+    """GE2E couples every speaker of the global batch: embeddings are all-gathered, every rank evaluates the global loss
+    and keeps the gradient rows of its own speakers (tensorized_rnn_b200/ge2e.py)."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_gather_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "g%d.pt" % r)) for r in range(world)]
+    base = torch.arange(3 * 2 * 4, dtype=torch.float32).view(3, 2, 4)
+    want_full = torch.cat([base, base + 100])
+    weight = torch.arange(want_full.numel(), dtype=torch.float32).view_as(want_full)
+    for r in range(world):
+        assert torch.equal(res[r]["full"], want_full)
+        assert torch.equal(res[r]["grad"], weight[3 * r:3 * r + 3])
