@@ -144,6 +144,31 @@ int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, cons
                         float *da, float *du, float *dh_prev, float *dc_prev, float *dc_total,
                         void *stream);
 
+/* Dense LSTM / GRU baselines through the same engine: the reference's `LSTM` / `GRU` modules with dense
+ * nn.Linear weights (tensorized_rnn/lstm.py:7-41,44-135, gru.py:11-50,52-136), selected by pmnist_test.py without --tt and
+ * by SpeakerEncoder(compression=None).  Same forward / backward contract as ttrnn_rnn_forward / _backward.
+ * Parameter blob, per layer: [W_ih (G*H x in)] [b_ih (G*H): GRU with bias only] [W_hh (G*H x H)] [b_hh (G*H) with bias]
+ * -- the reference's state_dict order cell{l}.input_weights.weight [.bias], cell{l}.hidden_weights.weight [.bias]
+ * (the dense LSTMCell gives its input map no bias, lstm.py:17-18).  The ih projection, dX and both weight gradients are
+ * batched over the whole sequence as tensor-core GEMMs; the recurrence is one GEMM + one fused gate kernel per step.
+ * hidden_size must be a multiple of 32 with G*H a multiple of 128. */
+typedef struct ttrnn_dense_desc {
+    int32_t cell, num_layers, input_size, hidden_size, has_bias, seq_len;
+    int64_t batch;
+} ttrnn_dense_desc;
+int64_t ttrnn_dense_rnn_param_count(const ttrnn_dense_desc *desc);
+int ttrnn_dense_rnn_workspace_bytes(const ttrnn_dense_desc *desc, int64_t *saved_bytes, int64_t *scratch_bytes);
+/* `saved` is required (training and inference): it holds the pre-activation blocks of every step. */
+int ttrnn_dense_rnn_forward(const ttrnn_dense_desc *desc, const float *x, const float *h0, const float *c0,
+                            const float *params, float *out, float *hT, float *cT,
+                            void *saved, void *scratch, void *stream);
+/* `saved` is consumed (overwritten with gradients): one backward per forward. */
+int ttrnn_dense_rnn_backward(const ttrnn_dense_desc *desc, const float *x, const float *h0, const float *c0,
+                             const float *params, const float *out, void *saved,
+                             const float *d_out, const float *d_hT, const float *d_cT,
+                             float *d_params, float *d_x, float *d_h0, float *d_c0,
+                             void *scratch, void *stream);
+
 /* GE2E head on the device: the part of the speaker-encoder training step the reference runs on the CPU
  * after every RNN pass (experiments/speaker_verification/encoder/main.py:279-280 moves the embeddings to `loss_device`).
  *

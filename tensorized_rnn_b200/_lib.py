@@ -34,6 +34,11 @@ class RnnDesc(C.Structure):
                 ("ih", TTShape * MAX_LAYERS), ("hh", TTShape * MAX_LAYERS)]
 
 
+class DenseDesc(C.Structure):
+    _fields_ = [("cell", C.c_int32), ("num_layers", C.c_int32), ("input_size", C.c_int32), ("hidden_size", C.c_int32),
+                ("has_bias", C.c_int32), ("seq_len", C.c_int32), ("batch", C.c_int64)]
+
+
 class RnnWorkspace(C.Structure):
     # `plan`: opaque execution plan stamped by ttrnn_rnn_workspace_bytes(); the same struct goes to the forward and
     # to its backward so both interpret `saved` / scratch identically whatever happens to the options in between
@@ -56,6 +61,10 @@ SYMBOLS = {
     "ttrnn_ttlinear_backward": (C.c_int, [C.POINTER(TTShape), C.c_int64] + [_P] * 8),
     "ttrnn_cell_forward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 7),
     "ttrnn_cell_backward": (C.c_int, [C.c_int32, C.c_int64, C.c_int32] + [_P] * 12),
+    "ttrnn_dense_rnn_param_count": (C.c_int64, [C.POINTER(DenseDesc)]),
+    "ttrnn_dense_rnn_workspace_bytes": (C.c_int, [C.POINTER(DenseDesc), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ttrnn_dense_rnn_forward": (C.c_int, [C.POINTER(DenseDesc)] + [_P] * 10),
+    "ttrnn_dense_rnn_backward": (C.c_int, [C.POINTER(DenseDesc)] + [_P] * 15),
     "ttrnn_embed_forward": (C.c_int, [C.c_int64, C.c_int32] + [_P] * 4),
     "ttrnn_embed_backward": (C.c_int, [C.c_int64, C.c_int32] + [_P] * 6),
     "ttrnn_ge2e_workspace_bytes": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32]),

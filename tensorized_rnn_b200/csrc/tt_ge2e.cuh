@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(NT) k_sim_loss(const float *__restrict__ emb, 
                                                  float *__restrict__ sim, float *__restrict__ prob,
                                                  float *__restrict__ row_loss, float *__restrict__ logits_out, int S, int U,
                                                  int E) {
-    extern __shared__ float sm[];                 // e[E] + logits[S] + 8
-    float *ev = sm, *lg = sm + E, *red = lg + S;
+    extern __shared__ float sm[];                 // e[E] + logits[S]
+    float *ev = sm, *lg = sm + E;
     const int row = blockIdx.x, s = row / U;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int e = threadIdx.x; e < E; e += NT) ev[e] = emb[(long long)row * E + e];
@@ -129,7 +129,6 @@ __global__ void __launch_bounds__(NT) k_sim_loss(const float *__restrict__ emb, 
     for (int j = 0; j < S; ++j) den += expf(lg[j] - mx);
     for (int j = threadIdx.x; j < S; j += NT) prob[(long long)row * S + j] = expf(lg[j] - mx) / den;
     if (threadIdx.x == 0) row_loss[row] = -(lg[s] - mx - logf(den));
-    (void)red;
 }
 
 // mean of n values in a fixed order (one block)

@@ -14,6 +14,7 @@
 #include "tt_gemm.cuh"
 #include "tt_tc.cuh"
 #include "tt_ge2e.cuh"
+#include "tt_dense.cuh"
 #include "tt_static.cuh"
 #include "tt_static_api.h"
 
@@ -1520,6 +1521,299 @@ int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, cons
     else k_cell_bwd<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// ---- dense LSTM / GRU baselines -----------------------------------------------------------------
+namespace {
+struct DenseLayerOff { long long w_ih, b_ih, w_hh, b_hh; int nin; bool has_bih, has_bhh; };
+struct DensePlan {
+    int G = 0;
+    long long param_floats = 0;
+    DenseLayerOff layer[TTRNN_MAX_LAYERS];
+};
+// parameter blob, per layer: [W_ih (G*H x I)] [b_ih (G*H): GRU with bias only] [W_hh (G*H x H)] [b_hh (G*H) with bias]
+// (LSTMCell: input_weights has no bias, lstm.py:17-21; GRUCell: both carry `bias`, gru.py:19-23)
+int build_dense_plan(const ttrnn_dense_desc *d, DensePlan *dp) {
+    if (!d) return fail("null descriptor");
+    if (d->cell != TTRNN_CELL_LSTM && d->cell != TTRNN_CELL_GRU) return fail("unknown cell kind %d", d->cell);
+    if (d->num_layers < 1 || d->num_layers > TTRNN_MAX_LAYERS) return fail("num_layers %d out of range", d->num_layers);
+    if (d->input_size < 1 || d->hidden_size < 1 || d->batch < 1 || d->seq_len < 1) return fail("sizes must be positive");
+    if (d->hidden_size % 32 != 0 || (gates_of(d->cell) * d->hidden_size) % 128 != 0)
+        return fail("dense cells: hidden_size must be a multiple of 32 with G*H a multiple of 128 (got %d)", d->hidden_size);
+    dp->G = gates_of(d->cell);
+    const long long GH = (long long)dp->G * d->hidden_size;
+    long long off = 0;
+    for (int l = 0; l < d->num_layers; ++l) {
+        DenseLayerOff &o = dp->layer[l];
+        o.nin = l == 0 ? d->input_size : d->hidden_size;
+        o.has_bih = d->has_bias && d->cell == TTRNN_CELL_GRU;
+        o.has_bhh = d->has_bias != 0;
+        o.w_ih = off; off += GH * o.nin;
+        o.b_ih = off; if (o.has_bih) off += GH;
+        o.w_hh = off; off += GH * d->hidden_size;
+        o.b_hh = off; if (o.has_bhh) off += GH;
+    }
+    dp->param_floats = off;
+    return 0;
+}
+struct DenseLayout {
+    long long BTH, BTG, BH;
+    long long sv_hs, sv_cs, sv_a, sv_u, sv_total;      // saved: inner-layer outputs, c states, a = W_ih x, u = W_hh h (per layer)
+    long long s_w, s_dh, s_part, s_total;              // scratch: weight splits / transposes, dh carries, reduction partials
+    long long wmax;
+};
+void build_dense_layout(const ttrnn_dense_desc *d, const DensePlan &dp, DenseLayout *lo) {
+    const long long B = d->batch, T = d->seq_len, H = d->hidden_size, L = d->num_layers, GH = (long long)dp.G * H;
+    const long long Imax = d->input_size > H ? d->input_size : H;
+    lo->BTH = B * T * H; lo->BTG = B * T * GH; lo->BH = B * H;
+    long long o = 0;
+    lo->sv_hs = o; o += r4((L - 1) * lo->BTH);
+    lo->sv_cs = o; o += (d->cell == TTRNN_CELL_LSTM) ? r4(L * lo->BTH) : 0;
+    lo->sv_a = o; o += r4(L * lo->BTG);
+    lo->sv_u = o; o += r4(L * lo->BTG);
+    lo->sv_total = o;
+    lo->wmax = r4(GH * Imax);
+    o = 0;
+    lo->s_w = o; o += 8 * lo->wmax;                    // W_ih hi/lo, W_hh hi/lo, W^T + hi/lo (one side at a time), dW^T
+    lo->s_dh = o; o += 6 * r4(lo->BH);                 // dh_gemm, dh_direct x 2 (ping-pong), dc, h zero pad, spare
+    lo->s_part = o; o += kDenseMaxSplit * (lo->wmax + r4(GH)) + 2 * r4(GH);
+    lo->s_total = o;
+}
+// y = x W^T (+ bias): rows GEMM on the tensor cores when it fits, else FFMA (needs W^T as K x N)
+int dense_linear(const DevInfo &dv, long long rows, int rpb, const float *x, long long x_bstride, int K, const float *w_hi,
+                 const float *w_lo, const float *wt, int N, const float *bias, float *y, long long y_bstride, bool grad,
+                 cudaStream_t st) {
+    return dense_rows_gemm(grad ? TTRNN_K_GEMM_DX : TTRNN_K_GEMM_FWD, dv, rows, rpb, x, x_bstride, K, wt, w_hi, w_lo, N, bias, nullptr,
+                           y, y_bstride, grad, st);
+}
+// out[n] = sum over rows of m[r, n] (rows x N contiguous): split partial sums, then a fixed-order sum of the splits
+int dense_colsum(const DevInfo &dv, const float *m, long long rows, int N, float *part, float *out, cudaStream_t st) {
+    int nsplit = (int)((rows + 511) / 512);
+    if (nsplit > kDenseMaxSplit) nsplit = kDenseMaxSplit;
+    if (nsplit < 1) nsplit = 1;
+    dim3 grid((N + 127) / 128, nsplit);
+    ttd::k_colsum_part<<<grid, 128, 0, st>>>(m, rows, N, nsplit, part);
+    ttg::k_sum_splits<<<(unsigned)((N / 4 + 255) / 256), 256, 0, st>>>(part, nsplit, N, N, out, 0);
+    g_launches += 2;
+    (void)dv;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+int transpose_to(const float *src, float *dst, int rows, int cols, cudaStream_t st) {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    ttg::k_transpose<<<grid, 256, 0, st>>>(src, dst, rows, cols);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
+int64_t ttrnn_dense_rnn_param_count(const ttrnn_dense_desc *desc) {
+    DensePlan dp;
+    if (build_dense_plan(desc, &dp)) return -1;
+    return dp.param_floats;
+}
+
+int ttrnn_dense_rnn_workspace_bytes(const ttrnn_dense_desc *desc, int64_t *saved_bytes, int64_t *scratch_bytes) {
+    DensePlan dp;
+    if (build_dense_plan(desc, &dp)) return 1;
+    if (!saved_bytes || !scratch_bytes) return fail("null output pointer");
+    DenseLayout lo;
+    build_dense_layout(desc, dp, &lo);
+    *saved_bytes = lo.sv_total * 4;
+    *scratch_bytes = lo.s_total * 4;
+    return 0;
+}
+
+int ttrnn_dense_rnn_forward(const ttrnn_dense_desc *d, const float *x, const float *h0, const float *c0, const float *params,
+                            float *out, float *hT, float *cT, void *saved, void *scratch, void *stream) {
+    t_opt = snapshot_options();
+    DensePlan dp;
+    if (build_dense_plan(d, &dp)) return 1;
+    if (!x || !params || !out || !saved || !scratch) return fail("x, params, out, saved and scratch must be non-null");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    DenseLayout lo;
+    build_dense_layout(d, dp, &lo);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long B = d->batch;
+    const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = dp.G, GH = G * H;
+    const bool lstm = d->cell == TTRNN_CELL_LSTM;
+    float *sv = (float *)saved, *sc = (float *)scratch;
+    float *w_ih_hi = sc + lo.s_w, *w_ih_lo = w_ih_hi + lo.wmax, *w_hh_hi = w_ih_lo + lo.wmax, *w_hh_lo = w_hh_hi + lo.wmax;
+    float *wt_ih = w_hh_lo + lo.wmax, *wt_hh = wt_ih + lo.wmax;
+    long long blocks = (B * (long long)H + 255) / 256;
+    if (blocks > (long long)dv.sms * 8) blocks = (long long)dv.sms * 8;
+    for (int l = 0; l < L; ++l) {
+        const DenseLayerOff &o = dp.layer[l];
+        const float *lin = l == 0 ? x : sv + lo.sv_hs + (long long)(l - 1) * lo.BTH;
+        float *lout = l == L - 1 ? out : sv + lo.sv_hs + (long long)l * lo.BTH;
+        float *cs = lstm ? sv + lo.sv_cs + (long long)l * lo.BTH : nullptr;
+        float *ab = sv + lo.sv_a + (long long)l * lo.BTG, *ub = sv + lo.sv_u + (long long)l * lo.BTG;
+        const float *W_ih = params + o.w_ih, *W_hh = params + o.w_hh;
+        const long long nih = (long long)GH * o.nin, nhh = (long long)GH * H;
+        // both operand forms: TF32 hi / lo split of W (tensor cores) and W^T as K x N (FFMA fallback)
+        if (split_tf32(W_ih, w_ih_hi, w_ih_lo, r4(nih), st) || transpose_to(W_ih, wt_ih, GH, o.nin, st)) return 1;
+        if (split_tf32(W_hh, w_hh_hi, w_hh_lo, r4(nhh), st) || transpose_to(W_hh, wt_hh, GH, H, st)) return 1;
+        // a = X W_ih^T (+ b_ih) for every timestep at once
+        if (dense_linear(dv, B * (long long)T, T, lin, (long long)T * o.nin, o.nin, w_ih_hi, w_ih_lo, wt_ih, GH,
+                         o.has_bih ? params + o.b_ih : nullptr, ab, (long long)T * GH, false, st))
+            return 1;
+        for (int t = 0; t < T; ++t) {
+            const float *hp = t == 0 ? h0 : lout + (long long)(t - 1) * H;
+            const long long ldhp = t == 0 ? H : (long long)T * H;
+            // u_t = h_{t-1} W_hh^T + b_hh  (h_{-1} = 0: u_0 = b_hh)
+            if (hp) {
+                if (dense_linear(dv, B, 1, hp, ldhp, H, w_hh_hi, w_hh_lo, wt_hh, GH,
+                                 o.has_bhh ? params + o.b_hh : nullptr, ub + (long long)t * GH, (long long)T * GH, false, st))
+                    return 1;
+            } else {
+                ttd::k_bias_rows<<<(unsigned)blocks, 256, 0, st>>>(o.has_bhh ? params + o.b_hh : nullptr, ub + (long long)t * GH,
+                                                                   (long long)T * GH, B, GH);
+                ++g_launches;
+            }
+            ttd::DenseStepArgs a;
+            memset(&a, 0, sizeof a);
+            a.B = B; a.H = H;
+            a.a = ab + (long long)t * GH; a.lda = (long long)T * GH;
+            a.u = ub + (long long)t * GH; a.ldu = (long long)T * GH;
+            a.h_prev = hp; a.ldhp = ldhp;
+            a.c_prev = t == 0 ? c0 : cs + (long long)(t - 1) * H; a.ldcp = t == 0 ? H : (long long)T * H;
+            a.h = lout + (long long)t * H; a.ldh = (long long)T * H;
+            a.c = lstm ? cs + (long long)t * H : nullptr; a.ldc = (long long)T * H;
+            {
+                KernelTimer tm(TTRNN_K_RNN_FWD, st);
+                if (lstm) ttd::k_dense_cell_fwd<true><<<(unsigned)blocks, 256, 0, st>>>(a);
+                else ttd::k_dense_cell_fwd<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+            }
+            ++g_launches;
+        }
+        CU_CHECK(cudaGetLastError());
+        if (l == L - 1) {
+            if (hT) CU_CHECK(cudaMemcpy2DAsync(hT, (size_t)H * 4, lout + (long long)(T - 1) * H, (size_t)T * H * 4, (size_t)H * 4, B,
+                                               cudaMemcpyDeviceToDevice, st));
+            if (lstm && cT) CU_CHECK(cudaMemcpy2DAsync(cT, (size_t)H * 4, cs + (long long)(T - 1) * H, (size_t)T * H * 4, (size_t)H * 4,
+                                                       B, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    return 0;
+}
+
+int ttrnn_dense_rnn_backward(const ttrnn_dense_desc *d, const float *x, const float *h0, const float *c0, const float *params,
+                             const float *out, void *saved, const float *d_out, const float *d_hT, const float *d_cT,
+                             float *d_params, float *d_x, float *d_h0, float *d_c0, void *scratch, void *stream) {
+    t_opt = snapshot_options();
+    DensePlan dp;
+    if (build_dense_plan(d, &dp)) return 1;
+    if (!x || !params || !out || !saved || !scratch || !d_params) return fail("x, params, out, saved, scratch, d_params must be non-null");
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    DenseLayout lo;
+    build_dense_layout(d, dp, &lo);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long B = d->batch;
+    const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = dp.G, GH = G * H;
+    const bool lstm = d->cell == TTRNN_CELL_LSTM;
+    float *sv = (float *)saved, *sc = (float *)scratch;
+    float *wT_hi = sc + lo.s_w, *wT_lo = wT_hi + lo.wmax, *wT = wT_lo + lo.wmax, *wplain_t = wT + lo.wmax, *dwt = wplain_t + lo.wmax;
+    float *dh_gemm = sc + lo.s_dh, *dhd[2] = {dh_gemm + r4(lo.BH), dh_gemm + 2 * r4(lo.BH)}, *dcc = dh_gemm + 3 * r4(lo.BH);
+    float *part = sc + lo.s_part, *pbias = part + kDenseMaxSplit * lo.wmax, *dbias = pbias + kDenseMaxSplit * r4(GH);
+    long long blocks = (B * (long long)H + 255) / 256;
+    if (blocks > (long long)dv.sms * 8) blocks = (long long)dv.sms * 8;
+    // dW^T (K x GH) = sum over rows of A^T Bm, then transposed into the parameter layout (GH x K); db = column sums of Bm
+    DenseIh D;
+    memset(&D, 0, sizeof D);
+    D.part = part; D.pbias = pbias; D.dwt = dwt; D.dbias = dbias;
+    for (int l = L - 1; l >= 0; --l) {
+        const DenseLayerOff &o = dp.layer[l];
+        const float *lin = l == 0 ? x : sv + lo.sv_hs + (long long)(l - 1) * lo.BTH;
+        const float *lout = l == L - 1 ? out : sv + lo.sv_hs + (long long)l * lo.BTH;
+        const float *cs = lstm ? sv + lo.sv_cs + (long long)l * lo.BTH : nullptr;
+        float *ab = sv + lo.sv_a + (long long)l * lo.BTG, *ub = sv + lo.sv_u + (long long)l * lo.BTG;
+        // gradient wrt this layer's outputs: the caller's d_out for the last layer; for an inner layer the dX of the layer
+        // above, which that layer wrote over its own (by then dead) `u` buffer, packed (B, T, H) at the front
+        const float *dhs = l == L - 1 ? d_out : sv + lo.sv_u + (long long)(l + 1) * lo.BTG;
+        const float *W_ih = params + o.w_ih, *W_hh = params + o.w_hh;
+        const long long nhh = (long long)GH * H;
+        // dh_{t-1} += du_t W_hh : rows GEMM with Bt = W_hh^T (H x GH)
+        if (transpose_to(W_hh, wT, GH, H, st)) return 1;                         // wT = W_hh^T (H x GH)
+        if (split_tf32(wT, wT_hi, wT_lo, r4(nhh), st)) return 1;
+        for (int t = T - 1; t >= 0; --t) {
+            ttd::DenseStepArgs a;
+            memset(&a, 0, sizeof a);
+            a.B = B; a.H = H;
+            a.a = ab + (long long)t * GH; a.lda = (long long)T * GH;
+            a.u = ub + (long long)t * GH; a.ldu = (long long)T * GH;
+            a.h_prev = t == 0 ? h0 : lout + (long long)(t - 1) * H; a.ldhp = t == 0 ? H : (long long)T * H;
+            a.c_prev = t == 0 ? c0 : (lstm ? cs + (long long)(t - 1) * H : nullptr); a.ldcp = t == 0 ? H : (long long)T * H;
+            a.dout = dhs ? dhs + (long long)t * H : nullptr; a.lddo = (long long)T * H;
+            a.first = t == T - 1;
+            a.dh_gemm = a.first ? nullptr : dh_gemm;
+            a.dh_direct = (a.first || lstm) ? nullptr : dhd[(t + 1) & 1];
+            a.dh_T = (a.first && l == L - 1) ? d_hT : nullptr;
+            a.dc_T = (a.first && l == L - 1) ? d_cT : nullptr;
+            a.da = ab + (long long)t * GH; a.ldda = (long long)T * GH;
+            a.du = ub + (long long)t * GH; a.lddu = (long long)T * GH;
+            a.dh_direct_out = dhd[t & 1];
+            a.dc = dcc;
+            {
+                KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                if (lstm) ttd::k_dense_cell_bwd<true><<<(unsigned)blocks, 256, 0, st>>>(a);
+                else ttd::k_dense_cell_bwd<false><<<(unsigned)blocks, 256, 0, st>>>(a);
+            }
+            ++g_launches;
+            if (t > 0 || (d_h0 && h0)) {
+                // dh_gemm = du_t W_hh
+                if (dense_linear(dv, B, 1, ub + (long long)t * GH, (long long)T * GH, GH, wT_hi, wT_lo, W_hh, H, nullptr,
+                                 dh_gemm, H, true, st))
+                    return 1;
+            }
+        }
+        CU_CHECK(cudaGetLastError());
+        // gradient wrt the shared initial state: sum over layers
+        if (d_h0 && h0) {
+            ttd::k_add2<<<(unsigned)blocks, 256, 0, st>>>(dh_gemm, lstm ? nullptr : dhd[0], sc + lo.s_dh + 4 * r4(lo.BH), lo.BH);
+            ++g_launches;
+            if (axpy1(sc + lo.s_dh + 4 * r4(lo.BH), d_h0, lo.BH, l != L - 1, st)) return 1;
+        }
+        if (lstm && d_c0 && c0 && axpy1(dcc, d_c0, lo.BH, l != L - 1, st)) return 1;
+        // dW_hh^T (H x GH) = sum_t h_{t-1}^T du_t ; db_hh = column sums of du (all T steps)
+        {
+            bool acc = false;
+            if (T > 1) {
+                if (dense_dw(dv, B * (long long)(T - 1), T - 1, lout, (long long)T * H, H, ub + GH, (long long)T * GH, GH, D, false, false, st))
+                    return 1;
+                acc = true;
+            }
+            if (h0) {
+                if (dense_dw(dv, B, 1, h0, H, H, ub, (long long)T * GH, GH, D, acc, false, st)) return 1;
+                acc = true;
+            }
+            if (acc) {
+                if (transpose_to(dwt, d_params + o.w_hh, H, GH, st)) return 1;
+            } else {
+                CU_CHECK(cudaMemsetAsync(d_params + o.w_hh, 0, (size_t)nhh * 4, st));
+            }
+            if (o.has_bhh && dense_colsum(dv, ub, B * (long long)T, GH, part, d_params + o.b_hh, st)) return 1;
+        }
+        // dW_ih^T (I x GH) = X^T da ; db_ih = column sums of da
+        if (dense_dw(dv, B * (long long)T, T, lin, (long long)T * o.nin, o.nin, ab, (long long)T * GH, GH, D, false, false, st)) return 1;
+        if (transpose_to(dwt, d_params + o.w_ih, o.nin, GH, st)) return 1;
+        if (o.has_bih && dense_colsum(dv, ab, B * (long long)T, GH, part, d_params + o.b_ih, st)) return 1;
+        // dX = da W_ih (B, T, I): for l > 0 it is the upstream gradient of the layer below, written over this layer's dead
+        // `u` buffer (packed (B, T, H) at its front); for l == 0 into the caller's d_x (if requested)
+        float *dxl = l == 0 ? d_x : ub;
+        if (dxl) {
+            if (o.nin % 128 != 0)
+                return fail("dense cells: the gradient wrt the input needs input_size %% 128 == 0 (got %d)", o.nin);
+            if (transpose_to(W_ih, wT, GH, o.nin, st)) return 1;                // wT = W_ih^T (I x GH)
+            if (split_tf32(wT, wT_hi, wT_lo, r4((long long)GH * o.nin), st)) return 1;
+            if (dense_linear(dv, B * (long long)T, T, ab, (long long)T * GH, GH, wT_hi, wT_lo, W_ih, o.nin, nullptr, dxl,
+                             (long long)T * o.nin, true, st))
+                return 1;
+        }
+    }
     return 0;
 }
 
