@@ -151,7 +151,7 @@ int ttrnn_cell_backward(int32_t cell, int64_t B, int32_t H, const float *a, cons
  * -- the reference's state_dict order cell{l}.input_weights.weight [.bias], cell{l}.hidden_weights.weight [.bias]
  * (the dense LSTMCell gives its input map no bias, lstm.py:17-18).  The ih projection, dX and both weight gradients are
  * batched over the whole sequence as tensor-core GEMMs; the recurrence is one GEMM + one fused gate kernel per step.
- * hidden_size must be a multiple of 32 with G*H a multiple of 128. */
+ * hidden_size must be a multiple of 128 (GEMM tile width); d_x needs input_size % 128 == 0. */
 typedef struct ttrnn_dense_desc {
     int32_t cell, num_layers, input_size, hidden_size, has_bias, seq_len;
     int64_t batch;

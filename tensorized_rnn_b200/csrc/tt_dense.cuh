@@ -141,6 +141,38 @@ __global__ void __launch_bounds__(128) k_colsum_part(const float *__restrict__ m
     part[(long long)s * N + n] = (a0 + a1) + (a2 + a3);
 }
 
+// Input widths that are not a multiple of 4 (pixel-by-pixel MNIST: input_size = 1) cannot go through the float4 GEMM
+// loaders; the projection is then a handful of multiply-adds per output and runs on these plain kernels.
+// y[r, n] = sum_k x[r, k] W[n, k] (+ bias[n]);  x rows contiguous (rows x K), y rows contiguous (rows x N)
+__global__ void __launch_bounds__(256) k_smallk_fwd(const float *__restrict__ x, const float *__restrict__ W,
+                                                    const float *__restrict__ bias, float *__restrict__ y, long long rows, int K,
+                                                    int N) {
+    const long long n_el = rows * N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n_el; e += (long long)gridDim.x * blockDim.x) {
+        const long long r = e / N;
+        const int n = (int)(e - r * N);
+        float t = bias ? bias[n] : 0.f;
+        for (int k = 0; k < K; ++k) t += x[r * K + k] * __ldg(W + (long long)n * K + k);
+        y[e] = t;
+    }
+}
+// part[s][n, k] = sum over the rows of split s of da[r, n] x[r, k]   (grid: ceil(N / 128) x nsplit x K)
+__global__ void __launch_bounds__(128) k_smallk_dw_part(const float *__restrict__ da, const float *__restrict__ x, long long rows,
+                                                        int N, int K, int nsplit, float *__restrict__ part) {
+    const int n = blockIdx.x * 128 + threadIdx.x, s = blockIdx.y, k = blockIdx.z;
+    if (n >= N) return;
+    const long long per = (rows + nsplit - 1) / nsplit;
+    const long long r0 = s * per, r1 = (r0 + per < rows) ? r0 + per : rows;
+    float a0 = 0.f, a1 = 0.f;
+    long long r = r0;
+    for (; r + 1 < r1; r += 2) {
+        a0 += da[r * N + n] * x[r * K + k];
+        a1 += da[(r + 1) * N + n] * x[(r + 1) * K + k];
+    }
+    if (r < r1) a0 += da[r * N + n] * x[r * K + k];
+    part[((long long)s * N + n) * K + k] = a0 + a1;
+}
+
 // out[e] = a[e] + (b ? b[e] : 0)
 __global__ void __launch_bounds__(256) k_add2(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ out,
                                               long long n) {

@@ -1539,8 +1539,8 @@ int build_dense_plan(const ttrnn_dense_desc *d, DensePlan *dp) {
     if (d->cell != TTRNN_CELL_LSTM && d->cell != TTRNN_CELL_GRU) return fail("unknown cell kind %d", d->cell);
     if (d->num_layers < 1 || d->num_layers > TTRNN_MAX_LAYERS) return fail("num_layers %d out of range", d->num_layers);
     if (d->input_size < 1 || d->hidden_size < 1 || d->batch < 1 || d->seq_len < 1) return fail("sizes must be positive");
-    if (d->hidden_size % 32 != 0 || (gates_of(d->cell) * d->hidden_size) % 128 != 0)
-        return fail("dense cells: hidden_size must be a multiple of 32 with G*H a multiple of 128 (got %d)", d->hidden_size);
+    if (d->hidden_size % 128 != 0)
+        return fail("dense cells: hidden_size must be a multiple of 128 (the GEMM tiles are 128 columns wide), got %d", d->hidden_size);
     dp->G = gates_of(d->cell);
     const long long GH = (long long)dp->G * d->hidden_size;
     long long off = 0;
@@ -1654,10 +1654,15 @@ int ttrnn_dense_rnn_forward(const ttrnn_dense_desc *d, const float *x, const flo
         const float *W_ih = params + o.w_ih, *W_hh = params + o.w_hh;
         const long long nih = (long long)GH * o.nin, nhh = (long long)GH * H;
         // both operand forms: TF32 hi / lo split of W (tensor cores) and W^T as K x N (FFMA fallback)
-        if (split_tf32(W_ih, w_ih_hi, w_ih_lo, r4(nih), st) || transpose_to(W_ih, wt_ih, GH, o.nin, st)) return 1;
+        if (o.nin % 4 == 0 && (split_tf32(W_ih, w_ih_hi, w_ih_lo, r4(nih), st) || transpose_to(W_ih, wt_ih, GH, o.nin, st))) return 1;
         if (split_tf32(W_hh, w_hh_hi, w_hh_lo, r4(nhh), st) || transpose_to(W_hh, wt_hh, GH, H, st)) return 1;
         // a = X W_ih^T (+ b_ih) for every timestep at once
-        if (dense_linear(dv, B * (long long)T, T, lin, (long long)T * o.nin, o.nin, w_ih_hi, w_ih_lo, wt_ih, GH,
+        if (o.nin % 4 != 0) {
+            long long gb = (B * (long long)T * GH + 255) / 256;
+            if (gb > (long long)dv.sms * 16) gb = (long long)dv.sms * 16;
+            ttd::k_smallk_fwd<<<(unsigned)gb, 256, 0, st>>>(lin, W_ih, o.has_bih ? params + o.b_ih : nullptr, ab, B * (long long)T, o.nin, GH);
+            ++g_launches;
+        } else if (dense_linear(dv, B * (long long)T, T, lin, (long long)T * o.nin, o.nin, w_ih_hi, w_ih_lo, wt_ih, GH,
                          o.has_bih ? params + o.b_ih : nullptr, ab, (long long)T * GH, false, st))
             return 1;
         for (int t = 0; t < T; ++t) {
@@ -1798,8 +1803,22 @@ int ttrnn_dense_rnn_backward(const ttrnn_dense_desc *d, const float *x, const fl
             if (o.has_bhh && dense_colsum(dv, ub, B * (long long)T, GH, part, d_params + o.b_hh, st)) return 1;
         }
         // dW_ih^T (I x GH) = X^T da ; db_ih = column sums of da
-        if (dense_dw(dv, B * (long long)T, T, lin, (long long)T * o.nin, o.nin, ab, (long long)T * GH, GH, D, false, false, st)) return 1;
-        if (transpose_to(dwt, d_params + o.w_ih, o.nin, GH, st)) return 1;
+        if (o.nin % 4 != 0) {
+            const long long rows = B * (long long)T;
+            int nsplit = (int)((rows + 511) / 512);
+            if (nsplit > kDenseMaxSplit) nsplit = kDenseMaxSplit;
+            if ((long long)nsplit * GH * o.nin > kDenseMaxSplit * lo.wmax) return fail("dense cells: input_size %d unsupported", o.nin);
+            dim3 grid((GH + 127) / 128, nsplit, o.nin);
+            ttd::k_smallk_dw_part<<<grid, 128, 0, st>>>(ab, lin, rows, GH, o.nin, nsplit, part);
+            const long long wn = r4((long long)GH * o.nin);
+            if (((long long)GH * o.nin) % 4 != 0) return fail("dense cells: G*H*input_size must be a multiple of 4");
+            ttg::k_sum_splits<<<(unsigned)((wn / 4 + 255) / 256), 256, 0, st>>>(part, nsplit, (long long)GH * o.nin, (long long)GH * o.nin,
+                                                                                 d_params + o.w_ih, 0);
+            g_launches += 2;
+        } else {
+            if (dense_dw(dv, B * (long long)T, T, lin, (long long)T * o.nin, o.nin, ab, (long long)T * GH, GH, D, false, false, st)) return 1;
+            if (transpose_to(dwt, d_params + o.w_ih, o.nin, GH, st)) return 1;
+        }
         if (o.has_bih && dense_colsum(dv, ab, B * (long long)T, GH, part, d_params + o.b_ih, st)) return 1;
         // dX = da W_ih (B, T, I): for l > 0 it is the upstream gradient of the layer below, written over this layer's dead
         // `u` buffer (packed (B, T, H) at its front); for l == 0 into the caller's d_x (if requested)

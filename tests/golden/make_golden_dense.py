@@ -17,11 +17,11 @@ from tensorized_rnn.lstm import LSTM    # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CASES = [
-    # name, cell, I, H, L, bias, B, T, with_init, want_dx   (engine limits: H % 32 == 0 and G*H % 128 == 0, so GRU needs
-    # H % 128 == 0; the gradient wrt the input needs input_size % 128 == 0)
-    ("dense_lstm_i40_h64_L2", "lstm", 40, 64, 2, True, 5, 9, False, False),
-    ("dense_lstm_i128_h32_L1_init_dx", "lstm", 128, 32, 1, True, 4, 7, True, True),
-    ("dense_lstm_nobias_L3", "lstm", 28, 32, 3, False, 3, 6, True, False),
+    # name, cell, I, H, L, bias, B, T, with_init, want_dx   (engine limits: hidden_size % 128 == 0; the gradient wrt the
+    # input needs input_size % 128 == 0)
+    ("dense_lstm_i40_h128_L2", "lstm", 40, 128, 2, True, 5, 9, False, False),
+    ("dense_lstm_i128_h128_L1_init_dx", "lstm", 128, 128, 1, True, 4, 7, True, True),
+    ("dense_lstm_nobias_i28_L2", "lstm", 28, 128, 2, False, 3, 6, True, False),
     ("dense_gru_i40_h128_L1", "gru", 40, 128, 1, True, 5, 9, False, False),
     ("dense_gru_i128_h128_L2_init_dx", "gru", 128, 128, 2, True, 4, 8, True, True),
     ("dense_gru_nobias", "gru", 1, 128, 1, False, 6, 20, False, False),

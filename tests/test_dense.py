@@ -79,7 +79,7 @@ def test_module_mirror_state_dict_contract(name):
 def test_dense_rejects_log_grads():
     import tensorized_rnn_b200 as tr
     with pytest.raises(NotImplementedError):
-        tr.LSTM(8, 32, 1, torch.device("cpu"), log_grads=True)
+        tr.LSTM(8, 128, 1, torch.device("cpu"), log_grads=True)
 
 
 def _gpu_case(cell, I, H, L, bias, x, init, w_out, w_h, sd, want_dx):
