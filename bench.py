@@ -57,11 +57,15 @@ CONFIGS = {
     # secondary point SURVEY.md 8(a) asks for: the reference's own default GE2E model (params_model.py: d2, r2)
     6: dict(name="cfg3-alt GE2E speaker encoder 3xTT-LSTM d2 r2 (params_model.py defaults)", cell="lstm", I=40, H=256, L=3,
             d=2, r=2, B=640, T=160, mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
+    # dense baseline of cfg3 through the same engine (SpeakerEncoder(compression=None), speaker_encoder.py:29-36): the paper's
+    # dense-vs-TT comparison on one device path
+    7: dict(name="cfg3-dense GE2E speaker encoder 3xLSTM (dense baseline)", cell="lstm", I=40, H=256, L=3, d=0, r=0, B=640, T=160,
+            mode="fwd+bwd", grad="hT", inp="uniform", seed=11, dense=True),
 }
 # per-config caps on (warmup, steps): cfg5 moves ~100 GB per step
 STEP_CAP = {5: (3, 3), 4: (3, 5)}
 # CPU sample (batch, T) per config for the in-line cpu_baseline: about 5-15 s of CPU work each
-CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160)}
+CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160), 7: (96, 160)}
 KINDS = ["k_ttlinear_fwd", "k_rnn_fwd", "k_rnn_bwd", "k_ttlinear_bwd", "gemm_ih_fwd", "gemm_dx", "gemm_dw"]
 
 
@@ -81,6 +85,11 @@ def algorithmic_flops(cfg):
     from tensorized_rnn_b200.shapes import tt_shape
     G = 4 if cfg["cell"] == "lstm" else 3
     H, d, r = cfg["H"], cfg["d"], cfg["r"]
+    if cfg.get("dense"):
+        hh = 2 * G * H * H
+        ih = [2 * G * H * (cfg["I"] if l == 0 else H) for l in range(cfg["L"])]
+        gate = 2 * G * H + 12 * H
+        return sum(ih) + cfg["L"] * (hh + gate), hh, ih, gate
     ranks = [1] + [r] * (d - 1) + [1]
     hh = chain_flops(*tt_shape(H, H, d, G), ranks)
     ih = [chain_flops(*tt_shape(cfg["I"] if l == 0 else H, H, d, G), ranks) for l in range(cfg["L"])]
@@ -202,6 +211,8 @@ def run_cpu_oracle(cfg, B, T, steps, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
     c = dict(cfg)
     c["T"] = T
+    if cfg.get("dense"):
+        return run_cpu_dense_oracle(c, B, T, steps, warmup)
     layers = oracle.random_layers(cfg["cell"], cfg["I"], cfg["H"], cfg["L"], cfg["d"], cfg["r"], bias=True,
                                   seed=cfg["seed"], requires_grad=(cfg["mode"] != "fwd"))
     x = make_input(c, B)
@@ -226,6 +237,31 @@ def run_cpu_oracle(cfg, B, T, steps, warmup):
                 gd = torch.Generator().manual_seed(5)
                 loss = (out * torch.rand(out.shape, generator=gd)).sum()
             loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return B * T / sec, sec
+
+
+def run_cpu_dense_oracle(cfg, B, T, steps, warmup):
+    import dense_oracle                                # bench: cpu_baseline leg only
+    import tensorized_rnn_b200 as tr
+    torch.manual_seed(cfg["seed"])
+    m = (tr.LSTM if cfg["cell"] == "lstm" else tr.GRU)(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu"))
+    layers = dense_oracle.layers_from_state_dict(m.state_dict(), cfg["L"], requires_grad=(cfg["mode"] != "fwd"))
+    x = make_input(cfg, B)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in dense_oracle.flat_params(layers):
+            p.grad = None
+        if cfg["cell"] == "lstm":
+            out, (h, _) = dense_oracle.lstm_forward(layers, x)
+        else:
+            out, h = dense_oracle.gru_forward(layers, x)
+        if cfg["mode"] != "fwd":
+            upstream(cfg, out, h).backward()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
@@ -284,9 +320,13 @@ class GpuBench(object):
         from tensorized_rnn_b200.dist import allreduce_gradients
         lib, dev, dist = self.lib, self.dev, self.dist
         torch.manual_seed(cfg["seed"])
-        cls = self.tr.TTLSTM if cfg["cell"] == "lstm" else self.tr.TTGRU
-        with redirect_stdout(io.StringIO()):
-            model = cls(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu"), n_cores=cfg["d"], tt_rank=cfg["r"]).to(dev)
+        dense = bool(cfg.get("dense"))
+        if dense:
+            model = (self.tr.LSTM if cfg["cell"] == "lstm" else self.tr.GRU)(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu")).to(dev)
+        else:
+            cls = self.tr.TTLSTM if cfg["cell"] == "lstm" else self.tr.TTGRU
+            with redirect_stdout(io.StringIO()):
+                model = cls(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu"), n_cores=cfg["d"], tt_rank=cfg["r"]).to(dev)
         params = [p for p in model.parameters()]
         B, T, H = B_rank, cfg["T"], cfg["H"]
         c_rank = dict(cfg)
@@ -371,7 +411,11 @@ class GpuBench(object):
             units = B * T * world * steps
             fwd_flops, hh_flops, ih_list, gate = algorithmic_flops(cfg)
             mult = 3 if train else 1
-            plan = self._lib.describe_plan(model.spec().desc(B, T), training=train)
+            if dense:
+                plan = [{"path": "dense cells: batched tensor-core GEMMs + one step GEMM and one gate kernel per timestep"}]
+                plan += [{"layer": l, "ih_route": "dense", "hh_dw": "dense_cell"} for l in range(cfg["L"])]
+            else:
+                plan = self._lib.describe_plan(model.spec().desc(B, T), training=train)
             layers = plan[1:]
             kern = {KINDS[i]: {"ms_per_step": kms[i] / steps, "launches_per_step": kcnt[i] / steps} for i in range(nk)}
             # algorithmic FLOPs credited to each kernel group per sequence-step (reference chain order; recomputed
@@ -395,6 +439,15 @@ class GpuBench(object):
                     cred["k_ttlinear_fwd"] += ihf
                     if train:
                         cred["k_ttlinear_bwd"] += 2 * ihf
+                if lay.get("hh_dw") == "dense_cell":
+                    # dense cells: the step GEMMs are timed with the ih projection (gemm_ih_fwd / gemm_dx), gates in k_rnn_*
+                    cred["gemm_ih_fwd"] += hh_flops
+                    cred["k_rnn_fwd"] += gate
+                    if train:
+                        cred["gemm_dx"] += hh_flops
+                        cred["gemm_dw"] += hh_flops
+                        cred["k_rnn_bwd"] += 2 * gate
+                    continue
                 cred["k_rnn_fwd"] += hh_flops + gate
                 if train:
                     if lay.get("hh_dw") == "dense":
@@ -450,7 +503,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--headline", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--config", type=int, default=0, help="shorthand: headline = this config and run only it")
-    ap.add_argument("--configs", default="1,2,3,4,5,6", help="configs measured into all_configs")
+    ap.add_argument("--configs", default="1,2,3,4,5,6,7", help="configs measured into all_configs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of the headline config (profiling)")
     ap.add_argument("--seq-len", type=int, default=0, help="override T of the headline config (profiling only)")

@@ -219,7 +219,7 @@ int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K
 int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row,
                        int64_t *dense_macs_per_row);
 
-/* Execution plan of `desc` under the current options, as text: first line "chunk_steps=.. sms=.. tc_gemm=..", then one
+/* Execution plan of `desc` under the current options, as text: first line "chunk_steps=.. sms=.. tc_gemm=.. rank_padded=..", then one
  * line per layer of key=value pairs (ih_route, ih_fwd_tc / ih_dw_tc = tensor-core GEMMs used, fwd_kernel, fwd_rows =
  * batch rows per CTA, save_mode, and with training != 0: bwd_kernel, bwd_rows, bwd_phase_rows, optional second phase,
  * hh_dw, hh_dw_tc).  Needs a CUDA device (the plan depends on its SM count).  Returns characters written, < 0 on error. */
@@ -249,6 +249,9 @@ int ttrnn_static_kernel_table(char *buf, int32_t cap);
  *                   accumulation dW_hh^T = H_prev^T delta + projection onto the cores (default 1)
  *   "dense_ih"      0 = never take the dense route of the ih projection (default 1)
  *   "dense_ih_ratio" dense route allowed while I*G*H * 100 <= chain multiply-adds * ratio (default 130)
+ *   "rank_pad"      1 (default) = a stack whose inner TT ranks are not multiples of 4 runs on the statically specialised
+ *                   kernels with zero-padded cores when every padded hh chain has one registered (e.g. the reference's GE2E
+ *                   default n_cores 2 / rank 2); 0 = runtime-shape kernels
  *   "tc_gemm"       1 (default) = the dense-route GEMMs run on the tensor cores (tcgen05.mma kind::tf32, error-compensated
  *                   3xTF32 split, TMA-staged operands, TMEM accumulators) where the shape fits; 0 = FP32 FFMA kernels
  *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of

@@ -108,7 +108,8 @@ def load() -> C.CDLL:
                      ("dense_ih", "TTRNN_DENSE_IH"), ("dense_ih_ratio", "TTRNN_DENSE_IH_RATIO"),
                      ("save_bytes", "TTRNN_SAVE_BYTES"), ("save_u_bytes", "TTRNN_SAVE_U_BYTES"),
                      ("row_plan", "TTRNN_ROW_PLAN"), ("gemm_wide", "TTRNN_GEMM_WIDE"), ("split_kept", "TTRNN_SPLIT_KEPT"),
-                     ("dense_hh_dw", "TTRNN_DENSE_HH_DW"), ("tc_gemm", "TTRNN_TC_GEMM")):
+                     ("dense_hh_dw", "TTRNN_DENSE_HH_DW"), ("tc_gemm", "TTRNN_TC_GEMM"),
+                     ("rank_pad", "TTRNN_RANK_PAD")):
         if os.environ.get(env):
             lib.ttrnn_set_option(key.encode(), int(os.environ[env]))
     _lib = lib

@@ -50,6 +50,8 @@ std::atomic<long long> g_opt_split_kept{1};    // kept gates: prefer the dX-only
 std::atomic<long long> g_opt_dense_ratio{130};
 // dense-route GEMMs on the tensor cores (tt_tc.cuh: tcgen05 3xTF32, TMA-staged) where the shape fits; 0 = FP32 FFMA kernels
 std::atomic<long long> g_opt_tc_gemm{1};
+// zero-pad TT ranks that are not multiples of 4 so that the static kernels apply (make_eff_desc); 0 = runtime-shape kernels
+std::atomic<long long> g_opt_rank_pad{1};
 
 // Snapshot of every option that decides a buffer layout or a kernel route.  ttrnn_rnn_workspace_bytes() takes it from the
 // process-wide options and stamps it into ttrnn_rnn_workspace.plan; forward and backward run from THAT copy, so a
@@ -57,7 +59,7 @@ std::atomic<long long> g_opt_tc_gemm{1};
 // the scratch buffers are interpreted.  Helpers read the calling thread's current snapshot `t_opt`.
 struct Opts {
     long long rows, chunk, chunk_bytes, stat, srows_fwd, srows_bwd, save_bytes, save_u_bytes, row_plan, dense_ih, gemm_wide,
-        dense_hh, split_kept, dense_ratio, tc_gemm;
+        dense_hh, split_kept, dense_ratio, tc_gemm, rank_pad;
 };
 constexpr int kOptFields = sizeof(Opts) / sizeof(long long);
 constexpr long long kPlanMagic = 0x7474726E6E706C33LL;          // "ttrnnpl3"
@@ -71,6 +73,7 @@ Opts snapshot_options() {
     o.save_bytes = g_opt_save_bytes.load(); o.save_u_bytes = g_opt_save_u_bytes.load(); o.row_plan = g_opt_row_plan.load();
     o.dense_ih = g_opt_dense_ih.load(); o.gemm_wide = g_opt_gemm_wide.load(); o.dense_hh = g_opt_dense_hh.load();
     o.split_kept = g_opt_split_kept.load(); o.dense_ratio = g_opt_dense_ratio.load(); o.tc_gemm = g_opt_tc_gemm.load();
+    o.rank_pad = g_opt_rank_pad.load();
     return o;
 }
 void plan_store(const Opts &o, int64_t *plan) {
@@ -301,6 +304,101 @@ int build_rnn_plan(const ttrnn_rnn_desc *d, RnnPlan *rp) {
         lp.off_hh_bias = off;  if (d->has_bias) off += GH;
     }
     rp->param_floats = off;
+    return 0;
+}
+
+// ---- rank padding -----------------------------------------------------------------------------------------------
+// The statically specialised kernels need inner TT ranks that are multiples of 4 (tt_static.cuh).  A chain whose ranks
+// are not (the reference's own GE2E default is n_cores = 2, rank = 2: encoder/params_model.py:15-16) is mathematically
+// identical to the chain with every inner rank rounded up and the cores zero-padded along their rank axes.  When ALL
+// hh chains of the padded stack have a registered static kernel, the call runs on the padded descriptor: the parameter
+// blob is expanded into scratch by k_pad_cores, and the backward cuts the real gradient block out of the padded one.
+// The padded chain executes more multiply-adds (r = 2 -> 4: 2x on the rank-bound stages), but on kernels that are
+// 5-10x faster than the runtime-shape fallback.
+constexpr int kMaxPadEntries = TTRNN_MAX_LAYERS * 2 * (TTRNN_MAX_CORES + 1);
+struct PadEntry { int src, dst, r, mid, rn, rnp; };       // core (r, mid, rn) at src -> (rp, mid, rnp) at dst (floats)
+struct PadTable { int n; PadEntry e[kMaxPadEntries]; };
+
+__global__ void __launch_bounds__(256) k_pad_cores(const __grid_constant__ PadTable t, const float *__restrict__ src,
+                                                   float *__restrict__ dst, int rp_dummy) {
+    const PadEntry en = t.e[blockIdx.x];
+    (void)rp_dummy;
+    // destination core is (rp, mid, rnp) with rp implied by the next entry's offset: iterate over the SOURCE extents and
+    // zero-fill is done by the memset the host issues before this kernel
+    const int n = en.r * en.mid * en.rn;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int b = i % en.rn, m = (i / en.rn) % en.mid, a = i / (en.rn * en.mid);
+        dst[en.dst + (a * en.mid + m) * en.rnp + b] = src[en.src + i];
+    }
+}
+__global__ void __launch_bounds__(256) k_unpad_cores(const __grid_constant__ PadTable t, const float *__restrict__ padded,
+                                                     float *__restrict__ real) {
+    const PadEntry en = t.e[blockIdx.x];
+    const int n = en.r * en.mid * en.rn;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const int b = i % en.rn, m = (i / en.rn) % en.mid, a = i / (en.rn * en.mid);
+        real[en.src + i] = padded[en.dst + (a * en.mid + m) * en.rnp + b];
+    }
+}
+
+struct EffDesc {
+    ttrnn_rnn_desc d;          // descriptor the kernels run on (padded ranks when `padded`)
+    bool padded = false;
+    PadTable tab;
+    long long pad_floats = 0;  // floats of the padded parameter blob
+};
+
+int make_eff_desc(const ttrnn_rnn_desc *d, const DevInfo *dv, EffDesc *e) {
+    e->d = *d;
+    e->padded = false;
+    e->pad_floats = 0;
+    e->tab.n = 0;
+    if (!t_opt.stat || !t_opt.rank_pad || !dv) return 0;
+    RnnPlan real;
+    if (build_rnn_plan(d, &real)) return 1;
+    bool any = false;
+    ttrnn_rnn_desc p = *d;
+    for (int l = 0; l < d->num_layers; ++l)
+        for (int side = 0; side < 2; ++side) {
+            ttrnn_tt_shape &sh = side ? p.hh[l] : p.ih[l];
+            for (int k = 1; k < sh.d; ++k) {
+                const int rp = (sh.ranks[k] + 3) & ~3;
+                if (rp != sh.ranks[k]) { sh.ranks[k] = rp; any = true; }
+            }
+        }
+    if (!any) return 0;
+    for (int l = 0; l < d->num_layers; ++l) {
+        const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
+        if (!tts_find_rnn_fwd(&p.hh[l], d->cell, mode, d->batch, dv->sms, 0)) return 0;     // padding would not reach a static kernel
+    }
+    RnnPlan pad;
+    if (build_rnn_plan(&p, &pad)) return 0;
+    const int GH = real.G * d->hidden_size;
+    PadTable &t = e->tab;
+    for (int l = 0; l < d->num_layers; ++l)
+        for (int side = 0; side < 2; ++side) {
+            const ttrnn_tt_shape &sr = side ? d->hh[l] : d->ih[l], &sp = side ? p.hh[l] : p.ih[l];
+            long long so = side ? real.layer[l].off_hh_cores : real.layer[l].off_ih_cores;
+            long long po = side ? pad.layer[l].off_hh_cores : pad.layer[l].off_ih_cores;
+            for (int k = 0; k < sr.d; ++k) {
+                PadEntry en;
+                en.src = (int)so; en.dst = (int)po;
+                en.r = sr.ranks[k]; en.mid = sr.out_modes[k] * sr.in_modes[k]; en.rn = sr.ranks[k + 1]; en.rnp = sp.ranks[k + 1];
+                t.e[t.n++] = en;
+                so += (long long)sr.ranks[k] * en.mid * sr.ranks[k + 1];
+                po += (long long)sp.ranks[k] * en.mid * sp.ranks[k + 1];
+            }
+            if (d->has_bias) {
+                PadEntry en;
+                en.src = (int)(side ? real.layer[l].off_hh_bias : real.layer[l].off_ih_bias);
+                en.dst = (int)(side ? pad.layer[l].off_hh_bias : pad.layer[l].off_ih_bias);
+                en.r = 1; en.mid = GH; en.rn = 1; en.rnp = 1;
+                t.e[t.n++] = en;
+            }
+        }
+    e->d = p;
+    e->padded = true;
+    e->pad_floats = r4(pad.param_floats);
     return 0;
 }
 
@@ -790,6 +888,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "dense_ih")) { g_opt_dense_ih.store(value); return 0; }
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
     if (!strcmp(key, "tc_gemm")) { g_opt_tc_gemm.store(value); return 0; }
+    if (!strcmp(key, "rank_pad")) { g_opt_rank_pad.store(value); return 0; }
     return 1;
 }
 
@@ -816,13 +915,17 @@ int64_t ttrnn_tc_launch_count(int32_t reset) {
     return v;
 }
 
-int ttrnn_rnn_describe(const ttrnn_rnn_desc *d, int32_t training, char *buf, int32_t cap) {
+int ttrnn_rnn_describe(const ttrnn_rnn_desc *d_in, int32_t training, char *buf, int32_t cap) {
     if (!buf || cap < 1) return -1;
     t_opt = snapshot_options();
     RnnPlan rp;
-    if (build_rnn_plan(d, &rp)) return -1;
+    if (build_rnn_plan(d_in, &rp)) return -1;
     DevInfo dv;
     if (get_dev(&dv)) return -1;
+    EffDesc eff;
+    if (make_eff_desc(d_in, &dv, &eff)) return -1;
+    const ttrnn_rnn_desc *d = &eff.d;
+    if (eff.padded && build_rnn_plan(d, &rp)) return -1;
     RnnLayout lo;
     if (build_layout(d, rp, dv, &lo)) return -1;
     const long long B = d->batch;
@@ -842,7 +945,7 @@ int ttrnn_rnn_describe(const ttrnn_rnn_desc *d, int32_t training, char *buf, int
             if (c == ' ') c = '_';
         return t;
     };
-    put("chunk_steps=%d sms=%d tc_gemm=%lld\n", lo.Tc, dv.sms, t_opt.tc_gemm);
+    put("chunk_steps=%d sms=%d tc_gemm=%lld rank_padded=%d\n", lo.Tc, dv.sms, t_opt.tc_gemm, (int)eff.padded);
     for (int l = 0; l < d->num_layers; ++l) {
         const LayerPlan &lp = rp.layer[l];
         const bool rank1 = (l == 0 && d->input_size == 1);
@@ -896,32 +999,49 @@ int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *w
     if (build_rnn_plan(desc, &rp)) return 1;
     DevInfo dv;
     if (get_dev(&dv)) return 1;
+    EffDesc eff;
+    if (make_eff_desc(desc, &dv, &eff)) return 1;
+    if (eff.padded && build_rnn_plan(&eff.d, &rp)) return 1;
     RnnLayout lo;
-    if (build_layout(desc, rp, dv, &lo)) return 1;
+    if (build_layout(&eff.d, rp, dv, &lo)) return 1;
     ws->saved_bytes = lo.sv_total * 4;
-    ws->fwd_scratch_bytes = lo.f_total * 4;
-    ws->bwd_scratch_bytes = lo.b_total * 4;
+    ws->fwd_scratch_bytes = (lo.f_total + eff.pad_floats) * 4;             // + the rank-padded parameter blob
+    ws->bwd_scratch_bytes = (lo.b_total + 2 * eff.pad_floats) * 4;         // + padded parameters and padded gradients
     memset(ws->plan, 0, sizeof ws->plan);
     plan_store(t_opt, ws->plan);
     return 0;
 }
 
-int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
-                      const float *c0, const float *params, float *out, float *hT, float *cT, void *saved, void *scratch,
+int ttrnn_rnn_forward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                      const float *c0, const float *params_in, float *out, float *hT, float *cT, void *saved, void *scratch,
                       void *stream) {
     if (!ws || !plan_load(ws->plan, &t_opt))
         return fail("ttrnn_rnn_forward: `ws` must be the struct filled by ttrnn_rnn_workspace_bytes() for this descriptor");
     RnnPlan rp;
-    if (build_rnn_plan(d, &rp)) return 1;
-    if (!x || !params || !out || !scratch) return fail("x, params, out and scratch must be non-null");
+    if (build_rnn_plan(d_in, &rp)) return 1;
+    if (!x || !params_in || !out || !scratch) return fail("x, params, out and scratch must be non-null");
     DevInfo dv;
     if (get_dev(&dv)) return 1;
+    EffDesc eff;
+    if (make_eff_desc(d_in, &dv, &eff)) return 1;
+    const ttrnn_rnn_desc *d = &eff.d;
+    if (eff.padded && build_rnn_plan(d, &rp)) return 1;
     RnnLayout lo;
     if (build_layout(d, rp, dv, &lo)) return 1;
-    if (lo.f_total * 4 != ws->fwd_scratch_bytes || lo.sv_total * 4 != ws->saved_bytes)
+    if ((lo.f_total + eff.pad_floats) * 4 != ws->fwd_scratch_bytes || lo.sv_total * 4 != ws->saved_bytes)
         return fail("ttrnn_rnn_forward: workspace struct does not belong to this descriptor (scratch %lld vs %lld bytes)",
-                    (long long)lo.f_total * 4, (long long)ws->fwd_scratch_bytes);
+                    (long long)(lo.f_total + eff.pad_floats) * 4, (long long)ws->fwd_scratch_bytes);
     cudaStream_t st = (cudaStream_t)stream;
+    const float *params = params_in;
+    if (eff.padded) {
+        // rank-padded copy of the parameter blob (zeros on the added rank slices)
+        float *pp = (float *)scratch + lo.f_total;
+        CU_CHECK(cudaMemsetAsync(pp, 0, (size_t)eff.pad_floats * 4, st));
+        k_pad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, params_in, pp, 0);
+        ++g_launches;
+        CU_CHECK(cudaGetLastError());
+        params = pp;
+    }
     const long long B = d->batch;
     const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = rp.G;
     const int GH = G * H;
@@ -1066,23 +1186,52 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, co
     return 0;
 }
 
-int ttrnn_rnn_backward(const ttrnn_rnn_desc *d, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+// body of ttrnn_rnn_backward on the effective (possibly rank-padded) descriptor
+static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const RnnLayout &lo, const DevInfo &dv, const float *x,
+                             const float *h0, const float *c0, const float *params, const float *out, const void *saved,
+                             const float *d_out, const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0,
+                             float *d_c0, void *scratch, cudaStream_t st);
+
+int ttrnn_rnn_backward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
                        const float *c0, const float *params, const float *out, const void *saved, const float *d_out,
                        const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
                        void *scratch, void *stream) {
     if (!ws || !plan_load(ws->plan, &t_opt))
         return fail("ttrnn_rnn_backward: `ws` must be the struct the matching forward ran with");
     RnnPlan rp;
-    if (build_rnn_plan(d, &rp)) return 1;
+    if (build_rnn_plan(d_in, &rp)) return 1;
     if (!x || !params || !out || !scratch || !d_params) return fail("x, params, out, scratch, d_params must be non-null");
     DevInfo dv;
     if (get_dev(&dv)) return 1;
+    EffDesc eff;
+    if (make_eff_desc(d_in, &dv, &eff)) return 1;
+    const ttrnn_rnn_desc *d = &eff.d;
+    if (eff.padded && build_rnn_plan(d, &rp)) return 1;
     RnnLayout lo;
     if (build_layout(d, rp, dv, &lo)) return 1;
-    if (lo.b_total * 4 != ws->bwd_scratch_bytes || lo.sv_total * 4 != ws->saved_bytes)
+    if ((lo.b_total + 2 * eff.pad_floats) * 4 != ws->bwd_scratch_bytes || lo.sv_total * 4 != ws->saved_bytes)
         return fail("ttrnn_rnn_backward: workspace struct does not belong to this descriptor (scratch %lld vs %lld bytes)",
-                    (long long)lo.b_total * 4, (long long)ws->bwd_scratch_bytes);
+                    (long long)(lo.b_total + 2 * eff.pad_floats) * 4, (long long)ws->bwd_scratch_bytes);
     cudaStream_t st = (cudaStream_t)stream;
+    if (!eff.padded)
+        return rnn_backward_impl(d, rp, lo, dv, x, h0, c0, params, out, saved, d_out, d_hT, d_cT, d_params, d_x, d_h0, d_c0, scratch, st);
+    float *pp = (float *)scratch + lo.b_total, *dpp = pp + eff.pad_floats;
+    CU_CHECK(cudaMemsetAsync(pp, 0, (size_t)eff.pad_floats * 4, st));
+    k_pad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, params, pp, 0);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    if (rnn_backward_impl(d, rp, lo, dv, x, h0, c0, pp, out, saved, d_out, d_hT, d_cT, dpp, d_x, d_h0, d_c0, scratch, st)) return 1;
+    // the gradient wrt a real core is the matching block of the padded core's gradient
+    k_unpad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, dpp, d_params);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const RnnLayout &lo, const DevInfo &dv, const float *x,
+                             const float *h0, const float *c0, const float *params, const float *out, const void *saved,
+                             const float *d_out, const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0,
+                             float *d_c0, void *scratch, cudaStream_t st) {
     const long long B = d->batch;
     const int T = d->seq_len, H = d->hidden_size, L = d->num_layers, G = rp.G;
     const int GH = G * H;

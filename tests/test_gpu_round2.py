@@ -31,7 +31,7 @@ DEV = "cuda:0"
 def options(**kw):
     """Set library options for the duration of a block; restore the defaults afterwards."""
     defaults = {"chunk_steps": 0, "save_u_bytes": 16 << 30, "tc_gemm": 1, "static_rows_fwd": 0, "static_rows_bwd": 0,
-                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1}
+                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1}
     lib = _lib.load()
     for k, v in kw.items():
         assert lib.ttrnn_set_option(k.encode(), int(v)) == 0, k
@@ -309,3 +309,37 @@ def test_cfg5_shape_three_chunks_matches_oracle():
         out, h, grads = gpu_run(cell, m, x, w_out, w_h)
     assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
     assert_grads(grads, g_ref)
+
+
+# ---- rank padding: ranks that are not multiples of 4 on the static kernels ----------------------------------------------------
+PAD_CASES = [
+    # name, cell, I, H, L, d, r, B, T
+    ("ge2e_default_d2r2", "lstm", 40, 256, 3, 2, 2, 24, 14),          # encoder/params_model.py:15-16 (n_cores 2, rank 2)
+    ("pmnist_gru_d2r2", "gru", 1, 256, 1, 2, 2, 20, 30),
+    ("lstm_d2r3", "lstm", 1, 256, 1, 2, 3, 9, 16),
+    ("lstm_d3r6", "lstm", 40, 256, 2, 3, 6, 40, 10),                  # pads to the registered d3 r8 chain; B*T >= 256: tensor cores
+]
+
+
+@pytest.mark.parametrize("case", PAD_CASES, ids=[c[0] for c in PAD_CASES])
+def test_rank_padded_static_path_matches_oracle(case):
+    name, cell, I, H, L, d, r, B, T = case
+    layers, m = make_pair(cell, I, H, L, d, r)
+    g = torch.Generator().manual_seed(15)
+    x = torch.rand(B, T, I, generator=g)
+    w_out, w_h = torch.randn(B, T, H, generator=g), torch.randn(B, H, generator=g)
+    o_ref, h_ref, g_ref = oracle_run(cell, layers, x, w_out, w_h)
+    plan = _lib.describe_plan(m.spec().desc(B, T), training=True)
+    assert plan[0]["rank_padded"] == 1, plan
+    assert all(lay["fwd_kernel"] != "runtime" and lay["bwd_kernel"] != "runtime" for lay in plan[1:]), plan
+    out, h, grads = gpu_run(cell, m, x, w_out, w_h)
+    assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
+    assert_grads(grads, g_ref)
+    for a, b in zip(grads, g_ref):
+        assert tuple(a.shape) == tuple(b.shape)             # gradients come back in the REAL core shapes
+    with options(rank_pad=0):
+        plan0 = _lib.describe_plan(m.spec().desc(B, T), training=True)
+        assert plan0[0]["rank_padded"] == 0 and plan0[1]["fwd_kernel"] == "runtime"
+        out0, h0, grads0 = gpu_run(cell, m, x, w_out, w_h)
+    assert rel_err(out0, o_ref) <= FWD_TOL
+    assert_grads(grads0, g_ref)
