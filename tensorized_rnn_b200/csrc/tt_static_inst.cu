@@ -65,6 +65,8 @@ using tts::Tune;
     {#S "(2 CTAs/SM)", CELL, MODE, R, x0_floats<S>(), tts::FwdSmem<S, R, __VA_ARGS__>::BYTES, &match_shape<S>, \
      &launch_fwd<S, CELL, R, MODE, __VA_ARGS__, 2>, &prepare_fwd<S, CELL, R, MODE, __VA_ARGS__, 2>}
 const TtsRnnFwdEntry kFwd[] = {
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
@@ -73,7 +75,13 @@ const TtsRnnFwdEntry kFwd[] = {
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
+    // one row per CTA: batches that cannot fill the SMs at two rows per CTA (strong scaling: 80 rows per GPU at 8 GPUs)
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<1, 1, 1, 2, 8, 2, 8>),
     TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 1, 1, 2, 8, 2, 8>),
+    // three / four rows per CTA: 296 < B <= 592 (the 320 rows per GPU of the 2-GPU strong-scaling point) would otherwise run
+    // 64 five-row CTAs on 148 SMs
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
+    TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
     TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
     TTS_FWD(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<4, 1, 4, 8, 8, 8, 8, 4, 8>),
     TTS_FWD(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<8, 1, 2, 8, 8, 4, 8, 4, 8>),
@@ -144,6 +152,8 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD_SAVED(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVED(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVED(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
@@ -158,6 +168,7 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d4r16_split),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d3_split_R2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_split_R2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_split_R3),
 };
@@ -213,6 +224,8 @@ using TBI_ih256_d4r8 = TuneB<TU_ih256_d4r8, 8, 4, 2, 1, 4, 4, 8, 8, 4>;
 const TtsTtlBwdEntry kTtlBwd[] = {
     TTS_TB(IH_40_H256_d3r8, 4, false, TBI_ih40_d3),
     TTS_TB(IH_256_H256_d3r8, 3, true, TBI_ih256_d3),
+    // without dX: the H-row projection of the dense dW^T onto the cores (once per layer and call; same shape for ih and hh)
+    TTS_TB(IH_256_H256_d3r8, 3, false, TBI_ih256_d3),
     TTS_TB(IH_256_H1024_d4r8, 1, false, TBI_ih256_d4r8),
     TTS_TB(HHW_H1024_d4r8, 1, false, TBI_hhw_h1024),
 };
@@ -270,7 +283,7 @@ const TtsRnnBwdEntry *tts_find_rnn_bwd(const ttrnn_tt_shape *hh, int cell, int m
         if (saved == 2 && (e.split != 0) != only_split) continue;
         const long long tiles = (B + e.R - 1) / e.R;
         const long long waves = (tiles + sms - 1) / sms;
-        const long long cost = waves * e.R;
+        const long long cost = waves * (2 * e.R + 3);
         if (!best || cost < best_cost || (cost == best_cost && e.R > best->R)) {
             best = &e;
             best_cost = cost;
@@ -335,7 +348,9 @@ const TtsRnnFwdEntry *tts_find_rnn_fwd(const ttrnn_tt_shape *hh, int cell, int m
         if (e.cell != cell || e.mode != mode || !e.match(hh) || e.smem > kMaxSmem) continue;
         const long long tiles = (B + e.R - 1) / e.R;
         const long long waves = (tiles + sms - 1) / sms;
-        const long long cost = waves * e.R;               // rows processed back to back by the busiest SM
+        // time of a wave of R rows per CTA ~ (1.5 + R): a latency floor per step (barriers, shared-memory round trips) plus
+        // the per-row work; without the floor a batch of 320 would run as three waves of one-row CTAs
+        const long long cost = waves * (2 * e.R + 3);
         if (!best || cost < best_cost || (cost == best_cost && e.R > best->R)) {
             best = &e;
             best_cost = cost;
