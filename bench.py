@@ -558,6 +558,11 @@ def main():
     # ---------------- our arm -----------------------------------------------------------------
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    # stdout carries exactly ONE line (the JSON record): anything libraries print while we run (NCCL prints its version
+    # banner to stdout at the first collective) is diverted to stderr at the file-descriptor level
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -615,7 +620,11 @@ def main():
         if "cpu_baseline" in head_rec:
             line["cpu_baseline"] = head_rec["cpu_baseline"]
         line["all_configs"] = [{k: v for k, v in r.items() if k != "config_id"} | {"id": r["config_id"]} for r in records]
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line))
+        sys.stdout.flush()
+        os.dup2(2, 1)
     if gb.dist is not None:
         gb.dist.destroy_process_group()
     return 0
