@@ -1239,8 +1239,8 @@ TTS_DEV void flush_all(DwRegs<S, R, TB> &dw, float *stg, float *slot, int tid) {
 // SV = 2: forward kept only the hh pre-activations u (G*H floats per row and step): stages d-1..1 are
 //         recomputed (their X_k feed the core gradients) but the final stage, its reduce-scatter and two
 //         barriers are skipped -- for two-core chains that is 60 % of the recomputed multiply-adds
-template <class S, int CELL, int R, int MODE, class TB, bool DWI = true, int SV = 0>
-__global__ void __launch_bounds__(NTHR, 1) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
+template <class S, int CELL, int R, int MODE, class TB, bool DWI = true, int SV = 0, int MINB = 1>
+__global__ void __launch_bounds__(NTHR, MINB) k_rnn_bwd_s(const __grid_constant__ RnnBwdSArgs a) {
     constexpr bool SAVED = (SV == 1), SAVEU = (SV != 0);
     static_assert(!SAVED || (S::D == 2 && DWI), "saved-activation backward is implemented for two-core chains");
     // DWI = false with kept gates: nothing of the forward chain is needed (gates come from the forward pass, the

@@ -88,14 +88,14 @@ const TtsRnnFwdEntry kFwd[] = {
 };
 
 
-template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0, int MINB = 1>
 int launch_bwd(const tts::RnnBwdSArgs *a, int grid, cudaStream_t st) {
-    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI, SV>::BYTES, st>>>(*a);
+    tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV, MINB><<<grid, tts::NTHR, tts::BwdSmem<S, R, TB, DWI, SV>::BYTES, st>>>(*a);
     return (int)cudaGetLastError();
 }
-template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0>
+template <class S, int CELL, int R, int MODE, class TB, bool DWI, int SV = 0, int MINB = 1>
 int prepare_bwd(int *occ) {
-    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV>;
+    auto k = tts::k_rnn_bwd_s<S, CELL, R, MODE, TB, DWI, SV, MINB>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tts::BwdSmem<S, R, TB, DWI, SV>::BYTES);
     if (e != cudaSuccess) return (int)e;
     return (int)cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, k, tts::NTHR, tts::BwdSmem<S, R, TB, DWI, SV>::BYTES);
@@ -124,6 +124,14 @@ constexpr long long slot_floats() { return tts::core_floats<S>() + 3LL * S::G * 
     {#S "(split, kept u)", CELL, MODE, R, 1, 2, tts::BwdSmem<S, R, __VA_ARGS__, false, 2>::BYTES, slot_floats<S>(), \
      &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false, 2>,                                  \
      &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, false, 2>}
+
+// the same with the register budget of two co-resident CTAs per SM (one-row variants: 80 KB of shared memory each).
+// Measured dead end (round 2, cfg3 shape, 196 / 296 rows): two co-resident one-row CTAs take 2.61 ms per layer-pass
+// against 2.33 ms for one two-row CTA per SM -- the per-step latency chain does not overlap across CTAs.  Not registered.
+#define TTS_BWD_SPLIT_SAVEU2(S, CELL, R, MODE, ...)                                                         \
+    {#S "(split, kept u, 2 CTAs/SM)", CELL, MODE, R, 1, 2, tts::BwdSmem<S, R, __VA_ARGS__, false, 2>::BYTES, slot_floats<S>(), \
+     &match_shape<S>, &launch_bwd<S, CELL, R, MODE, __VA_ARGS__, false, 2, 2>,                               \
+     &prepare_bwd<S, CELL, R, MODE, __VA_ARGS__, false, 2, 2>}
 
 // TuneB<forward Tune, BTM0..3 (rows per thread of bwd-data stage k), BSP (split of the last bwd-data
 // stage), WTK0..3 (kappa rows of the register tile of bwd-weight stage k)>
