@@ -245,7 +245,7 @@ def lstm_forward(layers: Sequence[LayerParams], x: Tensor,
     the return is (outputs (B, T, H), (h_T, c_T)) of the last layer only.
     """
     batch, seq_len, _ = x.shape
-    hid = int(layers[0]["hh_cores"][0].shape[2]) if False else _hidden_size(layers[0])
+    hid = _hidden_size(layers[0])
     outputs = torch.zeros(batch, seq_len, hid, dtype=x.dtype)
     if init_states is None:
         h0 = torch.zeros(batch, hid, dtype=x.dtype)
