@@ -71,6 +71,8 @@ const TtsRnnFwdEntry kFwd[] = {
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 1, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
+    TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 2, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD2(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, Tune<1, 2, 2, 1, 8>),
     TTS_FWD(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_XG, Tune<1, 2, 2, 1, 8>),
@@ -164,6 +166,8 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 1, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 2, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
     TTS_BWD_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d2),

@@ -370,7 +370,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
 // ---------------------------------------------------------------------------------------------------
 constexpr int RED_NT = 576;
 constexpr int RED_SEG = 8;                                   // k-blocks per TMEM segment: 32 chained hi*hi' MMAs (~6e-7)
-constexpr int RED_RAW_STAGES = 2, RED_OP_STAGES = 2;
+constexpr int RED_RAW_STAGES = 3, RED_OP_STAGES = 2;
 constexpr int RED_RAW_BYTES = 2 * TILE_BYTES;                // raw A [32][128], raw B [32][128]
 constexpr int RED_OP_BYTES = 4 * TILE_BYTES;                 // A hi, A lo, B hi, B lo
 constexpr int RED_SMEM = RED_RAW_STAGES * RED_RAW_BYTES + RED_OP_STAGES * RED_OP_BYTES + 1024 + 256 + 2 * 128 * 4;
