@@ -343,3 +343,13 @@ def test_rank_padded_static_path_matches_oracle(case):
         out0, h0, grads0 = gpu_run(cell, m, x, w_out, w_h)
     assert rel_err(out0, o_ref) <= FWD_TOL
     assert_grads(grads0, g_ref)
+
+
+def test_rank_padded_inference_matches_training_forward():
+    """The rank-padded descriptor also drives the `saved == NULL` branch (no_grad)."""
+    layers, m = make_pair("lstm", 40, 256, 2, 2, 2)
+    x = torch.rand(10, 9, 40, generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        o_ref, (h_ref, _) = oracle.lstm_forward(layers, x)
+        out, (h, c) = m(x.to(DEV))
+    assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
