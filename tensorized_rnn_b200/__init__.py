@@ -13,10 +13,11 @@ from .rnn_utils import ActivGradLogger, av_norm
 from .rnn import TTLSTM, TTLSTMCell, TTGRU, TTGRUCell, param_count
 from .ge2e import GE2EHead, embed_normalize, ge2e_loss
 from .dense import LSTM, LSTMCell, GRU, GRUCell
+from .speaker_encoder import SpeakerEncoder
 
 __all__ = ["auto_shape", "tt_shape", "TensorTrain", "transpose", "glorot_initializer", "random_matrix",
            "matrix_with_random_cores", "TTLinear", "TTLinearSet", "ActivGradLogger", "av_norm", "TTLSTM", "TTLSTMCell", "TTGRU", "TTGRUCell", "param_count",
-           "GE2EHead", "embed_normalize", "ge2e_loss", "LSTM", "LSTMCell", "GRU", "GRUCell"]
+           "GE2EHead", "embed_normalize", "ge2e_loss", "LSTM", "LSTMCell", "GRU", "GRUCell", "SpeakerEncoder"]
 from . import compat  # noqa: E402,F401  (compat.patch_reference(): switch a reference checkout over)
 
 __version__ = "0.2.0"

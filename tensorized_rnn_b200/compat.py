@@ -7,7 +7,8 @@ The reference's callers pick the recurrent classes by name at construction time
 (`experiments/digit_classification/mnist_classifier.py:19-35`,
 `experiments/speaker_verification/encoder/speaker_encoder.py:41-48`), so replacing the names in the
 modules they import from is enough: `tensorized_rnn.tt_lstm.TTLSTM`, `tensorized_rnn.gru.TTGRU`,
-`t3nsor.layers.TTLinear` (also re-exported as `t3nsor.TTLinear`), `tensorized_rnn.tt_linearset.TTLinearSet`
+`t3nsor.layers.TTLinear` (also re-exported as `t3nsor.TTLinear`), `tensorized_rnn.tt_linearset.TTLinearSet`, the dense
+baselines `tensorized_rnn.lstm.LSTM` / `tensorized_rnn.gru.GRU` (with their cells)
 and the logging registry `tensorized_rnn.rnn_utils.ActivGradLogger` (so that the training script's
 `ActivGradLogger.end_minibatch()` / `.get_logs()` calls see the loggers the B200 modules register).
 `unpatch_reference()` restores the originals.
@@ -18,7 +19,7 @@ import importlib
 import sys
 from typing import Dict, Tuple
 
-from . import layers, rnn, rnn_utils
+from . import dense, layers, rnn, rnn_utils
 
 _TARGETS = (
     ("tensorized_rnn.tt_lstm", "TTLSTM", rnn.TTLSTM),
@@ -26,6 +27,11 @@ _TARGETS = (
     ("tensorized_rnn.gru", "TTGRU", rnn.TTGRU),
     ("tensorized_rnn.gru", "TTGRUCell", rnn.TTGRUCell),
     ("tensorized_rnn.tt_linearset", "TTLinearSet", layers.TTLinearSet),
+    # dense baselines (pmnist_test.py without --tt, SpeakerEncoder(compression=None))
+    ("tensorized_rnn.lstm", "LSTM", dense.LSTM),
+    ("tensorized_rnn.lstm", "LSTMCell", dense.LSTMCell),
+    ("tensorized_rnn.gru", "GRU", dense.GRU),
+    ("tensorized_rnn.gru", "GRUCell", dense.GRUCell),
     ("tensorized_rnn.rnn_utils", "ActivGradLogger", rnn_utils.ActivGradLogger),
     ("tensorized_rnn.lstm", "ActivGradLogger", rnn_utils.ActivGradLogger),
     ("tensorized_rnn.gru", "ActivGradLogger", rnn_utils.ActivGradLogger),
