@@ -578,6 +578,10 @@ def main():
     records = []
     head_rec, head_weak = None, None
     order = [args.headline] + [i for i in ids if i != args.headline]
+    if world > 1:
+        # the dense baseline is a single-GPU comparison line (dense vs TT on one device path); its per-step GEMMs fall back to
+        # FFMA below 128 rows per GPU, which says nothing about the TT path that is being scaled
+        order = [i for i in order if not cfgs[i].get("dense") or i == args.headline]
     for cid in order:
         cfg = cfgs[cid]
         w, s = steps_for(cid)
