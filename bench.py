@@ -57,6 +57,10 @@ CONFIGS = {
     # secondary point SURVEY.md 8(a) asks for: the reference's own default GE2E model (params_model.py: d2, r2)
     6: dict(name="cfg3-alt GE2E speaker encoder 3xTT-LSTM d2 r2 (params_model.py defaults)", cell="lstm", I=40, H=256, L=3,
             d=2, r=2, B=640, T=160, mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
+    # the reference's own default GE2E model and batch (encoder/params_model.py: hidden 768, 1 layer, n_cores 2, rank 2,
+    # 16 speakers x 32 utterances): rank-padded onto the static H = 768 kernels
+    8: dict(name="ge2e-default GE2E speaker encoder 1xTT-LSTM H768 d2 r2 (params_model.py: 16 spk x 32 utt)", cell="lstm", I=40,
+            H=768, L=1, d=2, r=2, B=512, T=160, mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
     # dense baseline of cfg3 through the same engine (SpeakerEncoder(compression=None), speaker_encoder.py:29-36): the paper's
     # dense-vs-TT comparison on one device path
     7: dict(name="cfg3-dense GE2E speaker encoder 3xLSTM (dense baseline)", cell="lstm", I=40, H=256, L=3, d=0, r=0, B=640, T=160,
@@ -65,7 +69,7 @@ CONFIGS = {
 # per-config caps on (warmup, steps): cfg5 moves ~100 GB per step
 STEP_CAP = {5: (3, 3), 4: (3, 5)}
 # CPU sample (batch, T) per config for the in-line cpu_baseline: about 5-15 s of CPU work each
-CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160), 7: (96, 160)}
+CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160), 7: (96, 160), 8: (96, 160)}
 KINDS = ["k_ttlinear_fwd", "k_rnn_fwd", "k_rnn_bwd", "k_ttlinear_bwd", "gemm_ih_fwd", "gemm_dx", "gemm_dw"]
 
 
@@ -503,7 +507,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--headline", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--config", type=int, default=0, help="shorthand: headline = this config and run only it")
-    ap.add_argument("--configs", default="1,2,3,4,5,6,7", help="configs measured into all_configs")
+    ap.add_argument("--configs", default="1,2,3,4,5,6,7,8", help="configs measured into all_configs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of the headline config (profiling)")
     ap.add_argument("--seq-len", type=int, default=0, help="override T of the headline config (profiling only)")

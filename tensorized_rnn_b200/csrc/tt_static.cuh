@@ -210,7 +210,7 @@ struct FwdMap {
     static_assert(T::Mrow % TMr == 0, "TMr must divide Mrow");
     static constexpr int NTl = T::N / TN;
     static constexpr int MTl = T::Mrow / TMr;
-    static constexpr int LX = NTl >= 16 ? 16 : NTl;            // column tiles across a warp
+    static constexpr int LX = p2div(NTl, 16);                  // column tiles across a warp: largest power of two <= 16 dividing NTl
     static constexpr int LY = 32 / LX;
     static_assert(NTl % LX == 0 && MTl % LY == 0, "tile grid must be a multiple of the lane grid");
     static constexpr int WX = NTl / LX;                         // warps along columns
@@ -835,7 +835,7 @@ struct BdMap {
     static constexpr int MTl = T::Mrow / TMr;
     static constexpr int RED = T::NW;                           // reduction length (incl. the padded gate of stage 0)
     static_assert(T::Mrow % TMr == 0 && (RED / 4) % SPLIT == 0, "bwd-data tile shape");
-    static constexpr int LX = CTl >= 16 ? 16 : CTl;
+    static constexpr int LX = p2div(CTl, 16);                   // 12 column tiles (K = 96, H = 768 chains) -> 4 x 8 lanes
     static constexpr int LY = 32 / LX;
     static_assert(CTl % LX == 0 && MTl % LY == 0, "bwd-data lane grid");
     static constexpr int WX = CTl / LX;
@@ -1005,7 +1005,7 @@ struct BwMap {
     static constexpr int M = R * T::Mrow;
     static constexpr int ROWS = (M + MG - 1) / MG;                        // row iterations per thread
     // lanes: x = n tile (dY operand, pair-blocked), y = (kappa tile, row group) (X operand, period 2)
-    static constexpr int LX = NT4 >= 16 ? 16 : NT4;
+    static constexpr int LX = p2div(NT4, 16);
     static constexpr int LY = 32 / LX;
     static_assert(NT4 % LX == 0 && (KT * MG) % LY == 0, "bwd-weight lane grid");
     static constexpr int WXN = NT4 / LX;

@@ -18,6 +18,8 @@ TTS_SHAPE(HH_H256_d2r4_lstm, 2, 4, ARR(J, 16, 16) ARR(I, 32, 32) ARR(RK, 1, 4, 1
 TTS_SHAPE(HH_H256_d2r4_gru, 2, 3, ARR(J, 16, 16) ARR(I, 24, 32) ARR(RK, 1, 4, 1))
 TTS_SHAPE(HH_H256_d3r8_lstm, 3, 4, ARR(J, 4, 8, 8) ARR(I, 8, 8, 16) ARR(RK, 1, 8, 8, 1))
 TTS_SHAPE(HH_H256_d4r16_lstm, 4, 4, ARR(J, 4, 4, 4, 4) ARR(I, 4, 4, 8, 8) ARR(RK, 1, 16, 16, 16, 1))
+// H = 768 (the reference's default GE2E width, encoder/params_model.py:3; n_cores 2, rank 2 -> rank-padded to 4)
+TTS_SHAPE(HH_H768_d2r4_lstm, 2, 4, ARR(J, 24, 32) ARR(I, 48, 64) ARR(RK, 1, 4, 1))
 TTS_SHAPE(HH_H1024_d4r8_lstm, 4, 4, ARR(J, 4, 4, 8, 8) ARR(I, 8, 8, 8, 8) ARR(RK, 1, 8, 8, 8, 1))
 
 constexpr size_t kMaxSmem = 232448;     // 227 KB opt-in limit per CTA on sm_100
@@ -85,6 +87,8 @@ const TtsRnnFwdEntry kFwd[] = {
     TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
     TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
     TTS_FWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 5, tts::MODE_XG, Tune<1, 1, 1, 1, 8, 1, 8>),
+    TTS_FWD(HH_H768_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, Tune<1, 3, 1, 1, 8>),
+    TTS_FWD(HH_H768_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, Tune<1, 3, 1, 1, 8>),
     TTS_FWD(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<4, 1, 4, 8, 8, 8, 8, 4, 8>),
     TTS_FWD(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, Tune<8, 1, 2, 8, 8, 4, 8, 4, 8>),
 };
@@ -148,6 +152,8 @@ using TB_d3_R3 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 1, 1, 1, 1, 8, 4, 8, 4, 4>;
 using TB_d3_split_R2 = TuneB<Tune<1, 1, 1, 2, 8, 2, 8>, 2, 2, 1, 1, 8, 4, 8, 4, 4>;
 using TB_d3_split_R3 = TuneB<Tune<1, 1, 1, 1, 8, 1, 8>, 2, 2, 1, 1, 8, 4, 8, 4, 4>;
 // d4 r16 (cfg4 shape) training: dX-only kernel with kept gates; last bwd-data stage split 4 ways
+// H = 768 d2 r4: dX-only kernel with kept gates (the fused variant's core-gradient tiles do not divide 256 threads)
+using TB_h768_split = TuneB<Tune<1, 3, 1, 1, 8>, 1, 1, 1, 1, 2, 8, 8, 8, 8>;
 using TB_d4r16_split = TuneB<Tune<4, 1, 4, 8, 8, 8, 8, 4, 8>, 8, 8, 4, 1, 4, 4, 4, 4, 4>;
 const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
@@ -180,6 +186,8 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_R3),
     TTS_BWD_SPLIT(HH_H1024_d4r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_h1024_split),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d4r16_split),
+    TTS_BWD_SPLIT_SAVEU(HH_H768_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_h768_split),
+    TTS_BWD_SPLIT_SAVEU(HH_H768_d2r4_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_h768_split),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d3_split_R2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_split_R2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_split_R3),

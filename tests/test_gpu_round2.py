@@ -317,6 +317,7 @@ PAD_CASES = [
     ("ge2e_default_d2r2", "lstm", 40, 256, 3, 2, 2, 24, 14),          # encoder/params_model.py:15-16 (n_cores 2, rank 2)
     ("pmnist_gru_d2r2", "gru", 1, 256, 1, 2, 2, 20, 30),
     ("lstm_d2r3", "lstm", 1, 256, 1, 2, 3, 9, 16),
+    ("ge2e_default_h768_d2r2", "lstm", 40, 768, 1, 2, 2, 18, 16),     # params_model.py: hidden 768, 1 layer, n_cores 2, rank 2
     ("lstm_d3r6", "lstm", 40, 256, 2, 3, 6, 40, 10),                  # pads to the registered d3 r8 chain; B*T >= 256: tensor cores
 ]
 
