@@ -580,7 +580,7 @@ def main():
         return min(args.warmup, cw), min(args.steps, cs)
 
     records = []
-    head_rec, head_weak = None, None
+    head_rec = None
     order = [args.headline] + [i for i in ids if i != args.headline]
     if world > 1:
         # the dense baseline is a single-GPU comparison line (dense vs TT on one device path); its per-step GEMMs fall back to

@@ -630,28 +630,6 @@ inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_b
     return (int)cudaGetLastError();
 }
 
-// number of splits the reduction will use for `rows` (the caller sizes part / pbias with it)
-inline int tc_red_plan(long long rows, int rpb, long long a_bstride, int M, int N, int sms, int max_split, RagBox *gb, long long *per) {
-    long long rp, nb, bs;
-    rag_dims(rows, rpb, a_bstride, M, &rp, &nb, &bs);
-    RagBox g = make_ragbox(rp, nb, BK);
-    const long long tiles = (long long)((M + BM - 1) / BM) * (N / BN);
-    // choose the split count that minimises waves * k-blocks per split (+ a small per-CTA epilogue cost)
-    long long best = 1;
-    double best_cost = 1e300;
-    for (long long s = 1; s <= max_split && s <= g.nboxes; ++s) {
-        const long long p = (g.nboxes + s - 1) / s;
-        const long long s_eff = (g.nboxes + p - 1) / p;
-        const long long waves = (tiles * s_eff + sms - 1) / sms;
-        const double cost = (double)waves * ((double)p + 24.0);
-        if (cost < best_cost) { best_cost = cost; best = s_eff; }
-    }
-    const long long p = (g.nboxes + best - 1) / best;
-    if (gb) *gb = g;
-    if (per) *per = p;
-    return (int)((g.nboxes + p - 1) / p);
-}
-
 inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bstride, int M, const float *b, long long b_bstride,
                          int N, float *part, float *pbias, int sms, int max_split, int *nsplit_out, cudaStream_t st) {
     long long rp, nb, abs_, rp2, nb2, bbs;
@@ -662,7 +640,7 @@ inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bs
     long long per = 0;
     RagBox gb = make_ragbox(rp, nb, BK);
     {
-        // same search as tc_red_plan, on the geometry actually used
+        // number of row splits: minimise waves x (k-blocks per split + a per-CTA prologue / epilogue cost)
         const long long tiles = (long long)((M + BM - 1) / BM) * (N / BN);
         long long best = 1;
         double best_cost = 1e300;

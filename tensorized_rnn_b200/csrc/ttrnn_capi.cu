@@ -320,11 +320,9 @@ struct PadEntry { int src, dst, r, mid, rn, rnp; };       // core (r, mid, rn) a
 struct PadTable { int n; PadEntry e[kMaxPadEntries]; };
 
 __global__ void __launch_bounds__(256) k_pad_cores(const __grid_constant__ PadTable t, const float *__restrict__ src,
-                                                   float *__restrict__ dst, int rp_dummy) {
+                                                   float *__restrict__ dst) {
     const PadEntry en = t.e[blockIdx.x];
-    (void)rp_dummy;
-    // destination core is (rp, mid, rnp) with rp implied by the next entry's offset: iterate over the SOURCE extents and
-    // zero-fill is done by the memset the host issues before this kernel
+    // iterate over the SOURCE extents; the added rank slices are zeroed by the memset the host issues before this kernel
     const int n = en.r * en.mid * en.rn;
     for (int i = threadIdx.x; i < n; i += 256) {
         const int b = i % en.rn, m = (i / en.rn) % en.mid, a = i / (en.rn * en.mid);
@@ -1037,7 +1035,7 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws,
         // rank-padded copy of the parameter blob (zeros on the added rank slices)
         float *pp = (float *)scratch + lo.f_total;
         CU_CHECK(cudaMemsetAsync(pp, 0, (size_t)eff.pad_floats * 4, st));
-        k_pad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, params_in, pp, 0);
+        k_pad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, params_in, pp);
         ++g_launches;
         CU_CHECK(cudaGetLastError());
         params = pp;
@@ -1217,7 +1215,7 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws
         return rnn_backward_impl(d, rp, lo, dv, x, h0, c0, params, out, saved, d_out, d_hT, d_cT, d_params, d_x, d_h0, d_c0, scratch, st);
     float *pp = (float *)scratch + lo.b_total, *dpp = pp + eff.pad_floats;
     CU_CHECK(cudaMemsetAsync(pp, 0, (size_t)eff.pad_floats * 4, st));
-    k_pad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, params, pp, 0);
+    k_pad_cores<<<eff.tab.n, 256, 0, st>>>(eff.tab, params, pp);
     ++g_launches;
     CU_CHECK(cudaGetLastError());
     if (rnn_backward_impl(d, rp, lo, dv, x, h0, c0, pp, out, saved, d_out, d_hT, d_cT, dpp, d_x, d_h0, d_c0, scratch, st)) return 1;
