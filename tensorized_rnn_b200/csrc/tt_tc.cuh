@@ -116,6 +116,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]^T: the A operand (128 rows x 8 k, one 32-bit column per k value) read from TMEM
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 16 consecutive columns: thread l of the warp writes row (lane base + l)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -192,9 +213,12 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float *__restrict__ sr
 //   Bt : N x K, pre-split into hi / lo copies in global memory
 //   persistent CTAs over (row tile, 128-column tile); TMEM holds two (main, small-term) pairs of 128 x 128 accumulators
 //   so that the epilogue of one tile overlaps the main loop of the next
-// warps 0-3: splitters (A tile -> hi in place + lo), 4-7: epilogue, 8: TMA producer, 9: MMA issuer + TMEM allocator
+// warps 0-7: splitters (A tile -> hi in place + lo), 8-11: epilogue, 12: TMA producer, 13: MMA issuer + TMEM allocator
+// (eight splitter warps: with four, one warp per scheduler walked the whole split chain of a k-block and the tensor pipe
+// waited for it)
 // ---------------------------------------------------------------------------------------------------
 constexpr int ROWS_STAGES = 3;
+constexpr int ROWS_NT = 448;                     // 14 warps
 constexpr int ROWS_STAGE_BYTES = 4 * TILE_BYTES;             // A hi (raw lands here), A lo, Bt hi, Bt lo
 constexpr int ROWS_SMEM = ROWS_STAGES * ROWS_STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
@@ -208,7 +232,7 @@ struct TcRowsArgs {
     const float *bias, *bias2;
 };
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(ROWS_NT, 1)
 k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensorMap tmA,
           const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
     extern __shared__ uint8_t smem_raw[];
@@ -226,7 +250,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
     if (threadIdx.x == 0) {
         for (int s = 0; s < ROWS_STAGES; ++s) {
             mbar_init(bar_full(s), 1);
-            mbar_init(bar_split(s), 128);
+            mbar_init(bar_split(s), 256);
             mbar_init(bar_empty(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -235,7 +259,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
         }
         fence_barrier_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    if (warp == 13) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -245,7 +269,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
     const int nkb = (g.K + BK - 1) / BK;
     const uint32_t idesc = umma_idesc_tf32(BM, BN);
 
-    if (warp == 8) {
+    if (warp == 12) {
         // ---------------- TMA producer ----------------
         if (lane == 0) {
             tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
@@ -266,7 +290,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 13) {
         // ---------------- MMA issuer ----------------
         if (lane == 0) {
             long long it = 0, nt = 0;
@@ -290,7 +314,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
                 umma_commit(bar_tfull(acc));
             }
         }
-    } else if (warp < 4) {
+    } else if (warp < 8) {
         // ---------------- splitters: A tile -> hi (in place) + lo ----------------
         long long it = 0;
         for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
@@ -301,8 +325,8 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
                 uint8_t *st = smem_raw + (base - smem_u32(smem_raw)) + s * ROWS_STAGE_BYTES;
                 float4 *ah = reinterpret_cast<float4 *>(st), *al = reinterpret_cast<float4 *>(st + TILE_BYTES);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int idx = threadIdx.x + 128 * j;
+                for (int j = 0; j < 4; ++j) {
+                    const int idx = threadIdx.x + 256 * j;
                     float4 h, l;
                     split4(ah[idx], h, l);
                     ah[idx] = h;
@@ -314,7 +338,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
         }
     } else {
         // ---------------- epilogue: TMEM -> registers -> (+ bias) -> global ----------------
-        const int q = warp - 4;                        // TMEM lane quarter of this warp (warp % 4)
+        const int q = warp - 8;                        // TMEM lane quarter of this warp (warp % 4)
         const int i = q * 32 + lane;                   // row of the tile
         const int bi = i / g.g.rb, ti = i - bi * g.g.rb;
         long long nt = 0;
@@ -356,7 +380,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem_base, 512);
+    if (warp == 13) tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -559,6 +583,207 @@ k_tc_red(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtensorMa
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_tc_red_ts: k_tc_red with the A operand in TMEM (tcgen05.mma "TS" form).  A row m of the 128 x 32 A tile is one TMEM
+// lane: the four A-splitter warps (warp q owns lanes 32q..32q+31) read their column of the raw [32 r][128 m] tile, split it
+// and write hi / lo with tcgen05.st; only B goes through shared memory (K-major SWIZZLE_128B, written by warps 4-7).
+// Per k-block that removes 32 KB of operand-tile stores and 48 KB of MMA operand reads from the shared-memory port
+// (224 -> 144 KB), which is what bounds k_tc_red, and frees shared memory for a deeper B ring.
+// TMEM columns: [0,128) [128,256) main accumulators, [256,384) small terms, [384,512) two A stages of (hi 32 | lo 32).
+// warps 0-3: A splitters; 4-7: B splitters (+ bias column sums); 8-15: drain; 16: TMA; 17: MMA issuer + TMEM allocator
+// ---------------------------------------------------------------------------------------------------
+constexpr int RTS_RAW_STAGES = 3, RTS_OP_STAGES = 2;
+constexpr int RTS_OP_BYTES = 2 * TILE_BYTES;                 // B hi, B lo
+constexpr int RTS_SMEM = RTS_RAW_STAGES * RED_RAW_BYTES + RTS_OP_STAGES * RTS_OP_BYTES + 1024 + 256;
+
+__global__ void __launch_bounds__(RED_NT, 1)
+k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t raw0 = base, op0 = base + RTS_RAW_STAGES * RED_RAW_BYTES;
+    const uint32_t bars = op0 + RTS_OP_STAGES * RTS_OP_BYTES;
+    auto bar_rfull = [&](int s) { return bars + 8u * s; };
+    auto bar_rempty = [&](int s) { return bars + 8u * (RTS_RAW_STAGES + s); };
+    auto bar_ofull = [&](int s) { return bars + 8u * (2 * RTS_RAW_STAGES + s); };
+    auto bar_oempty = [&](int s) { return bars + 8u * (2 * RTS_RAW_STAGES + RTS_OP_STAGES + s); };
+    auto bar_afull = [&](int a) { return bars + 8u * (2 * RTS_RAW_STAGES + 2 * RTS_OP_STAGES + a); };
+    auto bar_aempty = [&](int a) { return bars + 8u * (2 * RTS_RAW_STAGES + 2 * RTS_OP_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * RTS_RAW_STAGES + 2 * RTS_OP_STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const int tiles = g.tiles_m * g.tiles_n;
+    const int split = blockIdx.x / tiles, rem = blockIdx.x % tiles;
+    const int m0 = (rem / g.tiles_n) * BM, n0 = (rem % g.tiles_n) * BN;
+    const long long kb0 = (long long)split * g.per;
+    const long long kb1 = (kb0 + g.per < g.g.nboxes) ? kb0 + g.per : g.g.nboxes;
+    const long long nkb = kb1 - kb0;
+    const long long nseg = (nkb + RED_SEG - 1) / RED_SEG;
+
+    if (g.g.rb * g.g.nbx < BK) {
+        float4 *z = reinterpret_cast<float4 *>(gbase);
+        for (int i = threadIdx.x; i < RTS_RAW_STAGES * RED_RAW_BYTES / 16; i += RED_NT) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        fence_proxy_async();
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RTS_RAW_STAGES; ++s) { mbar_init(bar_rfull(s), 1); mbar_init(bar_rempty(s), 256); }
+        for (int s = 0; s < RTS_OP_STAGES; ++s) { mbar_init(bar_ofull(s), 256); mbar_init(bar_oempty(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_afull(a), 1); mbar_init(bar_aempty(a), 256); }
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    constexpr uint32_t A_COL0 = 3 * BN;                     // TMEM columns of the A stages
+
+    if (warp == 16) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
+            const uint32_t box_bytes = (uint32_t)(g.g.rb * g.g.nbx * 128 * 4);
+            for (long long i = 0; i < nkb; ++i) {
+                const int s = (int)(i % RTS_RAW_STAGES);
+                const uint32_t ph = (uint32_t)((i / RTS_RAW_STAGES) & 1);
+                const long long box = kb0 + i;
+                const int b0 = (int)(box / g.g.tpb) * g.g.nbx, t0 = (int)(box % g.g.tpb) * g.g.rb;
+                mbar_wait(bar_rempty(s), ph ^ 1u);
+                mbar_arrive_expect_tx(bar_rfull(s), 2 * box_bytes);
+                tma_load_3d(raw0 + s * RED_RAW_BYTES, &tmA, bar_rfull(s), m0, t0, b0);
+                tma_load_3d(raw0 + s * RED_RAW_BYTES + TILE_BYTES, &tmB, bar_rfull(s), n0, t0, b0);
+            }
+        }
+    } else if (warp == 17) {
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(BM, BN);
+            for (long long i = 0; i < nkb; ++i) {
+                const long long seg = i / RED_SEG;
+                const int ab = (int)(seg & 1);
+                const bool seg_first = (i % RED_SEG) == 0, seg_last = ((i + 1) % RED_SEG) == 0 || i + 1 == nkb;
+                if (seg_first) {
+                    mbar_wait(bar_aempty(ab), (uint32_t)(((seg >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                }
+                const int s = (int)(i % RTS_OP_STAGES);
+                const uint32_t ph = (uint32_t)((i / RTS_OP_STAGES) & 1);
+                mbar_wait(bar_ofull(s), ph);
+                tc_fence_after();
+                const uint32_t st = op0 + s * RTS_OP_BYTES;
+                const uint64_t dbh = umma_desc_sw128(st), dbl = umma_desc_sw128(st + TILE_BYTES);
+                const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
+                const uint32_t d_main = tmem_base + ab * BN, d_small = tmem_base + 2 * BN;
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    const uint64_t o = (uint64_t)(ks * 2);
+                    umma_tf32_ts(d_small, a_lo + ks * 8, dbh + o, idesc, (i == 0 && ks == 0) ? 0u : 1u);
+                    umma_tf32_ts(d_small, a_hi + ks * 8, dbl + o, idesc, 1u);
+                    umma_tf32_ts(d_main, a_hi + ks * 8, dbh + o, idesc, (seg_first && ks == 0) ? 0u : 1u);
+                }
+                umma_commit(bar_oempty(s));
+                if (seg_last) umma_commit(bar_afull(ab));
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------- A splitters: column m of the raw tile -> TMEM lane m, hi / lo over 32 k columns ----------------
+        const int m = warp * 32 + lane;
+        for (long long i = 0; i < nkb; ++i) {
+            const int rs = (int)(i % RTS_RAW_STAGES), os = (int)(i % RTS_OP_STAGES);
+            const uint32_t rph = (uint32_t)((i / RTS_RAW_STAGES) & 1), oph = (uint32_t)((i / RTS_OP_STAGES) & 1);
+            mbar_wait(bar_rfull(rs), rph);
+            const float *rawA = reinterpret_cast<const float *>(gbase + rs * RED_RAW_BYTES);
+            float v[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) v[r] = rawA[r * 128 + m];
+            mbar_wait(bar_oempty(os), oph ^ 1u);             // the MMAs that read this A stage have completed
+            tc_fence_after();
+            const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + A_COL0 + (uint32_t)os * 64u;
+#pragma unroll
+            for (int hhalf = 0; hhalf < 2; ++hhalf) {
+                float hi[16], lo[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    hi[r] = tf32_rna(v[hhalf * 16 + r]);
+                    lo[r] = tf32_rna(v[hhalf * 16 + r] - hi[r]);
+                }
+                tmem_st16(ta + hhalf * 16, hi);
+                tmem_st16(ta + 32 + hhalf * 16, lo);
+            }
+            tmem_wait_st();
+            mbar_arrive(bar_rempty(rs));                     // after the values were consumed (see k_tc_red)
+            tc_fence_before();
+            mbar_arrive(bar_ofull(os));
+        }
+    } else if (warp < 8) {
+        // ---------------- B splitters: raw [r][col] -> hi / lo [col][r] (K-major, 128-byte swizzle) + bias column sums ---------
+        const int col = threadIdx.x - 128;
+        const bool want_bias = g.pbias != nullptr && m0 == 0;
+        float bsum = 0.f;
+        for (long long i = 0; i < nkb; ++i) {
+            const int rs = (int)(i % RTS_RAW_STAGES), os = (int)(i % RTS_OP_STAGES);
+            const uint32_t rph = (uint32_t)((i / RTS_RAW_STAGES) & 1), oph = (uint32_t)((i / RTS_OP_STAGES) & 1);
+            mbar_wait(bar_rfull(rs), rph);
+            const float *rawB = reinterpret_cast<const float *>(gbase + rs * RED_RAW_BYTES + TILE_BYTES);
+            mbar_wait(bar_oempty(os), oph ^ 1u);
+            uint8_t *op = gbase + (op0 - base) + os * RTS_OP_BYTES;
+#pragma unroll
+            for (int rq = 0; rq < 8; ++rq) {
+                const float4 vb = make_float4(rawB[(rq * 4 + 0) * 128 + col], rawB[(rq * 4 + 1) * 128 + col],
+                                              rawB[(rq * 4 + 2) * 128 + col], rawB[(rq * 4 + 3) * 128 + col]);
+                if (want_bias) bsum += (vb.x + vb.y) + (vb.z + vb.w);
+                const int off = col * 128 + ((rq ^ (col & 7)) << 4);
+                float4 h, l;
+                split4(vb, h, l);
+                *reinterpret_cast<float4 *>(op + off) = h;
+                *reinterpret_cast<float4 *>(op + TILE_BYTES + off) = l;
+            }
+            mbar_arrive(bar_rempty(rs));
+            fence_proxy_async();
+            mbar_arrive(bar_ofull(os));
+        }
+        if (want_bias) g.pbias[(long long)split * g.N + n0 + col] = bsum;
+    } else {
+        // ---------------- drain warps: promote every finished TMEM segment into FP32 registers (as in k_tc_red) ----------
+        const int dw = warp - 8;
+        const int q = dw & 3, ch = dw >> 2;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 64);
+        float acc[64];
+#pragma unroll
+        for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+        for (long long seg = 0; seg < nseg; ++seg) {
+            const int ab = (int)(seg & 1);
+            mbar_wait(bar_afull(ab), (uint32_t)((seg >> 1) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                tmem_ld32(tl + (uint32_t)(ab * BN + cc * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) acc[cc * 32 + j] += v[j];
+            }
+            tc_fence_before();
+            mbar_arrive(bar_aempty(ab));
+        }
+        const int m = m0 + q * 32 + lane;
+        float *prow = g.part + ((long long)split * g.M + m) * g.N + n0 + ch * 64;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            float v[32];
+            tmem_ld32(tl + (uint32_t)(2 * BN + cc * 32), v);
+            if (m < g.M) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4 *>(prow + cc * 32)[j] =
+                        make_float4(acc[cc * 32 + 4 * j] + v[4 * j], acc[cc * 32 + 4 * j + 1] + v[4 * j + 1],
+                                    acc[cc * 32 + 4 * j + 2] + v[4 * j + 2], acc[cc * 32 + 4 * j + 3] + v[4 * j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // host side: tensor maps and launchers.  Return 0 on success, a CUresult / cudaError_t code (> 0) otherwise,
 // -1 when the shape cannot go through this path (caller falls back to the FFMA kernels)
 // ---------------------------------------------------------------------------------------------------
@@ -626,9 +851,17 @@ inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_b
         attr = true;
     }
     long long grid = g.ntiles < sms ? g.ntiles : sms;
-    k_tc_rows<<<(unsigned)grid, NT, ROWS_SMEM, st>>>(g, tmA, tmBh, tmBl);
+    k_tc_rows<<<(unsigned)grid, ROWS_NT, ROWS_SMEM, st>>>(g, tmA, tmBh, tmBl);
     return (int)cudaGetLastError();
 }
+
+// 0 (default) = both operands from shared memory (k_tc_red); 1 = A operand from TMEM (k_tc_red_ts).  Measured on B200
+// (tools/tc_gemm_test, round 2): 161 / 169 / 172 TFLOP/s with A in TMEM against 164 / 174 / 176 from shared memory on the
+// cfg3 / cfg5 shapes, and an L2 prefetch 8 k-blocks ahead of the TMA loads changed nothing either: neither the shared-memory
+// port nor the TMA latency binds these kernels.  ncu: tensor pipe active 49-51 % -- which with cta_group::1 (M = 128) is
+// half of what the unit can do, so the remaining factor is (i) the splitter warps' latency per k-block and (ii) a
+// cta_group::2 pair, not operand traffic.
+inline int &tc_red_variant() { static int v = 0; return v; }
 
 inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bstride, int M, const float *b, long long b_bstride,
                          int N, float *part, float *pbias, int sms, int max_split, int *nsplit_out, cudaStream_t st) {
@@ -665,11 +898,13 @@ inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bs
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_red, cudaFuncAttributeMaxDynamicSharedMemorySize, RED_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_red_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, RTS_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
     const long long grid = (long long)g.tiles_m * g.tiles_n * g.nsplit;
-    k_tc_red<<<(unsigned)grid, RED_NT, RED_SMEM, st>>>(g, tmA, tmB);
+    if (tc_red_variant()) k_tc_red_ts<<<(unsigned)grid, RED_NT, RTS_SMEM, st>>>(g, tmA, tmB);
+    else k_tc_red<<<(unsigned)grid, RED_NT, RED_SMEM, st>>>(g, tmA, tmB);
     if (nsplit_out) *nsplit_out = g.nsplit;
     return (int)cudaGetLastError();
 }

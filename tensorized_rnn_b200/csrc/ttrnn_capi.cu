@@ -887,6 +887,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
     if (!strcmp(key, "tc_gemm")) { g_opt_tc_gemm.store(value); return 0; }
     if (!strcmp(key, "rank_pad")) { g_opt_rank_pad.store(value); return 0; }
+    if (!strcmp(key, "tc_red_ts")) { ttc::tc_red_variant() = value ? 1 : 0; return 0; }   // A/B switch, not part of a plan
     return 1;
 }
 

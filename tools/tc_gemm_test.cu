@@ -169,6 +169,8 @@ static int test_red(int nb, int rpb, int T, int M, int N, int sms, bool timing, 
 
 int main(int argc, char **argv) {
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
+    if (getenv("TC_RED_VARIANT")) ttc::tc_red_variant() = atoi(getenv("TC_RED_VARIANT"));
+    printf("k_tc_red variant: %s\n", ttc::tc_red_variant() ? "A from TMEM (k_tc_red_ts)" : "A from shared memory (k_tc_red)");
     if (argc > 1 && !strcmp(argv[1], "chain")) {
         int dev0 = 0, sms0 = 0;
         CK(cudaGetDevice(&dev0));
