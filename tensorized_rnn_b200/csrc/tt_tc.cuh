@@ -859,8 +859,9 @@ inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_b
 // (tools/tc_gemm_test, round 2): 161 / 169 / 172 TFLOP/s with A in TMEM against 164 / 174 / 176 from shared memory on the
 // cfg3 / cfg5 shapes, and an L2 prefetch 8 k-blocks ahead of the TMA loads changed nothing either: neither the shared-memory
 // port nor the TMA latency binds these kernels.  ncu: tensor pipe active 49-51 % -- which with cta_group::1 (M = 128) is
-// half of what the unit can do, so the remaining factor is (i) the splitter warps' latency per k-block and (ii) a
-// cta_group::2 pair, not operand traffic.
+// half of what the unit can do; the kernels are sensitive to pipeline depth instead (k_tc_rows: 2 stages 128-138 TFLOP/s,
+// 3 stages 145-181; k_tc_red: +12 % from the third raw stage), i.e. to the bytes in flight that 192-224 KB of stages can
+// hold against the TMA latency.  A cta_group::2 pair (half of B per CTA, full-rate M = 256 MMAs) is the next step.
 inline int &tc_red_variant() { static int v = 0; return v; }
 
 inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bstride, int M, const float *b, long long b_bstride,
