@@ -493,7 +493,12 @@ class GpuBench(object):
                              "peak_source": "ttrnn_ffma_probe measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
                              "algorithmic_flops_per_seqstep": cred[KINDS[dom]],
                              "whole_step_tflops_per_gpu": whole, "whole_step_frac": whole / self.peak if self.peak else None,
-                             "fwd_flops_per_seqstep": fwd_flops, "kernels": kern, "plan": plan},
+                             "fwd_flops_per_seqstep": fwd_flops, "kernels": kern, "plan": plan,
+                             # the second bound SURVEY.md 8d asks for: the sequential chain.  A CTA owns its rows for all T, so a
+                             # layer-pass cannot be shorter than T x (per-step dependency chain); these are the measured per-step
+                             # times of the recurrent kernels (all row tiles of a layer run concurrently when they fit the SMs)
+                             "recurrent_us_per_layer_step": {
+                                 "fwd": kms[1] / steps / (cfg["L"] * T) * 1e3, "bwd": kms[2] / steps / (cfg["L"] * T) * 1e3}},
             }
         del model, params, x_dev, x_host, dense_dout
         torch.cuda.empty_cache()
