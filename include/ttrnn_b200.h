@@ -254,8 +254,8 @@ int ttrnn_static_kernel_table(char *buf, int32_t cap);
  *                   default n_cores 2 / rank 2); 0 = runtime-shape kernels
  *   "tc_gemm"       1 (default) = the dense-route GEMMs run on the tensor cores (tcgen05.mma kind::tf32, error-compensated
  *                   3xTF32 split, TMA-staged operands, TMEM accumulators) where the shape fits; 0 = FP32 FFMA kernels
- *   "tc_red_ts"     1 = the reduction GEMM takes its A operand from TMEM (tcgen05.mma TS form) instead of shared memory
- *                   (default 0: measured 2 % slower; kept as a validated alternative, same results)
+ *   "tc_red_ts"     1 (default) = the reduction GEMM takes its A operand from TMEM (tcgen05.st + the TS form of tcgen05.mma),
+ *                   which leaves room for five raw TMA stages; 0 = both operands from shared memory (3 % slower, same results)
  *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of
  *                   recomputing them (default 0 = recompute)
  * returns 0 if the key is known. */

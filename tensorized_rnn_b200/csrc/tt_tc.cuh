@@ -591,7 +591,7 @@ k_tc_red(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtensorMa
 // TMEM columns: [0,128) [128,256) main accumulators, [256,384) small terms, [384,512) two A stages of (hi 32 | lo 32).
 // warps 0-3: A splitters; 4-7: B splitters (+ bias column sums); 8-15: drain; 16: TMA; 17: MMA issuer + TMEM allocator
 // ---------------------------------------------------------------------------------------------------
-constexpr int RTS_RAW_STAGES = 3, RTS_OP_STAGES = 2;
+constexpr int RTS_RAW_STAGES = 5, RTS_OP_STAGES = 2;
 constexpr int RTS_OP_BYTES = 2 * TILE_BYTES;                 // B hi, B lo
 constexpr int RTS_SMEM = RTS_RAW_STAGES * RED_RAW_BYTES + RTS_OP_STAGES * RTS_OP_BYTES + 1024 + 256;
 
@@ -855,14 +855,14 @@ inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_b
     return (int)cudaGetLastError();
 }
 
-// 0 (default) = both operands from shared memory (k_tc_red); 1 = A operand from TMEM (k_tc_red_ts).  Measured on B200
-// (tools/tc_gemm_test, round 2): 161 / 169 / 172 TFLOP/s with A in TMEM against 164 / 174 / 176 from shared memory on the
-// cfg3 / cfg5 shapes, and an L2 prefetch 8 k-blocks ahead of the TMA loads changed nothing either: neither the shared-memory
-// port nor the TMA latency binds these kernels.  ncu: tensor pipe active 49-51 % -- which with cta_group::1 (M = 128) is
-// half of what the unit can do; the kernels are sensitive to pipeline depth instead (k_tc_rows: 2 stages 128-138 TFLOP/s,
-// 3 stages 145-181; k_tc_red: +12 % from the third raw stage), i.e. to the bytes in flight that 192-224 KB of stages can
-// hold against the TMA latency.  A cta_group::2 pair (half of B per CTA, full-rate M = 256 MMAs) is the next step.
-inline int &tc_red_variant() { static int v = 0; return v; }
+// 1 (default) = A operand from TMEM (k_tc_red_ts); 0 = both operands from shared memory (k_tc_red).  Measured on B200
+// (tools/tc_gemm_test, round 2, cfg3 / cfg5 shapes): shared-memory variant 164 / 174 / 176 TFLOP/s; A in TMEM with the same
+// three raw stages 161 / 169 / 172 (the shared-memory port is not what binds these kernels); A in TMEM with the FIVE raw TMA
+// stages its smaller operand ring makes room for: 169 / 177 / 183.  An L2 prefetch 8 k-blocks ahead of the TMA loads changed
+// nothing.  ncu: tensor pipe active 49-51 %, which with cta_group::1 (M = 128) is half of what the unit can do; the kernels
+// respond to pipeline depth (bytes in flight against the TMA latency), so a cta_group::2 pair (half of B per CTA, full-rate
+// M = 256 MMAs) is the next step.
+inline int &tc_red_variant() { static int v = 1; return v; }
 
 inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bstride, int M, const float *b, long long b_bstride,
                          int N, float *part, float *pbias, int sms, int max_split, int *nsplit_out, cudaStream_t st) {

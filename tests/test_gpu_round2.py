@@ -31,7 +31,7 @@ DEV = "cuda:0"
 def options(**kw):
     """Set library options for the duration of a block; restore the defaults afterwards."""
     defaults = {"chunk_steps": 0, "save_u_bytes": 16 << 30, "tc_gemm": 1, "static_rows_fwd": 0, "static_rows_bwd": 0,
-                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1, "tc_red_ts": 0}
+                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1, "tc_red_ts": 1}
     lib = _lib.load()
     for k, v in kw.items():
         assert lib.ttrnn_set_option(k.encode(), int(v)) == 0, k
@@ -356,15 +356,15 @@ def test_rank_padded_inference_matches_training_forward():
     assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
 
 
-def test_reduction_gemm_with_a_operand_in_tmem_matches_oracle():
-    """`tc_red_ts`: the core-gradient GEMM with its A operand fed from TMEM (tcgen05.mma TS form) gives the same gradients."""
+def test_reduction_gemm_with_both_operands_in_shared_memory_matches_oracle():
+    """`tc_red_ts = 0`: the core-gradient GEMM with both operands from shared memory (the default feeds A from TMEM)."""
     cell, I, H, L, d, r, B, T = "lstm", 40, 256, 2, 3, 8, 40, 24
     layers, m = make_pair(cell, I, H, L, d, r)
     g = torch.Generator().manual_seed(5)
     x = torch.rand(B, T, I, generator=g)
     w_out, w_h = torch.randn(B, T, H, generator=g), torch.randn(B, H, generator=g)
     _, _, g_ref = oracle_run(cell, layers, x, w_out, w_h)
-    with options(tc_red_ts=1) as lib:
+    with options(tc_red_ts=0) as lib:
         lib.ttrnn_tc_launch_count(1)
         _, _, grads = gpu_run(cell, m, x, w_out, w_h)
         assert int(lib.ttrnn_tc_launch_count(0)) > 0
