@@ -61,6 +61,11 @@ CONFIGS = {
     # 16 speakers x 32 utterances): rank-padded onto the static H = 768 kernels
     8: dict(name="ge2e-default GE2E speaker encoder 1xTT-LSTM H768 d2 r2 (params_model.py: 16 spk x 32 utt)", cell="lstm", I=40,
             H=768, L=1, d=2, r=2, B=512, T=160, mode="fwd+bwd", grad="hT", inp="uniform", seed=11),
+    # cfg3 as the reference's training step actually runs it (encoder/main.py:271-290): recurrent stack -> TT projection ->
+    # ReLU + L2 norm -> GE2E similarity matrix + softmax loss -> backward, with the head on the DEVICE (the reference moves the
+    # embeddings to the CPU for the loss); same B x T units as cfg3
+    9: dict(name="cfg3-step full GE2E training step: 3xTT-LSTM d3 r8 + TT projection + GE2E loss on the device", cell="lstm", I=40,
+            H=256, L=3, d=3, r=8, B=640, T=160, mode="fwd+bwd", grad="ge2e", inp="uniform", seed=11, ge2e=(64, 10, 256)),
     # dense baseline of cfg3 through the same engine (SpeakerEncoder(compression=None), speaker_encoder.py:29-36): the paper's
     # dense-vs-TT comparison on one device path
     7: dict(name="cfg3-dense GE2E speaker encoder 3xLSTM (dense baseline)", cell="lstm", I=40, H=256, L=3, d=0, r=0, B=640, T=160,
@@ -69,7 +74,7 @@ CONFIGS = {
 # per-config caps on (warmup, steps): cfg5 moves ~100 GB per step
 STEP_CAP = {5: (3, 3), 4: (3, 5)}
 # CPU sample (batch, T) per config for the in-line cpu_baseline: about 5-15 s of CPU work each
-CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160), 7: (96, 160), 8: (96, 160)}
+CPU_SAMPLE = {1: (64, 784), 2: (64, 784), 3: (96, 160), 4: (32, 160), 5: (8, 200), 6: (96, 160), 7: (96, 160), 8: (96, 160), 9: (96, 160)}
 KINDS = ["k_ttlinear_fwd", "k_rnn_fwd", "k_rnn_bwd", "k_ttlinear_bwd", "gemm_ih_fwd", "gemm_dx", "gemm_dw"]
 
 
@@ -117,8 +122,8 @@ def upstream(cfg, out, hT):
     """Scalar whose gradient is the config's upstream gradient pattern."""
     if cfg["grad"] == "out_last":
         return out[:, -1, :].sum()
-    if cfg["grad"] == "hT":
-        return hT.sum()
+    if cfg["grad"] in ("hT", "ge2e"):         # CPU baseline of the GE2E step: the recurrent stack with a gradient on h_T
+        return hT.sum()                          # (the head is a few ms on the CPU as well and is left out of the CPU figure)
     return None
 
 
@@ -325,14 +330,22 @@ class GpuBench(object):
         lib, dev, dist = self.lib, self.dev, self.dist
         torch.manual_seed(cfg["seed"])
         dense = bool(cfg.get("dense"))
-        if dense:
+        ge2e = cfg.get("ge2e")
+        if ge2e:
+            with redirect_stdout(io.StringIO()):
+                enc = self.tr.SpeakerEncoder(cfg["I"], cfg["H"], cfg["L"], ge2e[2], torch.device("cpu"), None, compression="tt",
+                                             n_cores=cfg["d"], rank=cfg["r"]).to(dev)
+            model = enc.rnn
+        elif dense:
             model = (self.tr.LSTM if cfg["cell"] == "lstm" else self.tr.GRU)(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu")).to(dev)
         else:
             cls = self.tr.TTLSTM if cfg["cell"] == "lstm" else self.tr.TTGRU
             with redirect_stdout(io.StringIO()):
                 model = cls(cfg["I"], cfg["H"], cfg["L"], torch.device("cpu"), n_cores=cfg["d"], tt_rank=cfg["r"]).to(dev)
-        params = [p for p in model.parameters()]
+        params = [p for p in (enc if ge2e else model).parameters()]
         B, T, H = B_rank, cfg["T"], cfg["H"]
+        if ge2e and B % ge2e[1] != 0:
+            raise SystemExit("the GE2E step needs a per-rank batch that is a multiple of the utterances per speaker")
         c_rank = dict(cfg)
         c_rank["seed"] = cfg["seed"] + self.rank        # every rank owns different sequences
         x_host = make_input(c_rank, B).pin_memory()
@@ -347,6 +360,13 @@ class GpuBench(object):
                 return res[1][0] if cfg["cell"] == "lstm" else res[1]
             for p in params:
                 p.grad = None
+            if ge2e:
+                embeds = enc(x)
+                loss, _ = enc.loss(embeds.view(B // ge2e[1], ge2e[1], -1), group=(dist.group.WORLD if dist is not None else None))
+                loss.backward()
+                if dist is not None:
+                    allreduce_gradients(params)
+                return loss
             res = model(x)
             out = res[0]
             hT = res[1][0] if cfg["cell"] == "lstm" else res[1]
@@ -512,7 +532,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--headline", type=int, default=3, choices=sorted(CONFIGS))
     ap.add_argument("--config", type=int, default=0, help="shorthand: headline = this config and run only it")
-    ap.add_argument("--configs", default="1,2,3,4,5,6,7,8", help="configs measured into all_configs")
+    ap.add_argument("--configs", default="1,2,3,4,5,6,7,8,9", help="configs measured into all_configs")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the global batch of the headline config (profiling)")
     ap.add_argument("--seq-len", type=int, default=0, help="override T of the headline config (profiling only)")
