@@ -136,6 +136,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
         : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+          "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+          "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+          "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+          "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrive on an mbarrier once every MMA issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -179,17 +194,36 @@ __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo) {
     lo.x = tf32_rna(v.x - hi.x); lo.y = tf32_rna(v.y - hi.y); lo.z = tf32_rna(v.z - hi.z); lo.w = tf32_rna(v.w - hi.w);
 }
 
+// gradient kernels: lo = x - hi left unrounded (the tensor core truncates it to TF32: error <= 2^-21 |x|, two ALU ops fewer)
+__device__ __forceinline__ void split4_trunc(const float4 v, float4 &hi, float4 &lo) {
+    hi.x = tf32_rna(v.x); hi.y = tf32_rna(v.y); hi.z = tf32_rna(v.z); hi.w = tf32_rna(v.w);
+    lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+}
+
 // one k-block (BK = 32 k-values, `nks` slices of 8) of the compensated product: hi*hi' into the main accumulator,
-// lo*hi' + hi*lo' into the small-term accumulator
+// lo*hi' + hi*lo' into the small-term accumulator.
+// Measured on B200 (tools/mma_rate_probe, round 2): back-to-back kind::tf32 MMAs into ONE 128 x 128 accumulator dispatch
+// every 67.5 clk (A from TMEM) / 77 clk (A from shared memory), but every change of accumulator between two consecutive
+// MMAs costs ~55 clk more (the per-k-slice order small, small, main ran at 104 / 117 clk per MMA).  So the MMAs of a k-block
+// are grouped by accumulator, and `main_first` alternates between k-blocks: one accumulator change per k-block.
 __device__ __forceinline__ void issue_block_3x(uint32_t d_main, uint32_t d_small, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
-                                               uint32_t b_lo, int nks, uint32_t idesc, bool first_main, bool first_small) {
+                                               uint32_t b_lo, int nks, uint32_t idesc, bool first_main, bool first_small,
+                                               bool main_first) {
     const uint64_t dah = umma_desc_sw128(a_hi), dal = umma_desc_sw128(a_lo);
     const uint64_t dbh = umma_desc_sw128(b_hi), dbl = umma_desc_sw128(b_lo);
-    for (int ks = 0; ks < nks; ++ks) {
-        const uint64_t o = (uint64_t)(ks * 2);                  // 32 B per k-slice, in 16-byte units
-        umma_tf32(d_small, dal + o, dbh + o, idesc, (first_small && ks == 0) ? 0u : 1u);
-        umma_tf32(d_small, dah + o, dbl + o, idesc, 1u);
-        umma_tf32(d_main, dah + o, dbh + o, idesc, (first_main && ks == 0) ? 0u : 1u);
+    for (int pass = 0; pass < 2; ++pass) {
+        if ((pass == 0) == main_first) {
+            for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2);              // 32 B per k-slice, in 16-byte units
+                umma_tf32(d_main, dah + o, dbh + o, idesc, (first_main && ks == 0) ? 0u : 1u);
+            }
+        } else {
+            for (int ks = 0; ks < nks; ++ks) {
+                const uint64_t o = (uint64_t)(ks * 2);
+                umma_tf32(d_small, dal + o, dbh + o, idesc, (first_small && ks == 0) ? 0u : 1u);
+                umma_tf32(d_small, dah + o, dbl + o, idesc, 1u);
+            }
+        }
     }
 }
 
@@ -308,7 +342,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
                     const int krem = g.K - kb * BK;
                     const int nks = krem >= BK ? BK / 8 : (krem + 7) / 8;
                     issue_block_3x(tmem_base + acc * 2 * BN, tmem_base + acc * 2 * BN + BN, st, st + TILE_BYTES,
-                                   st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, nks, idesc, kb == 0, kb == 0);
+                                   st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, nks, idesc, kb == 0, kb == 0, (kb & 1) != 0);
                     umma_commit(bar_empty(s));
                 }
                 umma_commit(bar_tfull(acc));
@@ -484,7 +518,7 @@ k_tc_red(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtensorMa
                 tc_fence_after();
                 const uint32_t st = op0 + s * RED_OP_BYTES;
                 issue_block_3x(tmem_base + ab * BN, tmem_base + 2 * BN, st, st + TILE_BYTES, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES,
-                               BK / 8, idesc, seg_first, i == 0);
+                               BK / 8, idesc, seg_first, i == 0, (i & 1) != 0);
                 umma_commit(bar_oempty(s));
                 if (seg_last) umma_commit(bar_afull(ab));
             }
@@ -672,12 +706,20 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
                 const uint64_t dbh = umma_desc_sw128(st), dbl = umma_desc_sw128(st + TILE_BYTES);
                 const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
                 const uint32_t d_main = tmem_base + ab * BN, d_small = tmem_base + 2 * BN;
+                // grouped by accumulator, order alternating between k-blocks (see issue_block_3x)
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    const uint64_t o = (uint64_t)(ks * 2);
-                    umma_tf32_ts(d_small, a_lo + ks * 8, dbh + o, idesc, (i == 0 && ks == 0) ? 0u : 1u);
-                    umma_tf32_ts(d_small, a_hi + ks * 8, dbl + o, idesc, 1u);
-                    umma_tf32_ts(d_main, a_hi + ks * 8, dbh + o, idesc, (seg_first && ks == 0) ? 0u : 1u);
+                for (int pass = 0; pass < 2; ++pass) {
+                    if ((pass == 0) == ((i & 1) != 0)) {
+#pragma unroll
+                        for (int ks = 0; ks < BK / 8; ++ks)
+                            umma_tf32_ts(d_main, a_hi + ks * 8, dbh + (uint64_t)(ks * 2), idesc, (seg_first && ks == 0) ? 0u : 1u);
+                    } else {
+#pragma unroll
+                        for (int ks = 0; ks < BK / 8; ++ks) {
+                            umma_tf32_ts(d_small, a_lo + ks * 8, dbh + (uint64_t)(ks * 2), idesc, (i == 0 && ks == 0) ? 0u : 1u);
+                            umma_tf32_ts(d_small, a_hi + ks * 8, dbl + (uint64_t)(ks * 2), idesc, 1u);
+                        }
+                    }
                 }
                 umma_commit(bar_oempty(s));
                 if (seg_last) umma_commit(bar_afull(ab));
@@ -691,23 +733,20 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
             const uint32_t rph = (uint32_t)((i / RTS_RAW_STAGES) & 1), oph = (uint32_t)((i / RTS_OP_STAGES) & 1);
             mbar_wait(bar_rfull(rs), rph);
             const float *rawA = reinterpret_cast<const float *>(gbase + rs * RED_RAW_BYTES);
-            float v[32];
+            // split into registers BEFORE waiting for the operand stage: the ALU work overlaps the MMAs of the previous
+            // k-block and only the TMEM stores stay on the oempty -> ofull critical path
+            float hi[32], lo[32];
 #pragma unroll
-            for (int r = 0; r < 32; ++r) v[r] = rawA[r * 128 + m];
+            for (int r = 0; r < 32; ++r) {
+                const float x = rawA[r * 128 + m];
+                hi[r] = tf32_rna(x);
+                lo[r] = x - hi[r];                           // exact; kind::tf32 ignores the low 13 mantissa bits (<= 2^-21 |x|)
+            }
             mbar_wait(bar_oempty(os), oph ^ 1u);             // the MMAs that read this A stage have completed
             tc_fence_after();
             const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + A_COL0 + (uint32_t)os * 64u;
-#pragma unroll
-            for (int hhalf = 0; hhalf < 2; ++hhalf) {
-                float hi[16], lo[16];
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    hi[r] = tf32_rna(v[hhalf * 16 + r]);
-                    lo[r] = tf32_rna(v[hhalf * 16 + r] - hi[r]);
-                }
-                tmem_st16(ta + hhalf * 16, hi);
-                tmem_st16(ta + 32 + hhalf * 16, lo);
-            }
+            tmem_st32(ta, hi);
+            tmem_st32(ta + 32, lo);
             tmem_wait_st();
             mbar_arrive(bar_rempty(rs));                     // after the values were consumed (see k_tc_red)
             tc_fence_before();
@@ -723,18 +762,21 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
             const uint32_t rph = (uint32_t)((i / RTS_RAW_STAGES) & 1), oph = (uint32_t)((i / RTS_OP_STAGES) & 1);
             mbar_wait(bar_rfull(rs), rph);
             const float *rawB = reinterpret_cast<const float *>(gbase + rs * RED_RAW_BYTES + TILE_BYTES);
-            mbar_wait(bar_oempty(os), oph ^ 1u);
-            uint8_t *op = gbase + (op0 - base) + os * RTS_OP_BYTES;
+            float4 h[8], l[8];
 #pragma unroll
             for (int rq = 0; rq < 8; ++rq) {
                 const float4 vb = make_float4(rawB[(rq * 4 + 0) * 128 + col], rawB[(rq * 4 + 1) * 128 + col],
                                               rawB[(rq * 4 + 2) * 128 + col], rawB[(rq * 4 + 3) * 128 + col]);
                 if (want_bias) bsum += (vb.x + vb.y) + (vb.z + vb.w);
+                split4_trunc(vb, h[rq], l[rq]);
+            }
+            mbar_wait(bar_oempty(os), oph ^ 1u);
+            uint8_t *op = gbase + (op0 - base) + os * RTS_OP_BYTES;
+#pragma unroll
+            for (int rq = 0; rq < 8; ++rq) {
                 const int off = col * 128 + ((rq ^ (col & 7)) << 4);
-                float4 h, l;
-                split4(vb, h, l);
-                *reinterpret_cast<float4 *>(op + off) = h;
-                *reinterpret_cast<float4 *>(op + TILE_BYTES + off) = l;
+                *reinterpret_cast<float4 *>(op + off) = h[rq];
+                *reinterpret_cast<float4 *>(op + TILE_BYTES + off) = l[rq];
             }
             mbar_arrive(bar_rempty(rs));
             fence_proxy_async();
