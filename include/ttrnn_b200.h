@@ -219,7 +219,7 @@ int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K
 int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain_macs_per_row,
                        int64_t *dense_macs_per_row);
 
-/* Execution plan of `desc` under the current options, as text: first line "chunk_steps=.. sms=.. tc_gemm=.. rank_padded=..", then one
+/* Execution plan of `desc` under the current options, as text: first line "chunk_steps=.. sms=.. tc_gemm=.. rank_padded=.. bwd_overlap=..", then one
  * line per layer of key=value pairs (ih_route, ih_fwd_tc / ih_dw_tc = tensor-core GEMMs used, fwd_kernel, fwd_rows =
  * batch rows per CTA, save_mode, and with training != 0: bwd_kernel, bwd_rows, bwd_phase_rows, optional second phase,
  * hh_dw, hh_dw_tc).  Needs a CUDA device (the plan depends on its SM count).  Returns characters written, < 0 on error. */
@@ -256,6 +256,13 @@ int ttrnn_static_kernel_table(char *buf, int32_t cap);
  *                   3xTF32 split, TMA-staged operands, TMEM accumulators) where the shape fits; 0 = FP32 FFMA kernels
  *   "tc_red_ts"     1 (default) = the reduction GEMM takes its A operand from TMEM (tcgen05.st + the TS form of tcgen05.mma),
  *                   which leaves room for five raw TMA stages; 0 = both operands from shared memory (3 % slower, same results)
+ *   "tc_rows_ts"    1 (default) = the row GEMMs (ih projection, dX) with K >= 128 take their A operand from TMEM as well;
+ *                   0 = both operands from shared memory for every K (4-8 % slower at K >= 256, same results)
+ *   "bwd_overlap"   1 (default) = multi-layer backward of a single-chunk plan: the weight-gradient work of layer l (dW GEMMs,
+ *                   projections onto the cores, partial folds) runs on an internal second stream under the BPTT kernel of
+ *                   layer l - 1, planned for the SMs that kernel leaves idle; the second stream is forked from and joined back
+ *                   into the caller's stream inside ttrnn_rnn_backward (capturable).  Costs a second set of the per-layer
+ *                   backward scratch buffers.  0 = everything on the caller's stream
  *   "save_bytes"    budget for keeping chain activations of two-core chains for backward instead of
  *                   recomputing them (default 0 = recompute)
  * returns 0 if the key is known. */

@@ -184,6 +184,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// one lane of a fully converged warp (elect.sync).  The MMA issuer must be selected THIS way: under `if (lane == 0)` ptxas
+// wraps every UTCHMMA in a per-lane ELECT / BRA.U.ANY loop (it cannot prove the branch selects one lane), which costs ~100
+// clk of issue time per MMA on a shared scheduler -- more than the 64 clk the tensor core needs for it (measured, round 2)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -264,6 +277,9 @@ struct TcRowsArgs {
     long long c_bstride;
     int c_ld;
     const float *bias, *bias2;
+#ifdef TC_PROBE
+    long long *probe;
+#endif
 };
 
 __global__ void __launch_bounds__(ROWS_NT, 1)
@@ -305,7 +321,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
 
     if (warp == 12) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
             long long it = 0;
             for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
@@ -326,7 +342,7 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
         }
     } else if (warp == 13) {
         // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        if (elect_one()) {
             long long it = 0, nt = 0;
             for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++nt) {
                 const int acc = (int)(nt & 1);
@@ -418,6 +434,230 @@ k_tc_rows(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensor
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_tc_rows_ts: k_tc_rows with the A operand in TMEM (tcgen05.mma "TS" form), the default.  k_tc_rows moves 192 KB through
+// the shared-memory port per k-block (TMA 48, split load 16 + stores 32, three MMAs per k-slice reading A and B: 96), which
+// is what bounds it; here row m of the raw A tile is split into TMEM lane m (tcgen05.st) and only Bt is read from shared
+// memory by the MMAs: 112 KB per k-block, and a fourth TMA stage fits.
+// TMEM columns: [0,128) [128,256) main accumulators (double-buffered across tiles), [256,384) small terms (single: the
+// epilogue reads it first and hands it back before it touches the main accumulator), [384,512) two A stages (hi 32 | lo 32).
+// warps 0-3: A splitters; 8-15: epilogue (lane quarter = warp % 4, 64 columns each); 16: TMA; 17: MMA issuer + TMEM allocator
+// GRAD: the lo term is left unrounded (gradient tolerance 1e-4; see split4_trunc)
+// ---------------------------------------------------------------------------------------------------
+constexpr int RWT_STAGES = 4;
+constexpr int RWT_NT = 576;
+constexpr int RWT_STAGE_BYTES = 3 * TILE_BYTES;              // raw A, Bt hi, Bt lo
+constexpr int RWT_SMEM = RWT_STAGES * RWT_STAGE_BYTES + 1024 + 256;
+
+template <bool GRAD>
+__global__ void __launch_bounds__(RWT_NT, 1)
+k_tc_rows_ts(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUtensorMap tmA,
+             const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gbase = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + RWT_STAGES * RWT_STAGE_BYTES;
+    // full[s] (TMA landed), empty[s] (MMAs of the stage done + raw A consumed), aready[o] / afree[o] (A operand stage in
+    // TMEM), tfull[a] / tempty[a] (main accumulator), sfree (small-term accumulator read by the epilogue)
+    auto bar_full = [&](int s) { return bars + 8u * s; };
+    auto bar_empty = [&](int s) { return bars + 8u * (RWT_STAGES + s); };
+    auto bar_aready = [&](int o) { return bars + 8u * (2 * RWT_STAGES + o); };
+    auto bar_afree = [&](int o) { return bars + 8u * (2 * RWT_STAGES + 2 + o); };
+    auto bar_tfull = [&](int a) { return bars + 8u * (2 * RWT_STAGES + 4 + a); };
+    auto bar_tempty = [&](int a) { return bars + 8u * (2 * RWT_STAGES + 6 + a); };
+    const uint32_t bar_sfree = bars + 8u * (2 * RWT_STAGES + 8);
+    const uint32_t tmem_slot = bars + 8u * (2 * RWT_STAGES + 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RWT_STAGES; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 129); }
+        for (int o = 0; o < 2; ++o) { mbar_init(bar_aready(o), 128); mbar_init(bar_afree(o), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull(a), 1); mbar_init(bar_tempty(a), 256); }
+        mbar_init(bar_sfree, 256);
+        fence_barrier_init();
+    }
+    if (warp == 17) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    constexpr uint32_t A_COL0 = 3 * BN;
+    const int nkb = (g.K + BK - 1) / BK;
+
+    if (warp == 16) {
+        // ---------------- TMA producer ----------------
+        if (elect_one()) {
+            tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+            long long it = 0;
+            for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+                const long long box = tile / g.tiles_n;
+                const int n0 = (int)(tile % g.tiles_n) * BN;
+                const int b0 = (int)(box / g.g.tpb) * g.g.nbx, t0 = (int)(box % g.g.tpb) * g.g.rb;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = (int)(it % RWT_STAGES);
+                    const uint32_t ph = (uint32_t)((it / RWT_STAGES) & 1);
+                    mbar_wait(bar_empty(s), ph ^ 1u);
+                    const uint32_t st = base + s * RWT_STAGE_BYTES;
+                    mbar_arrive_expect_tx(bar_full(s), (uint32_t)(g.g.rb * g.g.nbx * BK * 4 + 2 * TILE_BYTES));
+                    tma_load_3d(st, &tmA, bar_full(s), kb * BK, t0, b0);
+                    tma_load_3d(st + TILE_BYTES, &tmBhi, bar_full(s), kb * BK, n0, 0);
+                    tma_load_3d(st + 2 * TILE_BYTES, &tmBlo, bar_full(s), kb * BK, n0, 0);
+                }
+            }
+        }
+    } else if (warp == 17) {
+        // ---------------- MMA issuer ----------------
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_tf32(BM, BN);
+            const uint32_t d_small = tmem_base + 2 * BN;
+            long long it = 0, nt = 0;
+#ifdef TC_PROBE
+            long long w_tempty = 0, w_full = 0, w_aready = 0, w_sfree = 0, t_issue = 0, tq;
+            const long long t_begin = clock64();
+#define PROBE(acc_, stmt) tq = clock64(); stmt; acc_ += clock64() - tq;
+#else
+#define PROBE(acc_, stmt) stmt;
+#endif
+            for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++nt) {
+                const int acc = (int)(nt & 1);
+                const uint32_t d_main = tmem_base + acc * BN;
+                PROBE(w_tempty, mbar_wait(bar_tempty(acc), (uint32_t)(((nt >> 1) & 1) ^ 1)))
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = (int)(it % RWT_STAGES), o = (int)(it & 1);
+                    PROBE(w_full, mbar_wait(bar_full(s), (uint32_t)((it / RWT_STAGES) & 1)))
+                    PROBE(w_aready, mbar_wait(bar_aready(o), (uint32_t)((it >> 1) & 1)))
+                    tc_fence_after();
+#ifdef TC_PROBE
+                    const long long ti0 = clock64();
+#endif
+                    const uint32_t st = base + s * RWT_STAGE_BYTES;
+                    const uint64_t dbh = umma_desc_sw128(st + TILE_BYTES), dbl = umma_desc_sw128(st + 2 * TILE_BYTES);
+                    const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)o * 64u, a_lo = a_hi + 32u;
+                    const int krem = g.K - kb * BK;
+                    const int nks = krem >= BK ? BK / 8 : (krem + 7) / 8;
+                    // grouped by accumulator (see issue_block_3x); the first k-block of a tile starts with the main products so
+                    // that the tensor core has work while the epilogue of the previous tile still reads the small-term accumulator
+                    const bool main_first = (kb & 1) == 0;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if ((pass == 0) == main_first) {
+                            for (int ks = 0; ks < nks; ++ks)
+                                umma_tf32_ts(d_main, a_hi + ks * 8, dbh + (uint64_t)(ks * 2), idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                        } else {
+                            if (kb == 0) {
+                                PROBE(w_sfree, mbar_wait(bar_sfree, (uint32_t)((nt & 1) ^ 1)))
+                                tc_fence_after();
+                            }
+                            for (int ks = 0; ks < nks; ++ks) {
+                                umma_tf32_ts(d_small, a_lo + ks * 8, dbh + (uint64_t)(ks * 2), idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+                                umma_tf32_ts(d_small, a_hi + ks * 8, dbl + (uint64_t)(ks * 2), idesc, 1u);
+                            }
+                        }
+                    }
+                    umma_commit(bar_empty(s));
+                    umma_commit(bar_afree(o));
+#ifdef TC_PROBE
+                    t_issue += clock64() - ti0;
+#endif
+                }
+                umma_commit(bar_tfull(acc));
+            }
+#ifdef TC_PROBE
+            if (blockIdx.x == 3 && g.probe) {
+                g.probe[0] = clock64() - t_begin; g.probe[1] = w_tempty; g.probe[2] = w_full; g.probe[3] = w_aready;
+                g.probe[4] = w_sfree; g.probe[5] = t_issue; g.probe[6] = it;
+            }
+#endif
+        }
+    } else if (warp < 4) {
+        // ---------------- A splitters: row m of the raw K-major (128-byte swizzled) tile -> TMEM lane m ----------------
+        const int m = warp * 32 + lane;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x) {
+            for (int kb = 0; kb < nkb; ++kb, ++it) {
+                const int s = (int)(it % RWT_STAGES), o = (int)(it & 1);
+                mbar_wait(bar_full(s), (uint32_t)((it / RWT_STAGES) & 1));
+                const uint8_t *row = gbase + s * RWT_STAGE_BYTES + m * 128;
+                float hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 v = *reinterpret_cast<const float4 *>(row + ((c ^ (m & 7)) << 4));
+                    float4 h, l;
+                    if (GRAD) split4_trunc(v, h, l); else split4(v, h, l);
+                    hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
+                    lo[4 * c] = l.x; lo[4 * c + 1] = l.y; lo[4 * c + 2] = l.z; lo[4 * c + 3] = l.w;
+                }
+                mbar_wait(bar_afree(o), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t ta = tmem_base + ((uint32_t)(warp * 32) << 16) + A_COL0 + (uint32_t)o * 64u;
+                tmem_st32(ta, hi);
+                tmem_st32(ta + 32, lo);
+                tmem_wait_st();
+                mbar_arrive(bar_empty(s));                   // raw A consumed (after the stores that take the loaded registers)
+                tc_fence_before();
+                mbar_arrive(bar_aready(o));
+            }
+        }
+    } else if (warp >= 8 && warp < 16) {
+        // ---------------- epilogue: small terms first (hand the accumulator back), then main + small (+ bias) -> global ------
+        const int q = warp & 3, ch = (warp - 8) >> 2;
+        const int i = q * 32 + lane;
+        const int bi = i / g.g.rb, ti = i - bi * g.g.rb;
+        const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 64);
+        long long nt = 0;
+        for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++nt) {
+            const int acc = (int)(nt & 1);
+            const long long box = tile / g.tiles_n;
+            const int n0 = (int)(tile % g.tiles_n) * BN + ch * 64;
+            const int b = (int)(box / g.g.tpb) * g.g.nbx + bi, t = (int)(box % g.g.tpb) * g.g.rb + ti;
+            const bool ok = bi < g.g.nbx && b < g.g.nb && t < g.g.rpb;
+            float *crow = g.c + (long long)b * g.c_bstride + (long long)t * g.c_ld + n0;
+            mbar_wait(bar_tfull(acc), (uint32_t)((nt >> 1) & 1));
+            tc_fence_after();
+            float w[64];
+            {
+                float v[32];
+                tmem_ld32(tl + (uint32_t)(2 * BN), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[j] = v[j];
+                tmem_ld32(tl + (uint32_t)(2 * BN + 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) w[32 + j] = v[j];
+            }
+            tc_fence_before();
+            mbar_arrive(bar_sfree);
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                float v[32];
+                tmem_ld32(tl + (uint32_t)(acc * BN + cc * 32), v);
+                if (cc == 1) {                               // both halves of the main accumulator are in registers
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty(acc));
+                }
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 o4 = make_float4(v[4 * j] + w[cc * 32 + 4 * j], v[4 * j + 1] + w[cc * 32 + 4 * j + 1],
+                                                v[4 * j + 2] + w[cc * 32 + 4 * j + 2], v[4 * j + 3] + w[cc * 32 + 4 * j + 3]);
+                        if (g.bias) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias + n0 + cc * 32) + j);
+                            o4.x += bb.x; o4.y += bb.y; o4.z += bb.z; o4.w += bb.w;
+                        }
+                        if (g.bias2) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(g.bias2 + n0 + cc * 32) + j);
+                            o4.x += bb.x; o4.y += bb.y; o4.z += bb.z; o4.w += bb.w;
+                        }
+                        reinterpret_cast<float4 *>(crow + cc * 32)[j] = o4;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // k_tc_red:  part[s][m, n] = sum_{r in k-blocks of split s} A[r, m] B[r, n];  pbias[s][n] = sum_r B[r, n]
 //   A : ragged rows x M, B : ragged rows x N (FP32).  The contraction runs over ROWS, so both operands are MN-major
 //   in memory: TMA delivers raw [32 rows][128] tiles (no swizzle) and the splitter warps write the hi / lo operand tiles
@@ -487,7 +727,7 @@ k_tc_red(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtensorMa
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     if (warp == 16) {
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
             const uint32_t box_bytes = (uint32_t)(g.g.rb * g.g.nbx * 128 * 4);
             for (long long i = 0; i < nkb; ++i) {
@@ -502,7 +742,7 @@ k_tc_red(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtensorMa
             }
         }
     } else if (warp == 17) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN);
             for (long long i = 0; i < nkb; ++i) {
                 const long long seg = i / RED_SEG;
@@ -673,7 +913,7 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
     constexpr uint32_t A_COL0 = 3 * BN;                     // TMEM columns of the A stages
 
     if (warp == 16) {
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB);
             const uint32_t box_bytes = (uint32_t)(g.g.rb * g.g.nbx * 128 * 4);
             for (long long i = 0; i < nkb; ++i) {
@@ -688,7 +928,7 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
             }
         }
     } else if (warp == 17) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN);
             for (long long i = 0; i < nkb; ++i) {
                 const long long seg = i / RED_SEG;
@@ -869,9 +1109,21 @@ inline bool tc_rows_ok(long long rows, int K, int N) { return rows >= 128 && K >
 inline bool tc_red_ok(long long rows, int M, int N) { return rows >= 256 && M >= 64 && M % 4 == 0 && N % BN == 0; }
 
 // C = A * Bt^T (+ biases); bt_hi / bt_lo: N x K pre-split copies of Bt
+// 1 (default) = A operand from TMEM (k_tc_rows_ts) when K >= 128; 0 = both operands from shared memory (k_tc_rows).
+// Measured on B200 (tools/tc_gemm_test, round 2, after the elect.sync issuer fix; rows 102 400 / 262 144):
+//   K 256 N 1024: 0.353 vs 0.380 ms (152 vs 141 TFLOP/s)   K 1024 N 256: 0.278 vs 0.302 (193 vs 178)
+//   K 256 N 4096: 3.414 vs 3.586 (161 vs 153)               K 40 N 1024: 0.222 vs 0.187 (epilogue-bound: shared-memory variant)
+// Instrumented (-DTC_PROBE: clock64 around every wait of the MMA issuer): with K = 256 the issuer waits ~500 clk per k-block
+// for the A operand stage -- the splitters' tcgen05.st queue behind the epilogue's tcgen05.ld (128 KB of accumulator reads per
+// tile at 64 B/clk) -- and ~170 clk with K = 1024, where the MMAs run back to back (issue time = 12 x 65 clk per k-block).
+inline int &tc_rows_variant() { static int v = 1; return v; }
+#ifdef TC_PROBE
+inline long long *&tc_probe_buf() { static long long *p = nullptr; return p; }
+#endif
+
 inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_bstride, int K, const float *bt_hi,
                           const float *bt_lo, int N, const float *bias, const float *bias2, float *c, long long c_bstride,
-                          int sms, cudaStream_t st) {
+                          int sms, cudaStream_t st, bool grad = false) {
     long long rp, nb, abs_, cbs, rp2, nb2;
     rag_dims(rows, rpb, a_bstride, K, &rp, &nb, &abs_);
     rag_dims(rows, rpb, c_bstride, N, &rp2, &nb2, &cbs);
@@ -881,6 +1133,9 @@ inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_b
     g.K = K; g.N = N; g.tiles_n = N / BN;
     g.ntiles = g.g.nboxes * g.tiles_n;
     g.c = c; g.c_bstride = cbs; g.c_ld = N; g.bias = bias; g.bias2 = bias2;
+#ifdef TC_PROBE
+    g.probe = tc_probe_buf();
+#endif
     CUtensorMap tmA, tmBh, tmBl;
     int rc = make_map(&tmA, a, K, rp, nb, K, abs_, BK, g.g.rb, g.g.nbx, true);
     if (rc) return rc;
@@ -889,11 +1144,17 @@ inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_b
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, ROWS_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_rows_ts<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, RWT_SMEM);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tc_rows_ts<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, RWT_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr = true;
     }
     long long grid = g.ntiles < sms ? g.ntiles : sms;
-    k_tc_rows<<<(unsigned)grid, ROWS_NT, ROWS_SMEM, st>>>(g, tmA, tmBh, tmBl);
+    // short K: a tile is one or two k-blocks and the kernel is epilogue-bound; the single small-term accumulator of the TMEM
+    // variant then stalls the MMAs (measured K = 40: 0.222 vs 0.187 ms)
+    if (!tc_rows_variant() || K < 128) k_tc_rows<<<(unsigned)grid, ROWS_NT, ROWS_SMEM, st>>>(g, tmA, tmBh, tmBl);
+    else if (grad) k_tc_rows_ts<true><<<(unsigned)grid, RWT_NT, RWT_SMEM, st>>>(g, tmA, tmBh, tmBl);
+    else k_tc_rows_ts<false><<<(unsigned)grid, RWT_NT, RWT_SMEM, st>>>(g, tmA, tmBh, tmBl);
     return (int)cudaGetLastError();
 }
 

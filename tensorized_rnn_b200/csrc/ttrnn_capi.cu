@@ -52,6 +52,10 @@ std::atomic<long long> g_opt_dense_ratio{130};
 std::atomic<long long> g_opt_tc_gemm{1};
 // zero-pad TT ranks that are not multiples of 4 so that the static kernels apply (make_eff_desc); 0 = runtime-shape kernels
 std::atomic<long long> g_opt_rank_pad{1};
+// multi-layer backward: run the weight-gradient work of layer l (dW GEMMs, projections onto the cores, partial folds) on a
+// second stream, on the SMs the BPTT kernel of layer l - 1 leaves idle (its grid is rows / rows-per-CTA, e.g. 98 of 148 at
+// cfg3).  Needs a second set of the per-layer scratch buffers; single-chunk plans only.  0 = everything on the caller's stream
+std::atomic<long long> g_opt_bwd_overlap{1};
 
 // Snapshot of every option that decides a buffer layout or a kernel route.  ttrnn_rnn_workspace_bytes() takes it from the
 // process-wide options and stamps it into ttrnn_rnn_workspace.plan; forward and backward run from THAT copy, so a
@@ -59,7 +63,7 @@ std::atomic<long long> g_opt_rank_pad{1};
 // the scratch buffers are interpreted.  Helpers read the calling thread's current snapshot `t_opt`.
 struct Opts {
     long long rows, chunk, chunk_bytes, stat, srows_fwd, srows_bwd, save_bytes, save_u_bytes, row_plan, dense_ih, gemm_wide,
-        dense_hh, split_kept, dense_ratio, tc_gemm, rank_pad;
+        dense_hh, split_kept, dense_ratio, tc_gemm, rank_pad, bwd_overlap;
 };
 constexpr int kOptFields = sizeof(Opts) / sizeof(long long);
 constexpr long long kPlanMagic = 0x7474726E6E706C33LL;          // "ttrnnpl3"
@@ -73,7 +77,7 @@ Opts snapshot_options() {
     o.save_bytes = g_opt_save_bytes.load(); o.save_u_bytes = g_opt_save_u_bytes.load(); o.row_plan = g_opt_row_plan.load();
     o.dense_ih = g_opt_dense_ih.load(); o.gemm_wide = g_opt_gemm_wide.load(); o.dense_hh = g_opt_dense_hh.load();
     o.split_kept = g_opt_split_kept.load(); o.dense_ratio = g_opt_dense_ratio.load(); o.tc_gemm = g_opt_tc_gemm.load();
-    o.rank_pad = g_opt_rank_pad.load();
+    o.rank_pad = g_opt_rank_pad.load(); o.bwd_overlap = g_opt_bwd_overlap.load();
     return o;
 }
 void plan_store(const Opts &o, int64_t *plan) {
@@ -450,6 +454,9 @@ struct RnnLayout {
     long long b_xg = 0, b_dhs = 0, b_sdh = 0, b_sdc = 0, b_part_hh = 0, b_part_ih = 0, b_spill = 0, b_aux = 0, b_dense = 0, b_dense_hh = 0, b_total = 0;
     long long part_stride = 0;  // floats per partial slot
     int nslots = 0;
+    // backward overlap: the per-layer buffers (everything from b_xg on) exist twice, set (l & 1) at + set * set_stride
+    int overlap = 0;
+    long long set_stride = 0;
     // kept chain activations (two-core static chains, within the save_bytes budget): per layer offsets into `saved`
     int save_mode[TTRNN_MAX_LAYERS] = {};
     long long sv_x0[TTRNN_MAX_LAYERS] = {}, sv_u[TTRNN_MAX_LAYERS] = {}, x0f[TTRNN_MAX_LAYERS] = {};
@@ -528,10 +535,11 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     lo->part_stride = r4(maxp);
     lo->nslots = dv.sms * kMaxSlotsPerSM;
     o = 0;
-    lo->b_xg = o; o += lo->xg_floats;
     lo->b_dhs = o; o += (L > 1 ? 2 * r4(lo->BTH) : 0);
     lo->b_sdh = o; o += r4(lo->BH);
     lo->b_sdc = o; o += r4(lo->BH);
+    const long long set_base = o;                         // per-layer buffers from here on
+    lo->b_xg = o; o += lo->xg_floats;
     lo->b_part_hh = o; o += lo->part_stride * lo->nslots;
     lo->b_part_ih = o; o += lo->part_stride * lo->nslots;
     // spill area for backward X_k slots that do not fit in shared memory (worst layer, either kernel)
@@ -559,6 +567,11 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
                 dhh = dense_bwd_floats(rp.layer[l].hh);
         }
     lo->b_dense_hh = o; o += dhh;
+    lo->overlap = (t_opt.bwd_overlap && t_opt.stat && L > 1 && tc == T) ? 1 : 0;
+    if (lo->overlap) {
+        lo->set_stride = r4(o - set_base);
+        o = set_base + 2 * lo->set_stride;
+    }
     lo->b_total = o;
     return 0;
 }
@@ -744,7 +757,7 @@ int dense_rows_gemm(int kind, const DevInfo &dv, long long rows, int rpb, const 
         int rc;
         {
             KernelTimer tm(kind, st);
-            rc = ttc::launch_tc_rows(rows, rpb, a, a_bstride, K, bt_hi, bt_lo, N, bias, bias2, c, c_bstride, dv.sms, st);
+            rc = ttc::launch_tc_rows(rows, rpb, a, a_bstride, K, bt_hi, bt_lo, N, bias, bias2, c, c_bstride, dv.sms, st, grad);
         }
         if (rc == 0) { ++g_launches; ++g_tc_launches; return 0; }
         if (rc > 0) return fail("k_tc_rows launch failed (code %d)", rc);
@@ -887,7 +900,9 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "dense_ih_ratio")) { g_opt_dense_ratio.store(value > 0 ? value : 130); return 0; }
     if (!strcmp(key, "tc_gemm")) { g_opt_tc_gemm.store(value); return 0; }
     if (!strcmp(key, "rank_pad")) { g_opt_rank_pad.store(value); return 0; }
+    if (!strcmp(key, "bwd_overlap")) { g_opt_bwd_overlap.store(value); return 0; }
     if (!strcmp(key, "tc_red_ts")) { ttc::tc_red_variant() = value ? 1 : 0; return 0; }   // A/B switch, not part of a plan
+    if (!strcmp(key, "tc_rows_ts")) { ttc::tc_rows_variant() = value ? 1 : 0; return 0; } // A/B switch, not part of a plan
     return 1;
 }
 
@@ -944,7 +959,7 @@ int ttrnn_rnn_describe(const ttrnn_rnn_desc *d_in, int32_t training, char *buf, 
             if (c == ' ') c = '_';
         return t;
     };
-    put("chunk_steps=%d sms=%d tc_gemm=%lld rank_padded=%d\n", lo.Tc, dv.sms, t_opt.tc_gemm, (int)eff.padded);
+    put("chunk_steps=%d sms=%d tc_gemm=%lld rank_padded=%d bwd_overlap=%d\n", lo.Tc, dv.sms, t_opt.tc_gemm, (int)eff.padded, lo.overlap);
     for (int l = 0; l < d->num_layers; ++l) {
         const LayerPlan &lp = rp.layer[l];
         const bool rank1 = (l == 0 && d->input_size == 1);
@@ -1185,6 +1200,28 @@ int ttrnn_rnn_forward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws,
     return 0;
 }
 
+// second stream + events of the backward overlap (one per host thread and device; created on first use, kept for the
+// life of the process).  Events carry no timing so that recording them is cheap.
+struct SideCtx {
+    int dev = -1;
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, fin = nullptr, done[2] = {nullptr, nullptr};
+};
+static SideCtx *side_ctx() {
+    thread_local SideCtx ctx[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideCtx &c = ctx[dev];
+    if (c.dev == dev) return &c;
+    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fin, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    for (int i = 0; i < 2; ++i)
+        if (cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    c.dev = dev;
+    return &c;
+}
+
 // body of ttrnn_rnn_backward on the effective (possibly rank-padded) descriptor
 static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const RnnLayout &lo, const DevInfo &dv, const float *x,
                              const float *h0, const float *c0, const float *params, const float *out, const void *saved,
@@ -1238,13 +1275,33 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
     if ((L > 1 || lstm) && !saved) return fail("backward needs the `saved` buffer written by a training forward");
     float *sc = (float *)scratch;
     const float *sv = (const float *)saved;
-    float *xg = sc + lo.b_xg;
     float *sdh = sc + lo.b_sdh, *sdc = sc + lo.b_sdc;
-    float *part_hh = sc + lo.b_part_hh, *part_ih = sc + lo.b_part_ih;
+    // backward overlap (build_layout): two sets of the per-layer buffers; `side` runs the deferred weight-gradient work
+    SideCtx *side = lo.overlap ? side_ctx() : nullptr;
+    bool set_busy[2] = {false, false};
+    // every exit path must give the caller's stream the side work back
+    struct Join {
+        SideCtx *side; cudaStream_t st; bool used;
+        ~Join() {
+            if (!side || !used) return;
+            cudaEventRecord(side->fin, side->s);
+            cudaStreamWaitEvent(st, side->fin, 0);
+        }
+    } join{side, st, false};
 
     for (int l = L - 1; l >= 0; --l) {
         const LayerPlan &lp = rp.layer[l];
         const int nin = lp.ih.n_in;
+        const int set = lo.overlap ? (l & 1) : 0;
+        float *ss = sc + (long long)set * lo.set_stride;      // this layer's buffer set
+        if (side && set_busy[set]) {                          // layer l + 2 used the same set
+            CU_CHECK(cudaStreamWaitEvent(st, side->done[set], 0));
+            set_busy[set] = false;
+        }
+        float *xg = ss + lo.b_xg;
+        float *part_hh = ss + lo.b_part_hh, *part_ih = ss + lo.b_part_ih;
+        cudaStream_t ws = st;                                 // stream of the weight-gradient work of this layer
+        DevInfo dvw = dv;                                     // ... and the SMs it may plan for
         const float *lin = (l == 0) ? x : sv + lo.sv_hs + (long long)(l - 1) * lo.BTH;
         const float *lout = (l == L - 1) ? out : sv + lo.sv_hs + (long long)l * lo.BTH;
         const float *lcs = lstm ? sv + lo.sv_cs + (long long)l * lo.BTH : nullptr;
@@ -1259,7 +1316,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
         const bool dense = mode == tts::MODE_XG && dense_ih_bwd_ok(lp.ih, dlin != nullptr, &d->ih[l]);
         DenseIh D;
         if (dense) {
-            dense_carve(sc + lo.b_dense, lp.ih, true, &D);
+            dense_carve(ss + lo.b_dense, lp.ih, true, &D);
             if (dense_prepare(lp.ih, &d->ih[l], dv, params + lp.off_ih_cores, D, dlin != nullptr,
                               tc_rows_use(B * (long long)lo.Tc, nin, GH, false),
                               dlin != nullptr && tc_rows_use(B * (long long)lo.Tc, GH, nin, true), st))
@@ -1275,27 +1332,30 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                                        &d->ih[l]);
         };
         // xg holds delta_ih of the chunk: core / bias gradients (accumulated over chunks) and dX
+        auto project_dx = [&](int t0, int tc) -> int {       // dense route: dX = delta W on the caller's stream
+            return dense_rows_gemm(TTRNN_K_GEMM_DX, dv, B * tc, tc, xg, (long long)tc * GH, GH, D.w, D.wt_hi, D.wt_lo, nin,
+                                   nullptr, nullptr, dlin + (long long)t0 * nin, (long long)T * nin, true, st);
+        };
+        bool dx_done = false;                                 // overlap: dX was issued before the fork
         auto project_bwd = [&](int t0, int tc, int *ih_used) -> int {
             if (dense) {
-                if (dense_dw(dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin, xg, (long long)tc * GH, GH,
-                             D, !dense_first, d->has_bias != 0, st))
+                if (dense_dw(dvw, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin, nin, xg, (long long)tc * GH, GH,
+                             D, !dense_first, d->has_bias != 0, ws))
                     return 1;
                 dense_first = false;
-                if (dlin)
-                    return dense_rows_gemm(TTRNN_K_GEMM_DX, dv, B * tc, tc, xg, (long long)tc * GH, GH, D.w, D.wt_hi, D.wt_lo,
-                                           nin, nullptr, nullptr, dlin + (long long)t0 * nin, (long long)T * nin, true, st);
+                if (dlin && !dx_done) return project_dx(t0, tc);
                 return 0;
             }
             return launch_ttlinear_bwd(lp.ih, dv, B * tc, tc, lin + (long long)t0 * nin, (long long)T * nin,
                                        params + lp.off_ih_cores, xg, (long long)tc * GH,
                                        dlin ? dlin + (long long)t0 * nin : nullptr, (long long)T * nin, part_ih,
-                                       lo.nslots, sc + lo.b_spill, 1, st, ih_used, &d->ih[l]);
+                                       lo.nslots, ss + lo.b_spill, 1, st, ih_used, &d->ih[l]);
         };
         // after the last chunk: dense dW^T -> TT cores (I-row TT-matvec backward on the identity), bias copy
         auto project_finish = [&](int *ih_used) -> int {
             if (!dense) return 0;
-            if (launch_ttlinear_bwd(lp.ih, dv, nin, nin, D.eye, 0, params + lp.off_ih_cores, D.dwt, 0, nullptr, 0, part_ih,
-                                    lo.nslots, sc + lo.b_spill, 0, st, ih_used, &d->ih[l]))
+            if (launch_ttlinear_bwd(lp.ih, dvw, nin, nin, D.eye, 0, params + lp.off_ih_cores, D.dwt, 0, nullptr, 0, part_ih,
+                                    lo.nslots, ss + lo.b_spill, 0, ws, ih_used, &d->ih[l]))
                 return 1;
             return 0;
         };
@@ -1386,7 +1446,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
             sa.partial = be->split ? nullptr : part_hh;
             if (be->saved == 1) { sa.x0_save = sv + lo.sv_x0[l]; sa.x0_bstride = (long long)T * lo.x0f[l]; }
             if (be->saved != 0) { sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * 4 * H; }
-            float *aux = sc + lo.b_aux;
+            float *aux = ss + lo.b_aux;
             float *aux_g = aux + r4(GH);
             float *one = aux_g + r4(GH);
             int ih_used = 0;
@@ -1394,7 +1454,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
             DenseIh DH;
             int hh_dense_calls = 0;
             if (dense_hh) {
-                dense_carve(sc + lo.b_dense_hh, lp.hh, true, &DH);
+                dense_carve(ss + lo.b_dense_hh, lp.hh, true, &DH);
                 ttg::k_eye<<<1024, 256, 0, st>>>(DH.eye, H);
                 ++g_launches;
                 CU_CHECK(cudaGetLastError());
@@ -1427,21 +1487,35 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                     sa.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
                     sa.dh_out = sdh; sa.dc_out = sdc;
                     if (launch_plan(sa)) return 1;
+                    if (getenv("TTRNN_DEBUG_OVERLAP"))
+                        fprintf(stderr, "[overlap] l=%d side=%d nchunks=%d dense=%d dlin=%d sms=%d sgrid=%d nph=%d\n", l, side != nullptr,
+                                nchunks, (int)dense, dlin != nullptr, dv.sms, sgrid, nph);
+                    if (side && l > 0 && nchunks == 1 && dense && dlin && dv.sms - sgrid >= 24) {
+                        // overlap: dX (the next layer's input) first, then everything that only produces parameter gradients
+                        // moves to the side stream, planned for the SMs the next BPTT kernel leaves idle
+                        if (project_dx(t0, tc)) return 1;
+                        dx_done = true;
+                        CU_CHECK(cudaEventRecord(side->fork, st));
+                        CU_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
+                        ws = side->s;
+                        join.used = true;
+                        dvw.sms = dv.sms - sgrid;
+                    }
                     if (be->split) {
                         // hh core gradients over rows (h_{t-1}, delta_t) of this chunk: dense accumulation of
                         // dW_hh^T = H_prev^T delta (projected onto the cores after the last chunk), or a batched
                         // TT-matvec backward (second chain pass) when the dense order is disabled / does not fit
                         auto hh_dw = [&](const float *xp, long long xbs, const float *dyp, long long rows, int rpb) {
                             if (dense_hh) {
-                                if (dense_dw(dv, rows, rpb, xp, xbs, H, dyp, (long long)tc * GH, GH, DH, hh_dense_calls > 0,
-                                             false, st))
+                                if (dense_dw(dvw, rows, rpb, xp, xbs, H, dyp, (long long)tc * GH, GH, DH, hh_dense_calls > 0,
+                                             false, ws))
                                     return 1;
                                 ++hh_dense_calls;
                                 return 0;
                             }
-                            return launch_ttlinear_bwd(lp.hh, dv, rows, rpb, xp, xbs, params + lp.off_hh_cores, dyp,
+                            return launch_ttlinear_bwd(lp.hh, dvw, rows, rpb, xp, xbs, params + lp.off_hh_cores, dyp,
                                                        (long long)tc * GH, nullptr, 0, part_hh, lo.nslots,
-                                                       sc + lo.b_spill, 0, st, &hh_used, &d->hh[l]);
+                                                       ss + lo.b_spill, 0, ws, &hh_used, &d->hh[l]);
                         };
                         if (t0 > 0) {
                             if (hh_dw(lout + (long long)(t0 - 1) * H, (long long)T * H, xg, B * tc, tc)) return 1;
@@ -1455,43 +1529,47 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                 if (project_finish(&ih_used)) return 1;
                 if (dense_hh && hh_dense_calls > 0) {
                     // dense dW_hh^T -> TT cores: H-row TT-matvec backward with the identity as input
-                    if (launch_ttlinear_bwd(lp.hh, dv, H, H, DH.eye, 0, params + lp.off_hh_cores, DH.dwt, 0, nullptr, 0,
-                                            part_hh, lo.nslots, sc + lo.b_spill, 0, st, &hh_used, &d->hh[l]))
+                    if (launch_ttlinear_bwd(lp.hh, dvw, H, H, DH.eye, 0, params + lp.off_hh_cores, DH.dwt, 0, nullptr, 0,
+                                            part_hh, lo.nslots, ss + lo.b_spill, 0, ws, &hh_used, &d->hh[l]))
                         return 1;
                 }
             }
             // fold the per-CTA slots into the gradient blob
             const long long cf = lp.hh.core_floats;
             if (be->split) {
-                if (reduce_partials(part_hh, hh_used, hhw_slot, 0, (int)cf, d_params + lp.off_hh_cores, st)) return 1;
-            } else if (reduce_partials(part_hh, sgrid, slot, 0, (int)cf, d_params + lp.off_hh_cores, st)) {
+                if (reduce_partials(part_hh, hh_used, hhw_slot, 0, (int)cf, d_params + lp.off_hh_cores, ws)) return 1;
+            } else if (reduce_partials(part_hh, sgrid, slot, 0, (int)cf, d_params + lp.off_hh_cores, ws)) {
                 return 1;
             }
             if (mode == tts::MODE_RANK1) {
                 if (d->has_bias) {
-                    if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, st)) return 1;
-                    if (reduce_partials(part_hh, sgrid, slot, cf + 2 * GH, GH, d_params + lp.off_ih_bias, st)) return 1;
+                    if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, ws)) return 1;
+                    if (reduce_partials(part_hh, sgrid, slot, cf + 2 * GH, GH, d_params + lp.off_ih_bias, ws)) return 1;
                 }
                 // gradient of the dense W_ih column -> TT cores of W_ih (one-row TT-matvec backward)
-                if (reduce_partials(part_hh, sgrid, slot, cf + GH, GH, aux_g, st)) return 1;
-                if (launch_ttlinear_bwd(lp.ih, dv, 1, 1, one, 0, params + lp.off_ih_cores, aux_g, 0, nullptr, 0, part_ih,
-                                        lo.nslots, sc + lo.b_spill, 0, st, &ih_used))
+                if (reduce_partials(part_hh, sgrid, slot, cf + GH, GH, aux_g, ws)) return 1;
+                if (launch_ttlinear_bwd(lp.ih, dvw, 1, 1, one, 0, params + lp.off_ih_cores, aux_g, 0, nullptr, 0, part_ih,
+                                        lo.nslots, ss + lo.b_spill, 0, ws, &ih_used))
                     return 1;
-                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
+                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, ws)) return 1;
             } else {
-                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, st)) return 1;
+                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, ws)) return 1;
                 if (d->has_bias) {
                     if (dense) {
-                        if (axpy1(D.dbias, d_params + lp.off_ih_bias, GH, 0, st)) return 1;
-                    } else if (reduce_partials(part_ih, ih_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, st)) {
+                        if (axpy1(D.dbias, d_params + lp.off_ih_bias, GH, 0, ws)) return 1;
+                    } else if (reduce_partials(part_ih, ih_used, ih_slot, lp.ih.core_floats, GH, d_params + lp.off_ih_bias, ws)) {
                         return 1;
                     }
                     if (lstm) {
-                        if (axpy1(d_params + lp.off_ih_bias, d_params + lp.off_hh_bias, GH, 0, st)) return 1;
+                        if (axpy1(d_params + lp.off_ih_bias, d_params + lp.off_hh_bias, GH, 0, ws)) return 1;
                     } else {
-                        if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, st)) return 1;
+                        if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, ws)) return 1;
                     }
                 }
+            }
+            if (ws != st) {                                   // the set stays busy until the side stream has passed this point
+                CU_CHECK(cudaEventRecord(side->done[set], ws));
+                set_busy[set] = true;
             }
             if (d_h0 && axpy1(sdh, d_h0, lo.BH, l != L - 1, st)) return 1;
             if (lstm && d_c0 && axpy1(sdc, d_c0, lo.BH, l != L - 1, st)) return 1;
@@ -1505,7 +1583,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
         a.p = cfg.p;
         const int R = cfg.R;
         a.R = R;
-        a.spill = cfg.spill > 0 ? sc + lo.b_spill : nullptr;
+        a.spill = cfg.spill > 0 ? ss + lo.b_spill : nullptr;
         fill_tiles(cfg.p, R, a.tile, a.tile_bd, a.mg);
         a.cell = d->cell; a.H = H; a.G = G; a.B = B; a.T = T;
         a.cores = params + lp.off_hh_cores;

@@ -31,7 +31,7 @@ DEV = "cuda:0"
 def options(**kw):
     """Set library options for the duration of a block; restore the defaults afterwards."""
     defaults = {"chunk_steps": 0, "save_u_bytes": 16 << 30, "tc_gemm": 1, "static_rows_fwd": 0, "static_rows_bwd": 0,
-                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1, "tc_red_ts": 1}
+                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1, "tc_red_ts": 1, "bwd_overlap": 1, "tc_rows_ts": 1}
     lib = _lib.load()
     for k, v in kw.items():
         assert lib.ttrnn_set_option(k.encode(), int(v)) == 0, k
@@ -369,3 +369,47 @@ def test_reduction_gemm_with_both_operands_in_shared_memory_matches_oracle():
         _, _, grads = gpu_run(cell, m, x, w_out, w_h)
         assert int(lib.ttrnn_tc_launch_count(0)) > 0
     assert_grads(grads, g_ref)
+
+
+def test_row_gemm_with_both_operands_in_shared_memory_matches_oracle():
+    """`tc_rows_ts = 0`: the ih projection / dX GEMMs with both operands from shared memory for every K (the default feeds A
+    from TMEM when K >= 128)."""
+    cell, I, H, L, d, r, B, T = "lstm", 40, 256, 2, 3, 8, 40, 24
+    layers, m = make_pair(cell, I, H, L, d, r)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(B, T, I, generator=g)
+    w_out, w_h = torch.randn(B, T, H, generator=g), torch.randn(B, H, generator=g)
+    o_ref, h_ref, g_ref = oracle_run(cell, layers, x, w_out, w_h)
+    with options(tc_rows_ts=0) as lib:
+        lib.ttrnn_tc_launch_count(1)
+        out, h, grads = gpu_run(cell, m, x, w_out, w_h)
+        assert int(lib.ttrnn_tc_launch_count(0)) > 0
+    assert rel_err(out, o_ref) <= FWD_TOL and rel_err(h, h_ref) <= FWD_TOL
+    assert_grads(grads, g_ref)
+
+
+@pytest.mark.parametrize("cell,I,H,L,d,r,B,T", [
+    ("lstm", 40, 256, 3, 3, 8, 40, 24),          # cfg3 shape: split BPTT (kept gates) + dense hh / ih weight gradients
+    ("lstm", 40, 256, 4, 2, 4, 24, 16),          # four layers: each buffer set is reused (layer l and l - 2)
+    ("gru", 40, 256, 2, 2, 4, 24, 16),           # fused (non-split) BPTT kernel
+])
+def test_backward_overlap_matches_oracle_and_serial_run(cell, I, H, L, d, r, B, T):
+    """`bwd_overlap`: the weight-gradient work of layer l runs on the library's second stream under the BPTT kernel of layer
+    l - 1, from a second set of scratch buffers.  Same gradients as the oracle, and as the single-stream run, over repeated
+    steps (the side stream is joined back at the end of every backward)."""
+    layers, m = make_pair(cell, I, H, L, d, r)
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(B, T, I, generator=g)
+    w_out, w_h = torch.randn(B, T, H, generator=g), torch.randn(B, H, generator=g)
+    _, _, g_ref = oracle_run(cell, layers, x, w_out, w_h)
+    plan = _lib.describe_plan(m.spec().desc(B, T), training=True)
+    assert plan[0]["bwd_overlap"] == 1, plan[0]
+    for _ in range(3):
+        _, _, grads = gpu_run(cell, m, x, w_out, w_h)
+        assert_grads(grads, g_ref)
+    with options(bwd_overlap=0):
+        assert _lib.describe_plan(m.spec().desc(B, T), training=True)[0]["bwd_overlap"] == 0
+        _, _, serial = gpu_run(cell, m, x, w_out, w_h)
+    assert_grads(serial, g_ref)
+    for a, b in zip(grads, serial):
+        assert rel_err(a, b) <= 1e-5

@@ -12,17 +12,37 @@ using namespace ttc;
 // mode 2: TS form, the 3xTF32 pattern (small, small, main) of k_tc_red_ts, k-slices walking through a 128-byte row
 // mode 3: SS form, 3xTF32 pattern (k_tc_rows)
 // N = 128 or 256
-__global__ void __launch_bounds__(128, 1) k_probe(int mode, int N, int iters, long long *out) {
+__global__ void __launch_bounds__(256, 1) k_probe(int mode, int N, int iters, long long *out, int bg) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar = base + 6 * TILE_BYTES, slot = bar + 32;
-    if (threadIdx.x == 0) { mbar_init(bar, 1); mbar_init(bar + 16, 1); fence_barrier_init(); }
+    __shared__ int done;
+    if (threadIdx.x == 0) { done = 0; mbar_init(bar, 1); mbar_init(bar + 16, 1); fence_barrier_init(); }
     if (threadIdx.x < 32) tmem_alloc(slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tb;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tb) : "r"(slot));
+    if (bg & 4) {                                            // random operands instead of whatever the memories held (zeros)
+        float *f = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)));
+        uint32_t x = 1234567u + threadIdx.x * 7919u + blockIdx.x;
+        for (int i = threadIdx.x; i < 6 * TILE_BYTES / 4; i += blockDim.x) {
+            x = x * 1664525u + 1013904223u;
+            f[i] = (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f;
+        }
+        fence_proxy_async();
+        if (threadIdx.x < 128) {
+            float v[32];
+            for (int j = 0; j < 32; ++j) { x = x * 1664525u + 1013904223u; v[j] = (float)(x >> 8) * (1.0f / 8388608.0f) - 1.0f; }
+            const uint32_t ta = tb + ((uint32_t)((threadIdx.x >> 5) & 3) * 32 << 16);
+            for (int c = 0; c < 512; c += 32) tmem_st32(ta + c, v);
+            tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
     if (threadIdx.x == 0) {
         const uint32_t idesc = umma_idesc_tf32(128, N);
         const uint64_t da = umma_desc_sw128(base), da2 = umma_desc_sw128(base + TILE_BYTES);
@@ -88,6 +108,32 @@ __global__ void __launch_bounds__(128, 1) k_probe(int mode, int N, int iters, lo
         const long long t1 = clock64();
         if (blockIdx.x == 0) out[0] = t1 - t0;
     }
+    // background traffic while thread 0 issues: bg & 1 = warps 1-3 stream LDS.128 / STS.128 over 32 KB of shared memory,
+    // bg & 2 = warps 4-7 keep writing 64 TMEM columns (tcgen05.st, as the A splitters of tt_tc.cuh do)
+    if (threadIdx.x == 0) done = 1;
+    if ((bg & 1) && threadIdx.x >= 32 && threadIdx.x < 128) {
+        float4 *p4 = reinterpret_cast<float4 *>(smem_raw + (base - smem_u32(smem_raw)) + 6 * TILE_BYTES + 1024);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        while (*(volatile int *)&done == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float4 v = p4[(threadIdx.x - 32) + 96 * j];
+                acc.x += v.x;
+                p4[(threadIdx.x - 32) + 96 * j] = acc;
+            }
+        }
+        if (acc.x == 123.f) out[1] = 1;
+    }
+    if ((bg & 2) && threadIdx.x >= 128) {
+        float v[32];
+        for (int j = 0; j < 32; ++j) v[j] = (float)j;
+        const uint32_t ta = tb + ((uint32_t)((threadIdx.x >> 5) & 3) * 32 << 16) + 256;
+        while (*(volatile int *)&done == 0) {
+            tmem_st32(ta, v);
+            tmem_st32(ta + 32, v);
+            tmem_wait_st();
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x < 32) tmem_dealloc(tb, 512);
@@ -95,20 +141,20 @@ __global__ void __launch_bounds__(128, 1) k_probe(int mode, int N, int iters, lo
 
 int main() {
     long long *d;
-    cudaMalloc(&d, 8);
-    const int smem = 6 * TILE_BYTES + 2048;
+    cudaMalloc(&d, 64);
+    const int smem = 6 * TILE_BYTES + 2048 + 96 * 16 * 16 + 1024;
     cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int iters = 2000;
     for (int N : {128, 256})
         for (int mode = 0; mode < 8; ++mode) {
             if (N == 256 && mode >= 2) continue;             // two 256-column accumulators + the A columns do not fit
-            for (int grid : {1, 148}) {
-                k_probe<<<grid, 128, smem>>>(mode, N, iters, d);
+            for (int bg : {0, 4, 7}) {
+                if (bg && mode != 1 && mode != 2 && mode != 4 && mode != 0) continue;
+                k_probe<<<148, 256, smem>>>(mode, N, iters, d, bg);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long c = 0;
                 cudaMemcpy(&c, d, 8, cudaMemcpyDeviceToHost);
-                printf("N=%d mode=%d grid=%3d : %s  %.1f clk per MMA (%d MMAs)\n", N, mode, grid, cudaGetErrorString(e),
-                       (double)c / (iters * 12.0), iters * 12);
+                printf("N=%d mode=%d bg=%d : %s  %.1f clk per MMA\n", N, mode, bg, cudaGetErrorString(e), (double)c / (iters * 12.0));
             }
         }
     return 0;

@@ -75,6 +75,14 @@ static int test_rows(int nb, int rpb, int T, int K, int N, bool bias, int sms, b
         CK(cudaEventRecord(e0));
         for (int w = 0; w < 5; ++w) ttc::launch_tc_rows(rows, rpb, dA, (long long)T * K, K, dBh, dBl, N, nullptr, nullptr, dC, (long long)T * N, sms, 0);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 5;
+#ifdef TC_PROBE
+        {
+            long long h[8];
+            CK(cudaMemcpy(h, ttc::tc_probe_buf(), sizeof h, cudaMemcpyDeviceToHost));
+            printf("  MMA thread of CTA 3: total %lld clk, %lld k-blocks (%.0f clk each); waits: tempty %lld full %lld aready %lld sfree %lld; issue %lld\n",
+                   h[0], h[6], (double)h[0] / (double)h[6], h[1], h[2], h[3], h[4], h[5]);
+        }
+#endif
         // FFMA reference kernel: needs B as K x N
         dim3 tg((K + 31) / 32, (N + 31) / 32);
         ttg::k_transpose<<<tg, 256>>>(dBt, dBkn, N, K);
@@ -168,8 +176,13 @@ static int test_red(int nb, int rpb, int T, int M, int N, int sms, bool timing, 
 }
 
 int main(int argc, char **argv) {
+#ifdef TC_PROBE
+    CK(cudaMalloc(&ttc::tc_probe_buf(), 64));
+    CK(cudaMemset(ttc::tc_probe_buf(), 0, 64));
+#endif
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
     if (getenv("TC_RED_VARIANT")) ttc::tc_red_variant() = atoi(getenv("TC_RED_VARIANT"));
+    if (getenv("TC_ROWS_VARIANT")) ttc::tc_rows_variant() = atoi(getenv("TC_ROWS_VARIANT"));
     printf("k_tc_red variant: %s\n", ttc::tc_red_variant() ? "A from TMEM (k_tc_red_ts)" : "A from shared memory (k_tc_red)");
     if (argc > 1 && !strcmp(argv[1], "chain")) {
         int dev0 = 0, sms0 = 0;
