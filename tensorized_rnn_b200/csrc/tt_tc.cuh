@@ -36,6 +36,14 @@
 
 namespace ttc {
 
+// -DTC_PROBE (tools/tc_gemm_test only): clock64 around every wait of the MMA issuer of one CTA
+#ifdef TC_PROBE
+inline long long *&tc_probe_buf() { static long long *p = nullptr; return p; }
+#define PROBE(acc_, stmt) tq = clock64(); stmt; acc_ += clock64() - tq;
+#else
+#define PROBE(acc_, stmt) stmt;
+#endif
+
 constexpr int BM = 128, BN = 128, BK = 32;
 constexpr int TILE_BYTES = BM * BK * 4;          // 16 KiB: one 128 x 32 FP32 operand tile
 constexpr int NT = 320;                          // 10 warps
@@ -514,9 +522,6 @@ k_tc_rows_ts(const __grid_constant__ TcRowsArgs g, const __grid_constant__ CUten
 #ifdef TC_PROBE
             long long w_tempty = 0, w_full = 0, w_aready = 0, w_sfree = 0, t_issue = 0, tq;
             const long long t_begin = clock64();
-#define PROBE(acc_, stmt) tq = clock64(); stmt; acc_ += clock64() - tq;
-#else
-#define PROBE(acc_, stmt) stmt;
 #endif
             for (long long tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++nt) {
                 const int acc = (int)(nt & 1);
@@ -680,6 +685,9 @@ struct TcRedArgs {
     int nsplit;
     float *part;             // [nsplit][M][N]
     float *pbias;            // [nsplit][N] or null
+#ifdef TC_PROBE
+    long long *probe;
+#endif
 };
 
 __global__ void __launch_bounds__(RED_NT, 1)
@@ -930,18 +938,25 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
     } else if (warp == 17) {
         if (elect_one()) {
             const uint32_t idesc = umma_idesc_tf32(BM, BN);
+#ifdef TC_PROBE
+            long long w_aempty = 0, w_ofull = 0, t_issue = 0, tq;
+            const long long t_begin = clock64();
+#endif
             for (long long i = 0; i < nkb; ++i) {
                 const long long seg = i / RED_SEG;
                 const int ab = (int)(seg & 1);
                 const bool seg_first = (i % RED_SEG) == 0, seg_last = ((i + 1) % RED_SEG) == 0 || i + 1 == nkb;
                 if (seg_first) {
-                    mbar_wait(bar_aempty(ab), (uint32_t)(((seg >> 1) & 1) ^ 1));
+                    PROBE(w_aempty, mbar_wait(bar_aempty(ab), (uint32_t)(((seg >> 1) & 1) ^ 1)))
                     tc_fence_after();
                 }
                 const int s = (int)(i % RTS_OP_STAGES);
                 const uint32_t ph = (uint32_t)((i / RTS_OP_STAGES) & 1);
-                mbar_wait(bar_ofull(s), ph);
+                PROBE(w_ofull, mbar_wait(bar_ofull(s), ph))
                 tc_fence_after();
+#ifdef TC_PROBE
+                const long long ti0 = clock64();
+#endif
                 const uint32_t st = op0 + s * RTS_OP_BYTES;
                 const uint64_t dbh = umma_desc_sw128(st), dbl = umma_desc_sw128(st + TILE_BYTES);
                 const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)s * 64u, a_lo = a_hi + 32u;
@@ -963,7 +978,16 @@ k_tc_red_ts(const __grid_constant__ TcRedArgs g, const __grid_constant__ CUtenso
                 }
                 umma_commit(bar_oempty(s));
                 if (seg_last) umma_commit(bar_afull(ab));
+#ifdef TC_PROBE
+                t_issue += clock64() - ti0;
+#endif
             }
+#ifdef TC_PROBE
+            if (blockIdx.x == 3 && g.probe) {
+                g.probe[0] = clock64() - t_begin; g.probe[1] = w_aempty; g.probe[2] = w_ofull; g.probe[3] = 0;
+                g.probe[4] = 0; g.probe[5] = t_issue; g.probe[6] = nkb;
+            }
+#endif
         }
     } else if (warp < 4) {
         // ---------------- A splitters: column m of the raw tile -> TMEM lane m, hi / lo over 32 k columns ----------------
@@ -1117,9 +1141,7 @@ inline bool tc_red_ok(long long rows, int M, int N) { return rows >= 256 && M >=
 // for the A operand stage -- the splitters' tcgen05.st queue behind the epilogue's tcgen05.ld (128 KB of accumulator reads per
 // tile at 64 B/clk) -- and ~170 clk with K = 1024, where the MMAs run back to back (issue time = 12 x 65 clk per k-block).
 inline int &tc_rows_variant() { static int v = 1; return v; }
-#ifdef TC_PROBE
-inline long long *&tc_probe_buf() { static long long *p = nullptr; return p; }
-#endif
+
 
 inline int launch_tc_rows(long long rows, int rpb, const float *a, long long a_bstride, int K, const float *bt_hi,
                           const float *bt_lo, int N, const float *bias, const float *bias2, float *c, long long c_bstride,
@@ -1195,6 +1217,9 @@ inline int launch_tc_red(long long rows, int rpb, const float *a, long long a_bs
     g.per = per;
     g.nsplit = (int)((gb.nboxes + per - 1) / per);
     g.part = part; g.pbias = pbias;
+#ifdef TC_PROBE
+    g.probe = tc_probe_buf();
+#endif
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, a, M, rp, nb, M, abs_, 128, gb.rb, gb.nbx, false);
     if (rc) return rc;

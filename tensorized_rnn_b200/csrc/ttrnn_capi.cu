@@ -1487,9 +1487,6 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                     sa.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
                     sa.dh_out = sdh; sa.dc_out = sdc;
                     if (launch_plan(sa)) return 1;
-                    if (getenv("TTRNN_DEBUG_OVERLAP"))
-                        fprintf(stderr, "[overlap] l=%d side=%d nchunks=%d dense=%d dlin=%d sms=%d sgrid=%d nph=%d\n", l, side != nullptr,
-                                nchunks, (int)dense, dlin != nullptr, dv.sms, sgrid, nph);
                     if (side && l > 0 && nchunks == 1 && dense && dlin && dv.sms - sgrid >= 24) {
                         // overlap: dX (the next layer's input) first, then everything that only produces parameter gradients
                         // moves to the side stream, planned for the SMs the next BPTT kernel leaves idle

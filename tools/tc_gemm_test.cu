@@ -79,7 +79,7 @@ static int test_rows(int nb, int rpb, int T, int K, int N, bool bias, int sms, b
         {
             long long h[8];
             CK(cudaMemcpy(h, ttc::tc_probe_buf(), sizeof h, cudaMemcpyDeviceToHost));
-            printf("  MMA thread of CTA 3: total %lld clk, %lld k-blocks (%.0f clk each); waits: tempty %lld full %lld aready %lld sfree %lld; issue %lld\n",
+            printf("  (next line) MMA issuer of CTA 3: total %lld clk, %lld k-blocks (%.0f clk each); waits: tempty %lld full %lld aready %lld sfree %lld; issue %lld\n",
                    h[0], h[6], (double)h[0] / (double)h[6], h[1], h[2], h[3], h[4], h[5]);
         }
 #endif
@@ -152,6 +152,14 @@ static int test_red(int nb, int rpb, int T, int M, int N, int sms, bool timing, 
         CK(cudaEventRecord(e0));
         for (int w = 0; w < 5; ++w) ttc::launch_tc_red(rows, rpb, dA, (long long)T * M, M, dB, (long long)T * N, N, dP, dPb, sms, max_split, &nsplit, 0);
         CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 5;
+#ifdef TC_PROBE
+        {
+            long long h[8];
+            CK(cudaMemcpy(h, ttc::tc_probe_buf(), sizeof h, cudaMemcpyDeviceToHost));
+            printf("  (next line) MMA issuer of CTA 3: total %lld clk, %lld k-blocks (%.0f clk each); waits: aempty %lld ofull %lld; issue %lld\n",
+                   h[0], h[6], (double)h[0] / (double)h[6], h[1], h[2], h[5]);
+        }
+#endif
         ttg::GemmRedArgs g; memset(&g, 0, sizeof g);
         const int tiles = ((M + 127) / 128) * (N / 128);
         long long ns = (4LL * sms) / tiles; if (ns < 1) ns = 1; if (ns > max_split) ns = max_split;
