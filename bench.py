@@ -387,27 +387,40 @@ class GpuBench(object):
         # ---- value: device-resident, per-step CUDA events, L2 flushed between steps -------------
         lib.ttrnn_launch_count(1)
         lib.ttrnn_tc_launch_count(1)
-        lib.ttrnn_kernel_timing(1)
-        ev = []
-        self.barrier()
-        w0 = time.perf_counter()
-        for _ in range(steps):
-            self.flush_buf.fill_(1)
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record()
-            one_pass(x_dev)
-            e1.record()
-            ev.append((e0, e1))
-        self.barrier()
-        self.windows.append((w0, time.perf_counter()))
-        lib.ttrnn_kernel_timing(0)
+
+        def timed(n):
+            ev = []
+            self.barrier()
+            w0 = time.perf_counter()
+            for _ in range(n):
+                self.flush_buf.fill_(1)
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record()
+                one_pass(x_dev)
+                e1.record()
+                ev.append((e0, e1))
+            self.barrier()
+            self.windows.append((w0, time.perf_counter()))
+            return sum(a.elapsed_time(b) for a, b in ev)
+
+        total_ms = timed(steps)
         launches = int(lib.ttrnn_launch_count(0))
         tc_launches = int(lib.ttrnn_tc_launch_count(0))
-        total_ms = sum(a.elapsed_time(b) for a, b in ev)
+        # ---- per-kernel times: a second pass with the library's event pairs around every launch.  While that timing is
+        # on, the library runs the row groups of a multi-layer stack back to back on one stream (per-launch events cannot
+        # attribute time between kernels of two streams that share the SMs), so these are each kernel's OWN durations,
+        # the figures an ncu launch list gives; `ms_per_step` above is the concurrent run.
+        ksteps = min(steps, 5)
+        lib.ttrnn_kernel_timing(1)
+        serial_ms = timed(ksteps)
+        lib.ttrnn_kernel_timing(0)
         nk = len(KINDS)
         kms = (C.c_double * nk)(*([0.0] * nk))
         kcnt = (C.c_int64 * nk)(*([0] * nk))
         lib.ttrnn_kernel_times(kms, kcnt)
+        for i in range(nk):                            # scale to `steps` so that every consumer below divides by steps
+            kms[i] = kms[i] * steps / ksteps
+            kcnt[i] = int(kcnt[i] * steps / ksteps)
 
         # ---- e2e: pinned host input -> H2D -> module API -> D2H of the result, wall clock ----------
         e2e_ms, d2h = 0.0, 0
@@ -504,6 +517,7 @@ class GpuBench(object):
                 "value": units / (total_ms * 1e-3), "unit": "cell-steps/s",
                 "layer_cell_steps_per_s": units * cfg["L"] / (total_ms * 1e-3),
                 "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+                "ms_per_step_kernel_timing_pass": serial_ms / ksteps,
                 "e2e": ({"value": units / (e2e_ms * 1e-3), "unit": "cell-steps/s", "h2d_bytes_per_step": x_host.numel() * 4,
                          "d2h_bytes_per_step": d2h} if with_e2e else None),
                 "gpu_launches": launches, "tc_gemm_launches": tc_launches,

@@ -224,6 +224,12 @@ int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain
  * batch rows per CTA, save_mode, and with training != 0: bwd_kernel, bwd_rows, bwd_phase_rows, optional second phase,
  * hh_dw, hh_dw_tc).  Needs a CUDA device (the plan depends on its SM count).  Returns characters written, < 0 on error. */
 int ttrnn_rnn_describe(const ttrnn_rnn_desc *desc, int32_t training, char *buf, int32_t cap);
+/* Row-group split of `desc` under the current options (round 2, "row_groups"): multi-layer stacks whose batch does not
+ * fill whole waves of CTAs are cut into two independent row groups that run the stack on two streams, so that the SMs
+ * a layer-pass of one group leaves idle run the next layer of the other (the reference has no counterpart: its layer
+ * loop, lstm.py:123-133, is sequential over the whole batch).  Returns the number of groups (1 or 2; < 0 on error) and
+ * their row counts.  sms > 0 plans for that SM count without touching a device (tests); sms <= 0 asks the device. */
+int ttrnn_rnn_row_groups(const ttrnn_rnn_desc *desc, int32_t sms, int64_t *rows /*[2]*/);
 /* launches of the tcgen05 (tensor-core, 3xTF32) GEMM kernels since the last reset (subset of ttrnn_launch_count) */
 int64_t ttrnn_tc_launch_count(int32_t reset);
 

@@ -74,6 +74,7 @@ SYMBOLS = {
     "ttrnn_static_kernel_table": (C.c_int, [C.c_char_p, C.c_int32]),
     "ttrnn_rnn_describe": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.c_char_p, C.c_int32]),
     "ttrnn_tc_launch_count": (C.c_int64, [C.c_int32]),
+    "ttrnn_rnn_row_groups": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.POINTER(C.c_int64)]),
     "ttrnn_ffma_probe": (C.c_int, [C.c_int32, _P, C.POINTER(C.c_double), _P]),
     "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
     "ttrnn_kernel_timing": (C.c_int, [C.c_int32]),
@@ -109,7 +110,8 @@ def load() -> C.CDLL:
                      ("save_bytes", "TTRNN_SAVE_BYTES"), ("save_u_bytes", "TTRNN_SAVE_U_BYTES"),
                      ("row_plan", "TTRNN_ROW_PLAN"), ("gemm_wide", "TTRNN_GEMM_WIDE"), ("split_kept", "TTRNN_SPLIT_KEPT"),
                      ("dense_hh_dw", "TTRNN_DENSE_HH_DW"), ("tc_gemm", "TTRNN_TC_GEMM"),
-                     ("rank_pad", "TTRNN_RANK_PAD"), ("bwd_overlap", "TTRNN_BWD_OVERLAP")):
+                     ("rank_pad", "TTRNN_RANK_PAD"), ("bwd_overlap", "TTRNN_BWD_OVERLAP"),
+                     ("row_groups", "TTRNN_ROW_GROUPS")):
         if os.environ.get(env):
             lib.ttrnn_set_option(key.encode(), int(os.environ[env]))
     _lib = lib

@@ -56,6 +56,12 @@ std::atomic<long long> g_opt_rank_pad{1};
 // second stream, on the SMs the BPTT kernel of layer l - 1 leaves idle (its grid is rows / rows-per-CTA, e.g. 98 of 148 at
 // cfg3).  Needs a second set of the per-layer scratch buffers; single-chunk plans only.  0 = everything on the caller's stream
 std::atomic<long long> g_opt_bwd_overlap{1};
+// multi-layer stacks: split the batch into two ROW GROUPS that run the whole stack independently on two streams (see
+// plan_row_groups).  A layer-pass of one launch leaves SMs idle whenever rows / rows-per-CTA is not a multiple of the SM
+// count (cfg3: 128 five-row CTAs forward, 148 + 98 CTAs backward on 148 SMs); with two groups the tail group of layer l
+// runs beside the head group of layer l + 1 (forward) / l - 1 (backward).  0 = one group (every launch on the caller's stream),
+// 1 = planned, >= 4 = force group 0 to that many rows whatever the plan says (tests)
+std::atomic<long long> g_opt_row_groups{1};
 
 // Snapshot of every option that decides a buffer layout or a kernel route.  ttrnn_rnn_workspace_bytes() takes it from the
 // process-wide options and stamps it into ttrnn_rnn_workspace.plan; forward and backward run from THAT copy, so a
@@ -63,11 +69,13 @@ std::atomic<long long> g_opt_bwd_overlap{1};
 // the scratch buffers are interpreted.  Helpers read the calling thread's current snapshot `t_opt`.
 struct Opts {
     long long rows, chunk, chunk_bytes, stat, srows_fwd, srows_bwd, save_bytes, save_u_bytes, row_plan, dense_ih, gemm_wide,
-        dense_hh, split_kept, dense_ratio, tc_gemm, rank_pad, bwd_overlap;
+        dense_hh, split_kept, dense_ratio, tc_gemm, rank_pad, bwd_overlap, row_groups;
 };
 constexpr int kOptFields = sizeof(Opts) / sizeof(long long);
-constexpr long long kPlanMagic = 0x7474726E6E706C33LL;          // "ttrnnpl3"
-static_assert(kOptFields + 1 <= TTRNN_PLAN_WORDS, "plan does not fit ttrnn_rnn_workspace.plan");
+constexpr long long kPlanMagic = 0x7474726E6E706C34LL;          // "ttrnnpl4"
+// plan words: [0] magic, [1 .. kOptFields] options, then the row-group split (group count, rows of group 0)
+constexpr int kPlanGroups = kOptFields + 1, kPlanRows0 = kOptFields + 2;
+static_assert(kOptFields + 3 <= TTRNN_PLAN_WORDS, "plan does not fit ttrnn_rnn_workspace.plan");
 thread_local Opts t_opt;
 
 Opts snapshot_options() {
@@ -77,7 +85,7 @@ Opts snapshot_options() {
     o.save_bytes = g_opt_save_bytes.load(); o.save_u_bytes = g_opt_save_u_bytes.load(); o.row_plan = g_opt_row_plan.load();
     o.dense_ih = g_opt_dense_ih.load(); o.gemm_wide = g_opt_gemm_wide.load(); o.dense_hh = g_opt_dense_hh.load();
     o.split_kept = g_opt_split_kept.load(); o.dense_ratio = g_opt_dense_ratio.load(); o.tc_gemm = g_opt_tc_gemm.load();
-    o.rank_pad = g_opt_rank_pad.load(); o.bwd_overlap = g_opt_bwd_overlap.load();
+    o.rank_pad = g_opt_rank_pad.load(); o.bwd_overlap = g_opt_bwd_overlap.load(); o.row_groups = g_opt_row_groups.load();
     return o;
 }
 void plan_store(const Opts &o, int64_t *plan) {
@@ -843,6 +851,176 @@ int dense_dw(const DevInfo &dv, long long rows, int rpb, const float *x, long lo
     return 0;
 }
 
+// ---- row groups ---------------------------------------------------------------------------------------------------
+// A layer-pass of a recurrent kernel is ONE launch of rows / R persistent CTAs that each own R batch rows for all T
+// steps, one CTA per SM.  Whenever rows / R is not a multiple of the SM count the launch leaves SMs idle for its whole
+// duration (cfg3, 640 rows on 148 SMs: 128 five-row CTAs forward; 148 three-row + 98 two-row CTAs backward), and nothing
+// else can use them because layer l + 1 needs layer l of the SAME rows.  Different rows are independent, though: with the
+// batch cut into two groups that run the whole stack on two streams, the hardware block scheduler places the CTAs of
+// group 1 / layer l beside those of group 0 / layer l + 1, and the SMs stay busy across layer boundaries.  Group 0 is a
+// whole number of full waves (sms * m rows), group 1 the remainder.  Each group is a complete, independent call of the
+// single-group path on its slice of every row-indexed buffer (own region of `saved` and of the scratch buffers, own
+// dense-route GEMMs, own gradient blob, summed at the end), so results do not depend on the split beyond FP32 summation
+// order of the parameter gradients.
+constexpr int kMaxGroups = 2;
+thread_local int t_group = 0;          // group the calling thread is issuing work for (selects the side-stream context)
+struct GroupPlan {
+    int n = 1;
+    long long rows[kMaxGroups] = {0, 0};
+};
+inline int64_t a256(int64_t bytes) { return (bytes + 255) & ~(int64_t)255; }
+
+struct SimLaunch { int ctas; double dur; };
+// Greedy list scheduling of `nq` in-order launch queues on `sms` SMs (one CTA per SM, the earlier-ready launch places its
+// CTAs first): the behaviour of the block scheduler with kernels of independent streams.  Returns the makespan.
+double sim_makespan(const std::vector<SimLaunch> *q, int nq, int sms) {
+    struct Run { double end; int n, s; };
+    std::vector<Run> running;
+    size_t idx[kMaxGroups] = {};
+    int pending[kMaxGroups] = {}, active[kMaxGroups] = {};
+    double ready[kMaxGroups] = {};
+    for (int s = 0; s < nq; ++s) pending[s] = q[s].empty() ? 0 : q[s][0].ctas;
+    int free_sms = sms;
+    double t = 0.0;
+    for (;;) {
+        int order[kMaxGroups];
+        for (int s = 0; s < nq; ++s) order[s] = s;
+        if (nq == 2 && ready[1] < ready[0]) { order[0] = 1; order[1] = 0; }
+        for (int o = 0; o < nq; ++o) {
+            const int s = order[o];
+            if (idx[s] >= q[s].size() || pending[s] <= 0 || free_sms <= 0) continue;
+            const int n = pending[s] < free_sms ? pending[s] : free_sms;
+            running.push_back({t + q[s][idx[s]].dur, n, s});
+            pending[s] -= n; active[s] += n; free_sms -= n;
+        }
+        if (running.empty()) break;
+        double tmin = running[0].end;
+        for (const Run &r : running) if (r.end < tmin) tmin = r.end;
+        t = tmin;
+        for (size_t i = 0; i < running.size();) {
+            if (running[i].end <= t + 1e-9) {
+                free_sms += running[i].n; active[running[i].s] -= running[i].n;
+                running[i] = running.back(); running.pop_back();
+            } else {
+                ++i;
+            }
+        }
+        for (int s = 0; s < nq; ++s)
+            if (idx[s] < q[s].size() && pending[s] == 0 && active[s] == 0) {
+                ++idx[s];
+                if (idx[s] < q[s].size()) { pending[s] = q[s][idx[s]].ctas; ready[s] = t; }
+            }
+    }
+    return t;
+}
+
+// launches of the recurrent kernels of one group of `Bg` rows: forward layers 0..L-1 into fq, backward L-1..0 into bq.
+// Cost of a wave of R rows per CTA ~ (0.4 + R) (measured on the d3r8 chain: forward 2.67 / 4.43 / 6.59 / 10.5 us per step
+// at R = 1 / 2 / 3 / 5, backward 2.96 / 4.86 / 7.0 at R = 1 / 2 / 3).  false: a layer has no static kernel.
+bool group_launches(const ttrnn_rnn_desc *d, const RnnPlan &rp, const RnnLayout &lo, long long Bg, int sms,
+                    std::vector<SimLaunch> *fq, std::vector<SimLaunch> *bq) {
+    constexpr double kFloor = 0.4;
+    auto push = [&](std::vector<SimLaunch> *q, long long rows, int R) {
+        const long long tiles = (rows + R - 1) / R;
+        const long long waves = (tiles + sms - 1) / sms;
+        q->push_back({(int)(tiles < sms ? tiles : sms), (double)waves * (kFloor + R)});
+    };
+    for (int l = 0; l < d->num_layers; ++l) {
+        const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
+        const TtsRnnFwdEntry *se = tts_find_rnn_fwd(&d->hh[l], d->cell, mode, Bg, sms, (int)t_opt.srows_fwd);
+        if (!se) return false;
+        push(fq, Bg, se->R);
+    }
+    for (int l = d->num_layers - 1; l >= 0; --l) {
+        const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
+        const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, Bg, sms, (int)t_opt.srows_bwd);
+        if (lo.save_mode[l] != 0)
+            if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, Bg, sms, (int)t_opt.srows_bwd, lo.save_mode[l],
+                                                            dense_hh_dw_ok(rp.layer[l].hh) && t_opt.split_kept))
+                be = bs;
+        if (!be) return false;
+        const TtsRnnBwdEntry *pe[2] = {be, nullptr};
+        long long pr0[2] = {0, 0}, pr[2] = {Bg, 0};
+        int np = 1;
+        if ((!be->split || be->saved == 2) && t_opt.row_plan) {
+            const int q = tts_plan_rnn_bwd(&d->hh[l], d->cell, mode, Bg, sms, (int)t_opt.srows_bwd, be->saved,
+                                           be->split && be->saved == 2, pe, pr0, pr);
+            if (q >= 1) np = q; else { pe[0] = be; pr[0] = Bg; }
+        }
+        for (int q = 0; q < np; ++q) push(bq, pr[q], pe[q]->R);
+    }
+    return true;
+}
+
+// Decide the split.  Only for multi-layer stacks on the static kernels in single-chunk plans (the large-batch configs that
+// need time chunks run many waves per launch and lose little to the last one).  Candidates: group 0 = sms * m rows.  A
+// split is taken when the modelled forward + backward recurrence time drops by >= 6 % and the forward alone does not get
+// slower (inference runs the same split).
+int plan_row_groups(const ttrnn_rnn_desc *d_in, GroupPlan *gp, const DevInfo *dev = nullptr) {
+    gp->n = 1;
+    gp->rows[0] = d_in ? d_in->batch : 0;
+    gp->rows[1] = 0;
+    if (!d_in || !t_opt.row_groups) return 0;
+    if (t_opt.row_groups >= 4) {                        // forced split (tests): group 0 = that many rows, any plan
+        const long long r0 = t_opt.row_groups & ~3LL;
+        if (r0 < d_in->batch) { gp->n = 2; gp->rows[0] = r0; gp->rows[1] = d_in->batch - r0; }
+        return 0;
+    }
+    if (!t_opt.stat || d_in->num_layers < 2) return 0;
+    RnnPlan rp;
+    if (build_rnn_plan(d_in, &rp)) return 1;
+    DevInfo dv;
+    if (dev) dv = *dev;
+    else if (get_dev(&dv)) return 1;
+    EffDesc eff;
+    if (make_eff_desc(d_in, &dv, &eff)) return 1;
+    const ttrnn_rnn_desc *d = &eff.d;
+    if (eff.padded && build_rnn_plan(d, &rp)) return 1;
+    RnnLayout lo;
+    if (build_layout(d, rp, dv, &lo)) return 1;
+    const long long B = d->batch;
+    if (lo.Tc != d->seq_len || B < 8 || B > 16LL * dv.sms) return 0;
+    std::vector<SimLaunch> f1, b1;
+    if (!group_launches(d, rp, lo, B, dv.sms, &f1, &b1)) return 0;
+    const double fwd1 = sim_makespan(&f1, 1, dv.sms), bwd1 = sim_makespan(&b1, 1, dv.sms);
+    double best = fwd1 + bwd1;
+    for (int m = 1; m <= 8; ++m) {
+        const long long r0 = (long long)dv.sms * m;
+        if (r0 >= B) break;
+        if (r0 % 4 != 0 || (B - r0) < 1) continue;     // row-indexed slices stay 16-byte aligned
+        std::vector<SimLaunch> fq[kMaxGroups], bq[kMaxGroups];
+        if (!group_launches(d, rp, lo, r0, dv.sms, &fq[0], &bq[0]) || !group_launches(d, rp, lo, B - r0, dv.sms, &fq[1], &bq[1]))
+            continue;
+        const double f2 = sim_makespan(fq, 2, dv.sms), b2 = sim_makespan(bq, 2, dv.sms);
+        if (f2 <= fwd1 * 1.02 && f2 + b2 < best && f2 + b2 <= 0.94 * (fwd1 + bwd1)) {
+            best = f2 + b2;
+            gp->n = 2;
+            gp->rows[0] = r0;
+            gp->rows[1] = B - r0;
+        }
+    }
+    return 0;
+}
+
+// stream + events of the second row group (one per host thread and device, kept for the life of the process)
+struct GroupCtx {
+    int dev = -1;
+    cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+GroupCtx *group_ctx() {
+    thread_local GroupCtx ctx[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    GroupCtx &c = ctx[dev];
+    if (c.dev == dev) return &c;
+    if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    c.dev = dev;
+    return &c;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -901,6 +1079,7 @@ int ttrnn_set_option(const char *key, int64_t value) {
     if (!strcmp(key, "tc_gemm")) { g_opt_tc_gemm.store(value); return 0; }
     if (!strcmp(key, "rank_pad")) { g_opt_rank_pad.store(value); return 0; }
     if (!strcmp(key, "bwd_overlap")) { g_opt_bwd_overlap.store(value); return 0; }
+    if (!strcmp(key, "row_groups")) { g_opt_row_groups.store(value); return 0; }
     if (!strcmp(key, "tc_red_ts")) { ttc::tc_red_variant() = value ? 1 : 0; return 0; }   // A/B switch, not part of a plan
     if (!strcmp(key, "tc_rows_ts")) { ttc::tc_rows_variant() = value ? 1 : 0; return 0; } // A/B switch, not part of a plan
     return 1;
@@ -923,15 +1102,44 @@ int ttrnn_rnn_ih_route(const ttrnn_rnn_desc *desc, int32_t layer, int64_t *chain
     return dense_ih_ok(ih, &desc->ih[layer]) ? 1 : 0;
 }
 
+int ttrnn_rnn_row_groups(const ttrnn_rnn_desc *desc, int32_t sms, int64_t *rows /*[2]*/) {
+    if (!rows) { fail("rows must be non-null"); return -1; }
+    t_opt = snapshot_options();
+    DevInfo dv;
+    if (sms > 0) {
+        dv.sms = sms;
+        dv.smem_optin = 232448;
+        dv.ok = true;
+    } else if (get_dev(&dv)) {
+        return -1;
+    }
+    GroupPlan gp;
+    if (plan_row_groups(desc, &gp, &dv)) return -1;
+    rows[0] = gp.rows[0];
+    rows[1] = gp.n == 2 ? gp.rows[1] : 0;
+    return gp.n;
+}
+
 int64_t ttrnn_tc_launch_count(int32_t reset) {
     long long v = g_tc_launches.load();
     if (reset) g_tc_launches.store(0);
     return v;
 }
 
-int ttrnn_rnn_describe(const ttrnn_rnn_desc *d_in, int32_t training, char *buf, int32_t cap) {
+int ttrnn_rnn_describe(const ttrnn_rnn_desc *d_full, int32_t training, char *buf, int32_t cap) {
     if (!buf || cap < 1) return -1;
     t_opt = snapshot_options();
+    // with two row groups the layer lines describe group 0 (the full waves); the header names the split and the
+    // rows per CTA the remainder group runs at
+    GroupPlan gp;
+    if (plan_row_groups(d_full, &gp)) return -1;
+    ttrnn_rnn_desc d_g0;
+    const ttrnn_rnn_desc *d_in = d_full;
+    if (gp.n == 2) {
+        d_g0 = *d_full;
+        d_g0.batch = gp.rows[0];
+        d_in = &d_g0;
+    }
     RnnPlan rp;
     if (build_rnn_plan(d_in, &rp)) return -1;
     DevInfo dv;
@@ -959,7 +1167,15 @@ int ttrnn_rnn_describe(const ttrnn_rnn_desc *d_in, int32_t training, char *buf, 
             if (c == ' ') c = '_';
         return t;
     };
-    put("chunk_steps=%d sms=%d tc_gemm=%lld rank_padded=%d bwd_overlap=%d\n", lo.Tc, dv.sms, t_opt.tc_gemm, (int)eff.padded, lo.overlap);
+    put("chunk_steps=%d sms=%d tc_gemm=%lld rank_padded=%d bwd_overlap=%d row_groups=%d", lo.Tc, dv.sms, t_opt.tc_gemm, (int)eff.padded,
+        lo.overlap, gp.n);
+    if (gp.n == 2) {
+        std::vector<SimLaunch> fq, bq;
+        put(" group_rows0=%lld group_rows1=%lld", gp.rows[0], gp.rows[1]);
+        if (group_launches(d, rp, lo, gp.rows[1], dv.sms, &fq, &bq) && !fq.empty() && !bq.empty())
+            put(" group1_fwd_ctas=%d group1_bwd_ctas=%d", fq.back().ctas, bq.front().ctas);
+    }
+    put("\n");
     for (int l = 0; l < d->num_layers; ++l) {
         const LayerPlan &lp = rp.layer[l];
         const bool rank1 = (l == 0 && d->input_size == 1);
@@ -1006,9 +1222,8 @@ int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc) {
     return rp.param_floats;
 }
 
-int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
-    if (!ws) return fail("null workspace struct");
-    t_opt = snapshot_options();
+// byte sizes of ONE row group (the whole batch when the plan has a single group), under the calling thread's options
+static int workspace_one(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
     RnnPlan rp;
     if (build_rnn_plan(desc, &rp)) return 1;
     DevInfo dv;
@@ -1021,16 +1236,41 @@ int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *w
     ws->saved_bytes = lo.sv_total * 4;
     ws->fwd_scratch_bytes = (lo.f_total + eff.pad_floats) * 4;             // + the rank-padded parameter blob
     ws->bwd_scratch_bytes = (lo.b_total + 2 * eff.pad_floats) * 4;         // + padded parameters and padded gradients
-    memset(ws->plan, 0, sizeof ws->plan);
-    plan_store(t_opt, ws->plan);
     return 0;
 }
 
-int ttrnn_rnn_forward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
-                      const float *c0, const float *params_in, float *out, float *hT, float *cT, void *saved, void *scratch,
-                      void *stream) {
-    if (!ws || !plan_load(ws->plan, &t_opt))
-        return fail("ttrnn_rnn_forward: `ws` must be the struct filled by ttrnn_rnn_workspace_bytes() for this descriptor");
+int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
+    if (!ws) return fail("null workspace struct");
+    t_opt = snapshot_options();
+    GroupPlan gp;
+    if (plan_row_groups(desc, &gp)) return 1;
+    if (gp.n == 1) {
+        if (workspace_one(desc, ws)) return 1;
+    } else {
+        // one region per group in every buffer (256-byte aligned), + the gradient blob of every group but the first
+        const int64_t pf = ttrnn_rnn_param_count(desc);
+        ws->saved_bytes = ws->fwd_scratch_bytes = ws->bwd_scratch_bytes = 0;
+        for (int g = 0; g < gp.n; ++g) {
+            ttrnn_rnn_desc dg = *desc;
+            dg.batch = gp.rows[g];
+            ttrnn_rnn_workspace wg;
+            if (workspace_one(&dg, &wg)) return 1;
+            ws->saved_bytes += a256(wg.saved_bytes);
+            ws->fwd_scratch_bytes += a256(wg.fwd_scratch_bytes);
+            ws->bwd_scratch_bytes += a256(wg.bwd_scratch_bytes) + (g > 0 ? a256(pf * 4) : 0);
+        }
+    }
+    memset(ws->plan, 0, sizeof ws->plan);
+    plan_store(t_opt, ws->plan);
+    ws->plan[kPlanGroups] = gp.n;
+    ws->plan[kPlanRows0] = gp.rows[0];
+    return 0;
+}
+
+// forward of ONE row group on stream `stream`; `ws` carries the byte sizes of this group, t_opt is already loaded
+static int forward_one(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                       const float *c0, const float *params_in, float *out, float *hT, float *cT, void *saved, void *scratch,
+                       void *stream) {
     RnnPlan rp;
     if (build_rnn_plan(d_in, &rp)) return 1;
     if (!x || !params_in || !out || !scratch) return fail("x, params, out and scratch must be non-null");
@@ -1208,10 +1448,10 @@ struct SideCtx {
     cudaEvent_t fork = nullptr, fin = nullptr, done[2] = {nullptr, nullptr};
 };
 static SideCtx *side_ctx() {
-    thread_local SideCtx ctx[16];
+    thread_local SideCtx ctx[16][kMaxGroups];      // every row group forks its own side stream
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
-    SideCtx &c = ctx[dev];
+    SideCtx &c = ctx[dev][t_group];
     if (c.dev == dev) return &c;
     if (cudaStreamCreateWithFlags(&c.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
     if (cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
@@ -1228,12 +1468,10 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                              const float *d_out, const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0,
                              float *d_c0, void *scratch, cudaStream_t st);
 
-int ttrnn_rnn_backward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
-                       const float *c0, const float *params, const float *out, const void *saved, const float *d_out,
-                       const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
-                       void *scratch, void *stream) {
-    if (!ws || !plan_load(ws->plan, &t_opt))
-        return fail("ttrnn_rnn_backward: `ws` must be the struct the matching forward ran with");
+static int backward_one(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                        const float *c0, const float *params, const float *out, const void *saved, const float *d_out,
+                        const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
+                        void *scratch, void *stream) {
     RnnPlan rp;
     if (build_rnn_plan(d_in, &rp)) return 1;
     if (!x || !params || !out || !scratch || !d_params) return fail("x, params, out, scratch, d_params must be non-null");
@@ -1639,6 +1877,125 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
         if (d_h0 && axpy1(sdh, d_h0, lo.BH, l != L - 1, st)) return 1;
         if (lstm && d_c0 && axpy1(sdc, d_c0, lo.BH, l != L - 1, st)) return 1;
     }
+    return 0;
+}
+
+// ---- public entry points: one call of the single-group path per row group ---------------------------------------
+// Group 0 runs on the caller's stream, group 1 on the group stream, forked from the caller's stream at entry (so that it
+// waits for whatever produced the inputs, not for group 0) and joined at exit.  While per-kernel event timing is on
+// (ttrnn_kernel_timing, bench only) the groups run back to back on the caller's stream: events around launches that
+// share the SMs with another stream's kernels would not measure those kernels.
+struct GroupSlices {
+    int n = 1;
+    long long row0[kMaxGroups] = {0, 0};
+    ttrnn_rnn_desc d[kMaxGroups];
+    ttrnn_rnn_workspace w[kMaxGroups];
+    int64_t sv_off[kMaxGroups] = {0, 0}, f_off[kMaxGroups] = {0, 0}, b_off[kMaxGroups] = {0, 0}, dp_off[kMaxGroups] = {0, 0};
+};
+static int group_slices(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, GroupSlices *gs, const char *who) {
+    const long long ng = ws->plan[kPlanGroups], rows0 = ws->plan[kPlanRows0];
+    if (!d_in) return fail("null descriptor");
+    if (ng != 2 || rows0 <= 0 || rows0 >= d_in->batch)
+        return fail("%s: workspace struct does not belong to this descriptor (row groups %lld, %lld of %lld rows)", who, ng, rows0,
+                    (long long)d_in->batch);
+    const int64_t pf = ttrnn_rnn_param_count(d_in);
+    if (pf < 0) return 1;
+    gs->n = 2;
+    int64_t sv = 0, f = 0, b = 0;
+    for (int g = 0; g < 2; ++g) {
+        gs->row0[g] = g ? rows0 : 0;
+        gs->d[g] = *d_in;
+        gs->d[g].batch = g ? d_in->batch - rows0 : rows0;
+        if (workspace_one(&gs->d[g], &gs->w[g])) return 1;
+        memcpy(gs->w[g].plan, ws->plan, sizeof ws->plan);
+        gs->sv_off[g] = sv; sv += a256(gs->w[g].saved_bytes);
+        gs->f_off[g] = f;   f += a256(gs->w[g].fwd_scratch_bytes);
+        gs->b_off[g] = b;   b += a256(gs->w[g].bwd_scratch_bytes);
+        if (g > 0) { gs->dp_off[g] = b; b += a256(pf * 4); }
+    }
+    if (sv != ws->saved_bytes || f != ws->fwd_scratch_bytes || b != ws->bwd_scratch_bytes)
+        return fail("%s: workspace struct does not belong to this descriptor (group sizes %lld / %lld / %lld bytes vs %lld / %lld / %lld)",
+                    who, (long long)sv, (long long)f, (long long)b, (long long)ws->saved_bytes, (long long)ws->fwd_scratch_bytes,
+                    (long long)ws->bwd_scratch_bytes);
+    return 0;
+}
+
+int ttrnn_rnn_forward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                      const float *c0, const float *params, float *out, float *hT, float *cT, void *saved, void *scratch,
+                      void *stream) {
+    if (!ws || !plan_load(ws->plan, &t_opt))
+        return fail("ttrnn_rnn_forward: `ws` must be the struct filled by ttrnn_rnn_workspace_bytes() for this descriptor");
+    if (ws->plan[kPlanGroups] <= 1) return forward_one(d_in, ws, x, h0, c0, params, out, hT, cT, saved, scratch, stream);
+    if (!x || !params || !out || !scratch) return fail("x, params, out and scratch must be non-null");
+    GroupSlices gs;
+    if (group_slices(d_in, ws, &gs, "ttrnn_rnn_forward")) return 1;
+    GroupCtx *gc = group_ctx();
+    if (!gc) return fail("ttrnn_rnn_forward: cannot create the row-group stream");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool serial = g_timing.load() != 0;
+    if (!serial) {
+        CU_CHECK(cudaEventRecord(gc->fork, st));
+        CU_CHECK(cudaStreamWaitEvent(gc->s, gc->fork, 0));
+    }
+    const long long T = d_in->seq_len, I = d_in->input_size, H = d_in->hidden_size;
+    int rc = 0;
+    for (int g = 0; g < gs.n && !rc; ++g) {
+        const long long r0 = gs.row0[g];
+        t_group = g;
+        rc = forward_one(&gs.d[g], &gs.w[g], x + r0 * T * I, h0 ? h0 + r0 * H : nullptr, c0 ? c0 + r0 * H : nullptr, params,
+                         out + r0 * T * H, hT ? hT + r0 * H : nullptr, cT ? cT + r0 * H : nullptr,
+                         saved ? (char *)saved + gs.sv_off[g] : nullptr, (char *)scratch + gs.f_off[g],
+                         (g == 0 || serial) ? (void *)st : (void *)gc->s);
+    }
+    t_group = 0;
+    if (!serial) {       // also on the error path: the caller's stream must not run ahead of the group stream
+        cudaEventRecord(gc->join, gc->s);
+        cudaStreamWaitEvent(st, gc->join, 0);
+    }
+    return rc;
+}
+
+int ttrnn_rnn_backward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                       const float *c0, const float *params, const float *out, const void *saved, const float *d_out,
+                       const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
+                       void *scratch, void *stream) {
+    if (!ws || !plan_load(ws->plan, &t_opt))
+        return fail("ttrnn_rnn_backward: `ws` must be the struct the matching forward ran with");
+    if (ws->plan[kPlanGroups] <= 1)
+        return backward_one(d_in, ws, x, h0, c0, params, out, saved, d_out, d_hT, d_cT, d_params, d_x, d_h0, d_c0, scratch, stream);
+    if (!x || !params || !out || !scratch || !d_params) return fail("x, params, out, scratch, d_params must be non-null");
+    GroupSlices gs;
+    if (group_slices(d_in, ws, &gs, "ttrnn_rnn_backward")) return 1;
+    GroupCtx *gc = group_ctx();
+    if (!gc) return fail("ttrnn_rnn_backward: cannot create the row-group stream");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool serial = g_timing.load() != 0;
+    if (!serial) {
+        CU_CHECK(cudaEventRecord(gc->fork, st));
+        CU_CHECK(cudaStreamWaitEvent(gc->s, gc->fork, 0));
+    }
+    const long long T = d_in->seq_len, I = d_in->input_size, H = d_in->hidden_size;
+    const int64_t pf = ttrnn_rnn_param_count(d_in);
+    int rc = 0;
+    for (int g = 0; g < gs.n && !rc; ++g) {
+        const long long r0 = gs.row0[g];
+        float *dp = g == 0 ? d_params : (float *)((char *)scratch + gs.dp_off[g]);
+        t_group = g;
+        rc = backward_one(&gs.d[g], &gs.w[g], x + r0 * T * I, h0 ? h0 + r0 * H : nullptr, c0 ? c0 + r0 * H : nullptr, params,
+                          out + r0 * T * H, saved ? (const char *)saved + gs.sv_off[g] : nullptr,
+                          d_out ? d_out + r0 * T * H : nullptr, d_hT ? d_hT + r0 * H : nullptr, d_cT ? d_cT + r0 * H : nullptr, dp,
+                          d_x ? d_x + r0 * T * I : nullptr, d_h0 ? d_h0 + r0 * H : nullptr, d_c0 ? d_c0 + r0 * H : nullptr,
+                          (char *)scratch + gs.b_off[g], (g == 0 || serial) ? (void *)st : (void *)gc->s);
+    }
+    t_group = 0;
+    if (!serial) {
+        cudaEventRecord(gc->join, gc->s);
+        cudaStreamWaitEvent(st, gc->join, 0);
+    }
+    if (rc) return rc;
+    // parameter gradients: sum of the groups' blobs
+    for (int g = 1; g < gs.n; ++g)
+        if (axpy1((const float *)((char *)scratch + gs.dp_off[g]), d_params, pf, 1, st)) return 1;
     return 0;
 }
 

@@ -31,7 +31,7 @@ DEV = "cuda:0"
 def options(**kw):
     """Set library options for the duration of a block; restore the defaults afterwards."""
     defaults = {"chunk_steps": 0, "save_u_bytes": 16 << 30, "tc_gemm": 1, "static_rows_fwd": 0, "static_rows_bwd": 0,
-                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1, "tc_red_ts": 1, "bwd_overlap": 1, "tc_rows_ts": 1}
+                "dense_ih": 1, "split_kept": 1, "row_plan": 1, "static_kernels": 1, "rank_pad": 1, "tc_red_ts": 1, "bwd_overlap": 1, "tc_rows_ts": 1, "row_groups": 1}
     lib = _lib.load()
     for k, v in kw.items():
         assert lib.ttrnn_set_option(k.encode(), int(v)) == 0, k
