@@ -953,9 +953,20 @@ bool group_launches(const ttrnn_rnn_desc *d, const RnnPlan &rp, const RnnLayout 
 }
 
 // Decide the split.  Only for multi-layer stacks on the static kernels in single-chunk plans (the large-batch configs that
-// need time chunks run many waves per launch and lose little to the last one).  Candidates: group 0 = sms * m rows.  A
-// split is taken when the modelled forward + backward recurrence time drops by >= 6 % and the forward alone does not get
-// slower (inference runs the same split).
+// need time chunks run many waves per launch and lose little to the last one).  Candidates: every cut of the batch at a
+// multiple of 4 rows (row-indexed slices stay 16-byte aligned); each side gets the rows-per-CTA variants the single-group
+// path would pick for that many rows.  A split is taken when the modelled forward + backward recurrence time drops by
+// >= 6 % and the forward alone does not get slower (inference runs the same split).  The search costs a few ms, so the
+// result is cached per (descriptor, options, SM count) and host thread.
+struct GroupCacheEntry {
+    bool used = false;
+    ttrnn_rnn_desc d;
+    Opts o;
+    int sms = 0;
+    GroupPlan gp;
+};
+constexpr int kGroupCache = 16;
+
 int plan_row_groups(const ttrnn_rnn_desc *d_in, GroupPlan *gp, const DevInfo *dev = nullptr) {
     gp->n = 1;
     gp->rows[0] = d_in ? d_in->batch : 0;
@@ -967,11 +978,24 @@ int plan_row_groups(const ttrnn_rnn_desc *d_in, GroupPlan *gp, const DevInfo *de
         return 0;
     }
     if (!t_opt.stat || d_in->num_layers < 2) return 0;
-    RnnPlan rp;
-    if (build_rnn_plan(d_in, &rp)) return 1;
     DevInfo dv;
     if (dev) dv = *dev;
     else if (get_dev(&dv)) return 1;
+    thread_local GroupCacheEntry cache[kGroupCache];
+    thread_local int cache_next = 0;
+    for (const GroupCacheEntry &e : cache)
+        if (e.used && e.sms == dv.sms && !memcmp(&e.d, d_in, sizeof *d_in) && !memcmp(&e.o, &t_opt, sizeof t_opt)) {
+            *gp = e.gp;
+            return 0;
+        }
+    auto remember = [&]() {
+        GroupCacheEntry &e = cache[cache_next];
+        cache_next = (cache_next + 1) % kGroupCache;
+        e.used = true; e.d = *d_in; e.o = t_opt; e.sms = dv.sms; e.gp = *gp;
+        return 0;
+    };
+    RnnPlan rp;
+    if (build_rnn_plan(d_in, &rp)) return 1;
     EffDesc eff;
     if (make_eff_desc(d_in, &dv, &eff)) return 1;
     const ttrnn_rnn_desc *d = &eff.d;
@@ -979,27 +1003,26 @@ int plan_row_groups(const ttrnn_rnn_desc *d_in, GroupPlan *gp, const DevInfo *de
     RnnLayout lo;
     if (build_layout(d, rp, dv, &lo)) return 1;
     const long long B = d->batch;
-    if (lo.Tc != d->seq_len || B < 8 || B > 16LL * dv.sms) return 0;
+    if (lo.Tc != d->seq_len || B < 8 || B > 16LL * dv.sms) return remember();
     std::vector<SimLaunch> f1, b1;
-    if (!group_launches(d, rp, lo, B, dv.sms, &f1, &b1)) return 0;
+    if (!group_launches(d, rp, lo, B, dv.sms, &f1, &b1)) return remember();
     const double fwd1 = sim_makespan(&f1, 1, dv.sms), bwd1 = sim_makespan(&b1, 1, dv.sms);
     double best = fwd1 + bwd1;
-    for (int m = 1; m <= 8; ++m) {
-        const long long r0 = (long long)dv.sms * m;
-        if (r0 >= B) break;
-        if (r0 % 4 != 0 || (B - r0) < 1) continue;     // row-indexed slices stay 16-byte aligned
+    const long long step = B <= 1024 ? 4 : 16;
+    for (long long r0 = step; r0 < B; r0 += step) {
         std::vector<SimLaunch> fq[kMaxGroups], bq[kMaxGroups];
         if (!group_launches(d, rp, lo, r0, dv.sms, &fq[0], &bq[0]) || !group_launches(d, rp, lo, B - r0, dv.sms, &fq[1], &bq[1]))
             continue;
         const double f2 = sim_makespan(fq, 2, dv.sms), b2 = sim_makespan(bq, 2, dv.sms);
-        if (f2 <= fwd1 * 1.02 && f2 + b2 < best && f2 + b2 <= 0.94 * (fwd1 + bwd1)) {
+        // ties go to the later candidate: the larger group 0 (issued first, on the caller's stream) is the critical path
+        if (f2 <= fwd1 * 1.02 && f2 + b2 <= best + 1e-9 && f2 + b2 <= 0.94 * (fwd1 + bwd1)) {
             best = f2 + b2;
             gp->n = 2;
             gp->rows[0] = r0;
             gp->rows[1] = B - r0;
         }
     }
-    return 0;
+    return remember();
 }
 
 // stream + events of the second row group (one per host thread and device, kept for the life of the process)
@@ -1725,7 +1748,10 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                     sa.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
                     sa.dh_out = sdh; sa.dc_out = sdc;
                     if (launch_plan(sa)) return 1;
-                    if (side && l > 0 && nchunks == 1 && dense && dlin && dv.sms - sgrid >= 24) {
+                    // bwd_overlap = 1: fork only when this layer's BPTT grid leaves >= 24 SMs idle; 2: always (the deferred
+                    // GEMMs then fill whatever the recurrent kernels of BOTH row groups leave idle)
+                    const int idle_sms = dv.sms - sgrid;
+                    if (side && l > 0 && nchunks == 1 && dense && dlin && (idle_sms >= 24 || t_opt.bwd_overlap >= 2)) {
                         // overlap: dX (the next layer's input) first, then everything that only produces parameter gradients
                         // moves to the side stream, planned for the SMs the next BPTT kernel leaves idle
                         if (project_dx(t0, tc)) return 1;
@@ -1734,7 +1760,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                         CU_CHECK(cudaStreamWaitEvent(side->s, side->fork, 0));
                         ws = side->s;
                         join.used = true;
-                        dvw.sms = dv.sms - sgrid;
+                        dvw.sms = idle_sms >= 24 ? idle_sms : 48;
                     }
                     if (be->split) {
                         // hh core gradients over rows (h_{t-1}, delta_t) of this chunk: dense accumulation of
