@@ -421,6 +421,19 @@ class GpuBench(object):
         for i in range(nk):                            # scale to `steps` so that every consumer below divides by steps
             kms[i] = kms[i] * steps / ksteps
             kcnt[i] = int(kcnt[i] * steps / ksteps)
+        # per-launch records of that pass: the recurrent kernels per variant (rows per CTA) and grid
+        nrec = int(lib.ttrnn_kernel_launch_records(None, 0))
+        rbuf = (C.c_double * (6 * max(nrec, 1)))()
+        lib.ttrnn_kernel_launch_records(rbuf, nrec)
+        variants = {}
+        for i in range(nrec):
+            kind, R, ctas, rows, tsteps, ms = (rbuf[6 * i + j] for j in range(6))
+            if int(kind) not in (1, 2) or R <= 0:
+                continue
+            v = variants.setdefault((int(kind), int(R), int(ctas), int(rows)), {"launches": 0, "ms": 0.0, "row_steps": 0.0})
+            v["launches"] += 1
+            v["ms"] += ms
+            v["row_steps"] += rows * tsteps
 
         # ---- e2e: pinned host input -> H2D -> module API -> D2H of the result, wall clock ----------
         e2e_ms, d2h = 0.0, 0
@@ -503,7 +516,31 @@ class GpuBench(object):
                 kern[KINDS[i]]["credited_tflops"] = cred[KINDS[i]] * B * T / (ms * 1e-3) / 1e12 if ms > 0 else None
                 kern[KINDS[i]]["frac_of_ffma_peak"] = (kern[KINDS[i]]["credited_tflops"] / self.peak
                                                        if ms > 0 and self.peak else None)
+            # the recurrent kernels per variant: every (kind, rows per CTA, grid) is one template instantiation launched
+            # with one grid; credited FLOPs of a launch = its rows x its timesteps x the per-layer credit of its kind
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            vlist = []
+            for (kind, R, ctas, rows), v in sorted(variants.items()):
+                per_layer = cred[KINDS[kind]] / cfg["L"]
+                tf = per_layer * v["row_steps"] / (v["ms"] * 1e-3) / 1e12 if v["ms"] > 0 else 0.0
+                vlist.append({"kernel": KINDS[kind], "rows_per_cta": R, "ctas": ctas, "rows": rows,
+                              "launches_per_step": v["launches"] / ksteps, "ms_per_launch": v["ms"] / v["launches"],
+                              "ms_per_step": v["ms"] / ksteps, "credited_tflops": tf,
+                              "frac_of_ffma_peak": tf / self.peak if self.peak else None,
+                              # the same on the SMs the grid occupies (one CTA per SM); the other SMs run the other row
+                              # group's kernels in the concurrent run
+                              "frac_on_occupied_sms": (tf / self.peak) * (sms / min(ctas, sms)) if self.peak and ctas else None})
             whole = mult * fwd_flops * B * T * steps / (total_ms * 1e-3) / 1e12
+            # dominant KERNEL of the step = the instantiation (variant + grid) with the largest time per step; `achieved` =
+            # its algorithmic FLOPs per launch / its average launch duration.  The aggregate over every variant of the same
+            # kind (the round-1 definition) stays beside it as kind_group_frac.
+            group_frac = achieved / self.peak if self.peak else None
+            roof_kernel, flops_per_launch = KINDS[dom], None
+            vd = max(vlist, key=lambda v: v["ms_per_step"]) if vlist else None
+            if vd is not None and KINDS[dom] in ("k_rnn_fwd", "k_rnn_bwd") and vd["kernel"] == KINDS[dom]:
+                roof_kernel = "%s (%d rows per CTA, %d CTAs, %d rows per launch)" % (vd["kernel"], vd["rows_per_cta"], vd["ctas"], vd["rows"])
+                achieved = vd["credited_tflops"]
+                flops_per_launch = vd["credited_tflops"] * 1e12 * vd["ms_per_launch"] * 1e-3
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -521,13 +558,19 @@ class GpuBench(object):
                 "e2e": ({"value": units / (e2e_ms * 1e-3), "unit": "cell-steps/s", "h2d_bytes_per_step": x_host.numel() * 4,
                          "d2h_bytes_per_step": d2h} if with_e2e else None),
                 "gpu_launches": launches, "tc_gemm_launches": tc_launches,
-                "roofline": {"bound": "fp32_ffma", "kernel": KINDS[dom], "achieved": achieved, "peak": self.peak,
+                "roofline": {"bound": "fp32_ffma", "kernel": roof_kernel, "achieved": achieved, "peak": self.peak,
                              "unit": "TFLOP/s", "frac": achieved / self.peak if self.peak else None, "traffic": traffic,
+                             "algorithmic_flops_per_launch": flops_per_launch,
+                             "kind_group": KINDS[dom], "kind_group_frac": group_frac,
                              "traffic_unit": "bytes per launch (ncu dram read+write, profiles/)",
                              "peak_source": "ttrnn_ffma_probe measured in this run (MEASURED_PEAKS.json has no FP32 entry)",
                              "algorithmic_flops_per_seqstep": cred[KINDS[dom]],
                              "whole_step_tflops_per_gpu": whole, "whole_step_frac": whole / self.peak if self.peak else None,
-                             "fwd_flops_per_seqstep": fwd_flops, "kernels": kern, "plan": plan,
+                             "fwd_flops_per_seqstep": fwd_flops, "kernels": kern, "recurrent_variants": vlist,
+                             "kernel_times": "second pass of %d steps with an event pair around every launch; row groups run "
+                                             "back to back in that pass, so these are each kernel's own durations (what an ncu "
+                                             "launch list gives), while ms_per_step is the concurrent run" % ksteps,
+                             "plan": plan,
                              # the second bound SURVEY.md 8d asks for: the sequential chain.  A CTA owns its rows for all T, so a
                              # layer-pass cannot be shorter than T x (per-step dependency chain); these are the measured per-step
                              # times of the recurrent kernels (all row tiles of a layer run concurrently when they fit the SMs)

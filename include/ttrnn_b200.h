@@ -211,6 +211,11 @@ int64_t ttrnn_launch_count(int32_t reset);
 #define TTRNN_K_KINDS        7
 int ttrnn_kernel_timing(int32_t enable);
 int ttrnn_kernel_times(double *ms /*[TTRNN_K_KINDS]*/, int64_t *count /*[TTRNN_K_KINDS]*/);
+/* Per-launch records of the last ttrnn_kernel_times() call: 6 doubles per record = {kind, rows per CTA, grid size (CTAs),
+ * batch rows of the launch, timesteps of the launch, milliseconds}; all but kind and milliseconds are 0 for the kinds
+ * that are not recurrent kernels.
+ * Returns the number of records (buf NULL: just the count).  bench.py reports the recurrent kernels per variant from it. */
+int64_t ttrnn_kernel_launch_records(double *buf, int64_t cap_records);
 
 /* Which contraction order the batched ih projection of `layer` uses: 0 = TT chain core by core
  * (t3nsor/ops.py:81-90), 1 = dense route (W_ih formed once per call from the cores, then one dense

@@ -79,6 +79,7 @@ SYMBOLS = {
     "ttrnn_launch_count": (C.c_int64, [C.c_int32]),
     "ttrnn_kernel_timing": (C.c_int, [C.c_int32]),
     "ttrnn_kernel_times": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    "ttrnn_kernel_launch_records": (C.c_int64, [C.POINTER(C.c_double), C.c_int64]),
     "ttrnn_set_option": (C.c_int, [C.c_char_p, C.c_int64]),
 }
 

@@ -99,9 +99,12 @@ bool plan_load(const int64_t *plan, Opts *o) {
 }
 
 // ---- optional per-kernel event timing (bench only) -----------------------------------------
-struct TimedLaunch { int kind; cudaEvent_t a, b; };
+// R / ctas / rows / steps: rows per CTA, grid size, batch rows and timesteps of a recurrent-kernel launch (0 for the other kinds)
+struct TimedLaunch { int kind; cudaEvent_t a, b; int R, ctas; long long rows; int steps; };
+struct LaunchRecord { int kind, R, ctas; long long rows; int steps; double ms; };
 std::mutex g_time_mu;
 std::vector<TimedLaunch> g_timed;
+std::vector<LaunchRecord> g_records;           // per-launch durations of the last ttrnn_kernel_times() call
 std::atomic<int> g_timing{0};
 constexpr size_t kMaxTimed = 8192;
 
@@ -110,7 +113,11 @@ struct KernelTimer {
     int kind;
     cudaStream_t st;
     bool on = false;
-    KernelTimer(int kind_, cudaStream_t st_) : kind(kind_), st(st_) {
+    int R, ctas;
+    long long rows;
+    int steps;
+    KernelTimer(int kind_, cudaStream_t st_, int R_ = 0, int ctas_ = 0, long long rows_ = 0, int steps_ = 0)
+        : kind(kind_), st(st_), R(R_), ctas(ctas_), rows(rows_), steps(steps_) {
         if (!g_timing.load()) return;
         {
             std::lock_guard<std::mutex> lk(g_time_mu);
@@ -124,7 +131,7 @@ struct KernelTimer {
         if (!on) return;
         cudaEventRecord(b, st);
         std::lock_guard<std::mutex> lk(g_time_mu);
-        g_timed.push_back({kind, a, b});
+        g_timed.push_back({kind, a, b, R, ctas, rows, steps});
     }
 };
 
@@ -1070,17 +1077,33 @@ int ttrnn_kernel_times(double *ms, int64_t *count) {
         std::lock_guard<std::mutex> lk(g_time_mu);
         recs.swap(g_timed);
     }
+    std::vector<LaunchRecord> out;
     for (auto &r : recs) {
         float t = 0.f;
         if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess &&
             r.kind >= 0 && r.kind < TTRNN_K_KINDS) {
             ms[r.kind] += t;
             count[r.kind] += 1;
+            out.push_back({r.kind, r.R, r.ctas, r.rows, r.steps, (double)t});
         }
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);
     }
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    g_records.swap(out);
     return 0;
+}
+
+int64_t ttrnn_kernel_launch_records(double *buf, int64_t cap_records) {
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    const int64_t n = (int64_t)g_records.size();
+    if (!buf) return n;
+    for (int64_t i = 0; i < n && i < cap_records; ++i) {
+        const LaunchRecord &r = g_records[i];
+        double *o = buf + 6 * i;
+        o[0] = r.kind; o[1] = r.R; o[2] = r.ctas; o[3] = (double)r.rows; o[4] = r.steps; o[5] = r.ms;
+    }
+    return n;
 }
 
 int ttrnn_set_option(const char *key, int64_t value) {
@@ -1412,7 +1435,7 @@ static int forward_one(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws
                 sa.h_out = (last && l == L - 1 && hT) ? hT : st_h;
                 sa.c_out = (last && l == L - 1 && cT) ? cT : st_c;
                 {
-                    KernelTimer tm(TTRNN_K_RNN_FWD, st);
+                    KernelTimer tm(TTRNN_K_RNN_FWD, st, se->R, (int)g, B, tc);
                     rc = se->launch(&sa, (int)g, st);
                 }
                 ++g_launches;
@@ -1453,7 +1476,7 @@ static int forward_one(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws
             a.h_out = (last && l == L - 1 && hT) ? hT : st_h;
             a.c_out = (last && l == L - 1 && cT) ? cT : st_c;
             {
-                KernelTimer tm(TTRNN_K_RNN_FWD, st);
+                KernelTimer tm(TTRNN_K_RNN_FWD, st, R, grid, B, tc);
                 k_rnn_fwd<<<grid, TT_NTHREADS, smem, st>>>(a);
             }
             ++g_launches;
@@ -1684,7 +1707,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                     if (a2.u_save) a2.u_save += r0 * a2.u_bstride;
                     int e;
                     {
-                        KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                        KernelTimer tm(TTRNN_K_RNN_BWD, st, ph_e[q]->R, ph_grid[q], ph_rows[q], a2.steps);
                         e = ph_e[q]->launch(&a2, ph_grid[q], st);
                     }
                     ++g_launches;
@@ -1875,7 +1898,7 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
             a.dc_in = last ? (l == L - 1 ? d_cT : nullptr) : sdc;
             a.dh_out = sdh; a.dc_out = sdc;
             {
-                KernelTimer tm(TTRNN_K_RNN_BWD, st);
+                KernelTimer tm(TTRNN_K_RNN_BWD, st, R, grid, B, tc);
                 k_rnn_bwd<<<grid, TT_NTHREADS, smem, st>>>(a);
             }
             ++g_launches;
