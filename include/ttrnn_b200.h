@@ -89,6 +89,10 @@ const char *ttrnn_last_error(void);            /* thread-local, never NULL */
 int64_t ttrnn_rnn_param_count(const ttrnn_rnn_desc *desc);
 
 int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws);
+/* The same with flags.  TTRNN_WS_WHOLE_BATCH: plan one row group, so that every layer's h_t / c_t sequence is one
+ * (B,T,H) block of `saved` (required by ttrnn_rnn_saved_layout / ttrnn_rnn_backward_logged). */
+#define TTRNN_WS_WHOLE_BATCH 1
+int ttrnn_rnn_workspace_bytes_ex(const ttrnn_rnn_desc *desc, int32_t flags, ttrnn_rnn_workspace *ws);
 
 /* Forward over the whole stack.  h0 / c0 may be NULL (zeros); one (h0, c0) seeds
  * every layer (lstm.py:120-121).  c0 / cT / d_c* are ignored for GRU.
@@ -111,6 +115,24 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *desc, const ttrnn_rnn_workspace *ws
                        const float *d_out, const float *d_hT, const float *d_cT,
                        float *d_params, float *d_x, float *d_h0, float *d_c0,
                        void *scratch, void *stream);
+
+/* log_grads=True (tensorized_rnn/lstm.py:35-39,66-80, gru.py:47-48,76-85, rnn_utils.py:127-172): the reference hooks
+ * every cell call and logs, per layer and timestep, mean_b ||v||^2 and mean_b log ||v||^2 of h_t, c_t and of the
+ * gradients reaching them.  Fused form: the training forward already keeps every layer's h_t / c_t sequence
+ * (ttrnn_rnn_saved_layout says where: float offsets into `saved`; hs_off = -1 means the last layer, whose sequence is
+ * `out`; cs_off = -1 for GRU), ttrnn_rnn_backward_logged additionally makes the BPTT kernel of layer l write the TOTAL
+ * gradient of h_t (and c_t, LSTM) of every step -- what the reference's tensor hooks on hy / cy receive -- into
+ * dh_log / dc_log, (L,B,T,H) each (dc_log may be NULL), and ttrnn_step_norms reduces a (B,T,H) block to the two logged
+ * statistics: out[0:T] = mean_b ||v[b,t]||^2, out[T:2T] = mean_b log ||v[b,t]||^2. */
+int ttrnn_rnn_saved_layout(const ttrnn_rnn_desc *desc, const ttrnn_rnn_workspace *ws, int32_t layer,
+                           int64_t *hs_off, int64_t *cs_off);
+int ttrnn_rnn_backward_logged(const ttrnn_rnn_desc *desc, const ttrnn_rnn_workspace *ws,
+                              const float *x, const float *h0, const float *c0,
+                              const float *params, const float *out, const void *saved,
+                              const float *d_out, const float *d_hT, const float *d_cT,
+                              float *d_params, float *d_x, float *d_h0, float *d_c0,
+                              void *scratch, void *stream, float *dh_log, float *dc_log);
+int ttrnn_step_norms(const float *v, int64_t B, int32_t T, int32_t H, float *out, void *stream);
 
 /* Stand-alone TT linear map y = x W^T + bias over `rows` rows:
  * replaces TTLinear.forward (t3nsor/layers.py:121-127) -> tt_dense_matmul

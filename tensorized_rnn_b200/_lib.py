@@ -14,6 +14,7 @@ ABI_VERSION = 3
 MAX_CORES = 6
 MAX_LAYERS = 8
 PLAN_WORDS = 24
+WS_WHOLE_BATCH = 1
 CELL_LSTM, CELL_GRU = 0, 1
 
 _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libttrnn_b200.so")
@@ -53,6 +54,11 @@ SYMBOLS = {
     "ttrnn_last_error": (C.c_char_p, []),
     "ttrnn_rnn_param_count": (C.c_int64, [C.POINTER(RnnDesc)]),
     "ttrnn_rnn_workspace_bytes": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)]),
+    "ttrnn_rnn_workspace_bytes_ex": (C.c_int, [C.POINTER(RnnDesc), C.c_int32, C.POINTER(RnnWorkspace)]),
+    "ttrnn_rnn_saved_layout": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace), C.c_int32, C.POINTER(C.c_int64),
+                                         C.POINTER(C.c_int64)]),
+    "ttrnn_rnn_backward_logged": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)] + [_P] * 17),
+    "ttrnn_step_norms": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
     "ttrnn_rnn_forward": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)] + [_P] * 10),
     "ttrnn_rnn_backward": (C.c_int, [C.POINTER(RnnDesc), C.POINTER(RnnWorkspace)] + [_P] * 15),
     "ttrnn_ttlinear_param_count": (C.c_int64, [C.POINTER(TTShape)]),

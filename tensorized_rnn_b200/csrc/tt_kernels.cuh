@@ -319,6 +319,10 @@ struct RnnBwdArgs {
     float *dc_out;         // (B,H)
     float *partial;        // [gridDim.x][core_floats + G*H]: hh core grads + hh bias grad (GRU)
     float *spill;          // [gridDim.x][R * spill_floats] or null
+    // log_grads (reference lstm.py:35-39,66-80): total gradient of h_t / c_t of every step, what the reference's tensor
+    // hooks on hy / cy see; (B,T,H) addressed like hs, or null
+    float *dh_log;
+    float *dc_log;
 };
 
 // base of the X_k slot: shared memory or the per-CTA global spill area
@@ -580,6 +584,7 @@ k_rnn_bwd(const __grid_constant__ RnnBwdArgs a) {
                     float dh = dhd[b * H + h] + dhc[b * sl.BS + hix];
                     if (a.dhs) dh += __ldg(a.dhs + (row * a.T + tg) * H + h);
                     float *dxg = a.xg + row * a.xg_bstride + (long long)t * GH;
+                    if (a.dh_log) a.dh_log[(row * a.T + tg) * H + h] = dh;
                     if (lstm) {
                         const float ig = tt_sigmoid(gb[gi0] + xb[h]);
                         const float fg = tt_sigmoid(gb[gi1] + xb[H + h]);
@@ -589,6 +594,7 @@ k_rnn_bwd(const __grid_constant__ RnnBwdArgs a) {
                         const float cnew = fg * cprev + ig * gg;
                         const float tc = tanhf(cnew);
                         const float dc = dcs[b * H + h] + dh * og * (1.0f - tc * tc);
+                        if (a.dc_log) a.dc_log[(row * a.T + tg) * H + h] = dc;
                         const float d_i = dc * gg * ig * (1.0f - ig);
                         const float d_f = dc * cprev * fg * (1.0f - fg);
                         const float d_g = dc * ig * (1.0f - gg * gg);
@@ -643,6 +649,31 @@ __global__ void k_reduce_partials(const float *__restrict__ partial, int nslots,
     float s = 0.f;
     for (int i = 0; i < nslots; ++i) s += partial[(long long)i * slot_stride + e];
     out[e] = s;
+}
+
+// Per-step batch statistics of a (B,T,H) tensor, the two quantities ActivGradLogger keeps (reference rnn_utils.py:217-226):
+//   out[t] = mean_b ||v[b,t,:]||^2,   out[T + t] = mean_b log ||v[b,t,:]||^2.   One CTA per timestep, one warp per row.
+__global__ void __launch_bounds__(256) k_step_norms(const float *__restrict__ v, long long B, int T, int H,
+                                                    float *__restrict__ out) {
+    __shared__ float s_sum[8], s_log[8];
+    const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float acc = 0.f, acc_log = 0.f;
+    for (long long b = warp; b < B; b += 8) {
+        const float *row = v + (b * T + t) * (long long)H;
+        float q = 0.f;
+        for (int h = lane; h < H; h += 32) q = fmaf(row[h], row[h], q);
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        acc += q;
+        acc_log += logf(q);
+    }
+    if (lane == 0) { s_sum[warp] = acc; s_log[warp] = acc_log; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, l = 0.f;
+        for (int w = 0; w < 8; ++w) { a += s_sum[w]; l += s_log[w]; }
+        out[t] = a / (float)B;
+        out[T + t] = l / (float)B;
+    }
 }
 
 __global__ void k_fill(float *dst, float v, int n) {

@@ -869,6 +869,11 @@ int dense_dw(const DevInfo &dv, long long rows, int rpb, const float *x, long lo
 // single-group path on its slice of every row-indexed buffer (own region of `saved` and of the scratch buffers, own
 // dense-route GEMMs, own gradient blob, summed at the end), so results do not depend on the split beyond FP32 summation
 // order of the parameter gradients.
+// per-step gradient logging (log_grads, ttrnn_rnn_backward_logged): (L, B, T, H) buffers the BPTT kernel of layer l writes
+// the total gradient of h_t / c_t of every step into; set for the duration of one backward call on this thread
+struct StepLog { float *dh = nullptr, *dc = nullptr; long long layer_stride = 0; };
+thread_local StepLog t_log;
+
 constexpr int kMaxGroups = 2;
 thread_local int t_group = 0;          // group the calling thread is issuing work for (selects the side-stream context)
 struct GroupPlan {
@@ -1286,8 +1291,13 @@ static int workspace_one(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
 }
 
 int ttrnn_rnn_workspace_bytes(const ttrnn_rnn_desc *desc, ttrnn_rnn_workspace *ws) {
+    return ttrnn_rnn_workspace_bytes_ex(desc, 0, ws);
+}
+
+int ttrnn_rnn_workspace_bytes_ex(const ttrnn_rnn_desc *desc, int32_t flags, ttrnn_rnn_workspace *ws) {
     if (!ws) return fail("null workspace struct");
     t_opt = snapshot_options();
+    if (flags & TTRNN_WS_WHOLE_BATCH) t_opt.row_groups = 0;
     GroupPlan gp;
     if (plan_row_groups(desc, &gp)) return 1;
     if (gp.n == 1) {
@@ -1645,8 +1655,11 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
         };
 
         // ---- statically specialised BPTT kernel for this hh shape, if one is registered ---------------
-        const TtsRnnBwdEntry *be = t_opt.stat ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd) : nullptr;
-        if (t_opt.stat && lo.save_mode[l] != 0 && sv) {
+        // per-step gradient logging is emitted by the runtime-shape BPTT kernel (it recomputes from hs / cs, which every
+        // training forward keeps, so it can follow a forward that ran on the static kernels)
+        const bool logging = t_log.dh != nullptr;
+        const TtsRnnBwdEntry *be = (t_opt.stat && !logging) ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd) : nullptr;
+        if (t_opt.stat && !logging && lo.save_mode[l] != 0 && sv) {
             // forward kept (X_0 and) the hh pre-activations of this layer: use the kernel that consumes them
             if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd,
                                                             lo.save_mode[l], dense_hh_dw_ok(lp.hh) && t_opt.split_kept))
@@ -1873,6 +1886,10 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
         a.cores = params + lp.off_hh_cores;
         a.bias_hh = lstm ? nullptr : b_hh;
         a.hs = lout; a.cs = lcs; a.h0 = h0; a.c0 = c0; a.dhs = dhs;
+        if (logging) {
+            a.dh_log = t_log.dh + (long long)l * t_log.layer_stride;
+            a.dc_log = (lstm && t_log.dc) ? t_log.dc + (long long)l * t_log.layer_stride : nullptr;
+        }
         const size_t smem = cfg.smem;
         int grid = 0;
         if (grid_for(k_rnn_bwd, smem, (B + R - 1) / R, dv, &grid)) return 1;
@@ -2045,6 +2062,52 @@ int ttrnn_rnn_backward(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws
     // parameter gradients: sum of the groups' blobs
     for (int g = 1; g < gs.n; ++g)
         if (axpy1((const float *)((char *)scratch + gs.dp_off[g]), d_params, pf, 1, st)) return 1;
+    return 0;
+}
+
+int ttrnn_rnn_backward_logged(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, const float *x, const float *h0,
+                              const float *c0, const float *params, const float *out, const void *saved, const float *d_out,
+                              const float *d_hT, const float *d_cT, float *d_params, float *d_x, float *d_h0, float *d_c0,
+                              void *scratch, void *stream, float *dh_log, float *dc_log) {
+    if (!d_in || !ws) return fail("null descriptor / workspace struct");
+    if (!dh_log) return fail("ttrnn_rnn_backward_logged: dh_log must be non-null");
+    if (ws->plan[kPlanGroups] > 1)
+        return fail("ttrnn_rnn_backward_logged needs a whole-batch plan: size the call with "
+                    "ttrnn_rnn_workspace_bytes_ex(desc, TTRNN_WS_WHOLE_BATCH, ws)");
+    t_log.dh = dh_log;
+    t_log.dc = dc_log;
+    t_log.layer_stride = (long long)d_in->batch * d_in->seq_len * d_in->hidden_size;
+    const int rc = ttrnn_rnn_backward(d_in, ws, x, h0, c0, params, out, saved, d_out, d_hT, d_cT, d_params, d_x, d_h0, d_c0,
+                                      scratch, stream);
+    t_log = StepLog();
+    return rc;
+}
+
+int ttrnn_rnn_saved_layout(const ttrnn_rnn_desc *d_in, const ttrnn_rnn_workspace *ws, int32_t layer, int64_t *hs_off,
+                           int64_t *cs_off) {
+    if (!ws || !plan_load(ws->plan, &t_opt)) return fail("ttrnn_rnn_saved_layout: `ws` must come from ttrnn_rnn_workspace_bytes()");
+    if (ws->plan[kPlanGroups] > 1) return fail("ttrnn_rnn_saved_layout needs a whole-batch plan (TTRNN_WS_WHOLE_BATCH)");
+    if (!hs_off || !cs_off) return fail("hs_off and cs_off must be non-null");
+    RnnPlan rp;
+    if (build_rnn_plan(d_in, &rp)) return 1;
+    if (layer < 0 || layer >= d_in->num_layers) return fail("layer %d out of range", layer);
+    DevInfo dv;
+    if (get_dev(&dv)) return 1;
+    EffDesc eff;
+    if (make_eff_desc(d_in, &dv, &eff)) return 1;
+    if (eff.padded && build_rnn_plan(&eff.d, &rp)) return 1;
+    RnnLayout lo;
+    if (build_layout(&eff.d, rp, dv, &lo)) return 1;
+    *hs_off = (layer == d_in->num_layers - 1) ? -1 : lo.sv_hs + (long long)layer * lo.BTH;
+    *cs_off = (d_in->cell == TTRNN_CELL_LSTM) ? lo.sv_cs + (long long)layer * lo.BTH : -1;
+    return 0;
+}
+
+int ttrnn_step_norms(const float *v, int64_t B, int32_t T, int32_t H, float *out, void *stream) {
+    if (!v || !out || B < 1 || T < 1 || H < 1) return fail("ttrnn_step_norms: bad arguments");
+    k_step_norms<<<(unsigned)T, 256, 0, (cudaStream_t)stream>>>(v, B, T, H, out);
+    ++g_launches;
+    CU_CHECK(cudaGetLastError());
     return 0;
 }
 

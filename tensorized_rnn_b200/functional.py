@@ -79,9 +79,21 @@ def _dense16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t
 
 
+def _step_stats(lib, v: torch.Tensor, stream) -> torch.Tensor:
+    """(2, T): mean_b ||v[b,t]||^2 and mean_b log ||v[b,t]||^2 of a contiguous (B,T,H) block (ttrnn_step_norms)."""
+    B, T, H = v.shape
+    out = torch.empty((2, T), device=v.device, dtype=torch.float32)
+    _lib.check(lib.ttrnn_step_norms(_ptr(v), B, T, H, _ptr(out), stream), "ttrnn_step_norms")
+    return out
+
+
 class _RnnFunction(torch.autograd.Function):
+    """`step_log` (None or an object with .activations(layer, var, stats) / .gradients(layer, var, stats)): fused
+    log_grads.  The training forward reports the per-step statistics of every layer's h_t / c_t sequence, the
+    backward those of the total gradients reaching them, (2, T) tensors each (reference rnn_utils.py:127-172)."""
+
     @staticmethod
-    def forward(ctx, spec: RnnSpec, grad_enabled: bool, x, h0, c0, *params):
+    def forward(ctx, spec: RnnSpec, grad_enabled: bool, step_log, x, h0, c0, *params):
         lib = _lib.load()
         _require_cuda_f32("input", x)
         for i, p in enumerate(params):
@@ -109,10 +121,13 @@ class _RnnFunction(torch.autograd.Function):
             if want != blob.numel():
                 raise RuntimeError("parameter blob has %d floats, descriptor expects %d" % (blob.numel(), want))
             ws = _lib.RnnWorkspace()
-            _lib.check(lib.ttrnn_rnn_workspace_bytes(C.byref(desc), C.byref(ws)), "ttrnn_rnn_workspace_bytes")
+            _lib.check(lib.ttrnn_rnn_workspace_bytes_ex(C.byref(desc), _lib.WS_WHOLE_BATCH if step_log is not None else 0,
+                                                        C.byref(ws)), "ttrnn_rnn_workspace_bytes")
             # grad mode is always off inside Function.forward and needs_input_grad stays True for nn.Parameters under
             # torch.no_grad(): the caller captures torch.is_grad_enabled() before .apply
-            training = bool(grad_enabled) and any(ctx.needs_input_grad[2:])
+            training = bool(grad_enabled) and any(ctx.needs_input_grad[3:])
+            if step_log is not None and not training:
+                raise RuntimeError("fused per-step logging needs a training forward (it reads the kept h_t / c_t sequences)")
             out = torch.empty((B, T, H), device=x.device, dtype=torch.float32)
             hT = torch.empty((B, H), device=x.device, dtype=torch.float32)
             cT = torch.empty((B, H), device=x.device, dtype=torch.float32) if spec.cell == "lstm" else None
@@ -123,8 +138,18 @@ class _RnnFunction(torch.autograd.Function):
             _lib.check(lib.ttrnn_rnn_forward(C.byref(desc), C.byref(ws), _ptr(x), _ptr(h0c), _ptr(c0c), _ptr(blob), _ptr(out),
                                              _ptr(hT), _ptr(cT), _ptr(saved), _ptr(scratch), stream),
                        "ttrnn_rnn_forward")
+            if step_log is not None:
+                hs_off, cs_off = C.c_int64(), C.c_int64()
+                for l in range(spec.num_layers):
+                    _lib.check(lib.ttrnn_rnn_saved_layout(C.byref(desc), C.byref(ws), l, C.byref(hs_off), C.byref(cs_off)),
+                               "ttrnn_rnn_saved_layout")
+                    hs = out if hs_off.value < 0 else saved[hs_off.value:hs_off.value + B * T * H].view(B, T, H)
+                    step_log.activations(l, "h", _step_stats(lib, hs, stream))
+                    if cs_off.value >= 0:
+                        step_log.activations(l, "c", _step_stats(lib, saved[cs_off.value:cs_off.value + B * T * H].view(B, T, H), stream))
         if training:
             ctx.spec = spec
+            ctx.step_log = step_log
             ctx.shapes = [tuple(p.shape) for p in params]
             ctx.ws = ws                    # sizes + execution plan: backward runs from the same plan as this forward
             ctx.bwd_floats = _bytes_to_floats(ws.bwd_scratch_bytes)
@@ -151,34 +176,44 @@ class _RnnFunction(torch.autograd.Function):
         d_cT = _dense16(d_cT)
         with torch.cuda.device(x.device):
             d_blob = torch.empty_like(blob)
-            d_x = torch.empty_like(x) if ctx.needs_input_grad[2] else None
+            d_x = torch.empty_like(x) if ctx.needs_input_grad[3] else None
             d_h0 = torch.empty((B, H), device=x.device, dtype=torch.float32) \
-                if (ctx.has_h0 and ctx.needs_input_grad[3]) else None
+                if (ctx.has_h0 and ctx.needs_input_grad[4]) else None
             d_c0 = torch.empty((B, H), device=x.device, dtype=torch.float32) \
-                if (spec.cell == "lstm" and ctx.has_c0 and ctx.needs_input_grad[4]) else None
+                if (spec.cell == "lstm" and ctx.has_c0 and ctx.needs_input_grad[5]) else None
             scratch = torch.empty(ctx.bwd_floats, device=x.device, dtype=torch.float32)
             stream = torch.cuda.current_stream(x.device).cuda_stream
-            _lib.check(lib.ttrnn_rnn_backward(C.byref(desc), C.byref(ctx.ws), _ptr(x), _ptr(h0), _ptr(c0), _ptr(blob), _ptr(out),
-                                              _ptr(saved), _ptr(d_out), _ptr(d_hT), _ptr(d_cT), _ptr(d_blob),
-                                              _ptr(d_x), _ptr(d_h0), _ptr(d_c0), _ptr(scratch), stream),
-                       "ttrnn_rnn_backward")
+            args = (C.byref(desc), C.byref(ctx.ws), _ptr(x), _ptr(h0), _ptr(c0), _ptr(blob), _ptr(out),
+                    _ptr(saved), _ptr(d_out), _ptr(d_hT), _ptr(d_cT), _ptr(d_blob),
+                    _ptr(d_x), _ptr(d_h0), _ptr(d_c0), _ptr(scratch), stream)
+            if ctx.step_log is None:
+                _lib.check(lib.ttrnn_rnn_backward(*args), "ttrnn_rnn_backward")
+            else:
+                L = spec.num_layers
+                dh_log = torch.empty((L, B, T, H), device=x.device, dtype=torch.float32)
+                dc_log = torch.empty((L, B, T, H), device=x.device, dtype=torch.float32) if spec.cell == "lstm" else None
+                _lib.check(lib.ttrnn_rnn_backward_logged(*(args + (_ptr(dh_log), _ptr(dc_log)))), "ttrnn_rnn_backward_logged")
+                for l in range(L):
+                    ctx.step_log.gradients(l, "h", _step_stats(lib, dh_log[l], stream))
+                    if dc_log is not None:
+                        ctx.step_log.gradients(l, "c", _step_stats(lib, dc_log[l], stream))
         d_params: List[Optional[torch.Tensor]] = []
         off = 0
         for i, shp in enumerate(ctx.shapes):
             n = 1
             for v in shp:
                 n *= v
-            d_params.append(d_blob[off:off + n].view(shp) if ctx.needs_input_grad[5 + i] else None)
+            d_params.append(d_blob[off:off + n].view(shp) if ctx.needs_input_grad[6 + i] else None)
             off += n
-        return (None, None, d_x, d_h0, d_c0) + tuple(d_params)
+        return (None, None, None, d_x, d_h0, d_c0) + tuple(d_params)
 
 
 def rnn_sequence(spec: RnnSpec, x: torch.Tensor, h0: Optional[torch.Tensor], c0: Optional[torch.Tensor],
-                 params: Sequence[torch.Tensor]):
-    """Run the whole stack over the whole sequence.  Returns (out, hT[, cT])."""
+                 params: Sequence[torch.Tensor], step_log=None):
+    """Run the whole stack over the whole sequence.  Returns (out, hT[, cT]).  `step_log`: see _RnnFunction."""
     if x.dim() != 3:
         raise ValueError("input must be (batch, seq_len, input_size), got shape %s" % (tuple(x.shape),))
-    return _RnnFunction.apply(spec, torch.is_grad_enabled(), x, h0, c0, *params)
+    return _RnnFunction.apply(spec, torch.is_grad_enabled(), step_log, x, h0, c0, *params)
 
 
 class _TTLinearFunction(torch.autograd.Function):

@@ -13,8 +13,13 @@ Two execution modes, chosen per module:
     (lstm.py:123-133), used when the reference feature needs per-step module calls:
     `is_naive=True` (one TT matrix per gate, tt_linearset.py:5-38; the gate blocks come from
     G batched TT-matvec kernel calls and a fused gate kernel, `ttrnn_cell_forward/backward`) and
-    `log_grads=True` (forward hooks on the cells + tensor hooks on h_t / c_t feeding
-    `ActivGradLogger`, rnn_utils.py:42-215; each step is then one fused single-step call).
+    `log_grads=True` with `fused_logging = False` or outside a training forward (forward hooks on the
+    cells + tensor hooks on h_t / c_t feeding `ActivGradLogger`, rnn_utils.py:42-215; each step is then
+    one fused single-step call).
+  A training forward of a `log_grads=True` module stays fused (`fused_logging`, the default): the sequence
+  kernels keep every layer's h_t / c_t, the BPTT kernel writes the total gradient of h_t / c_t of every
+  step, and one reduction per (layer, variable) turns them into the four logged statistics
+  (`ttrnn_rnn_backward_logged`, `ttrnn_step_norms`) that are appended to the same loggers.
   `new_core='first'/'last'` (rnn_utils.py:29-34) only changes the TT shapes and runs in either mode.
 """
 from __future__ import annotations
@@ -29,6 +34,27 @@ from .functional import cell_step
 from .layers import TTLinear, TTLinearSet
 from .rnn_utils import ActivGradLogger
 from .shapes import tt_shape
+
+
+class _StepLogSink(object):
+    """Feeds ActivGradLogger from the fused path: (2, T) statistics per (layer, variable) instead of T hook calls.
+    Same per-logger order as the reference's hooks: activations in time order (rnn_utils.py:139-140), gradients
+    pushed to the left in reverse time (rnn_utils.py:149-150), i.e. in time order once the backward has finished."""
+
+    def __init__(self, loggers):
+        self.loggers = loggers           # per layer: {"h": logger, "c": logger (LSTM)}
+
+    def activations(self, layer, var, stats):
+        lg = self.loggers[layer].get(var)
+        if lg is not None:
+            lg.act.extend(stats[0].unbind(0))
+            lg.log_act.extend(stats[1].unbind(0))
+
+    def gradients(self, layer, var, stats):
+        lg = self.loggers[layer].get(var)
+        if lg is not None:
+            lg.grad.extendleft(reversed(stats[0].unbind(0)))
+            lg.log_grad.extendleft(reversed(stats[1].unbind(0)))
 
 
 def param_count(matrix: nn.Module) -> int:
@@ -155,6 +181,10 @@ class _TTRNNBase(nn.Module):
             setattr(self, 'cell{}'.format(i), cell)
             self._all_layers.append(cell)
         self._spec: Optional[RnnSpec] = None
+        # log_grads: keep training forwards on the sequence kernels (see the module docstring); False = the reference's
+        # per-step hooks in cell-step mode
+        self.fused_logging = True
+        self._step_loggers = []
         if log_grads:
             self._install_loggers()
 
@@ -166,11 +196,21 @@ class _TTRNNBase(nn.Module):
             h_forward, h_backward = h_logger.create_hooks(0)
             cell.register_forward_hook(h_forward)
             cell._h_backward_hook = h_backward
+            self._step_loggers.append({"h": h_logger})
             if self.cell_kind == "lstm":
                 c_logger = ActivGradLogger("cell_{}".format(i))
                 c_forward, c_backward = c_logger.create_hooks(1)
                 cell.register_forward_hook(c_forward)
                 cell._c_backward_hook = c_backward
+                self._step_loggers[-1]["c"] = c_logger
+
+    def _fused_step_log(self):
+        """The sink of the fused logging path, or None when this call must run step by step."""
+        if not (self.log_grads and self.fused_logging) or self.is_naive or not torch.is_grad_enabled():
+            return None
+        if not any(p.requires_grad for p in self.parameters()):
+            return None
+        return _StepLogSink(self._step_loggers)
 
     @property
     def cell_step_mode(self) -> bool:
@@ -229,10 +269,11 @@ class TTLSTM(_TTRNNBase):
         """input (batch, seq_len, input_size) -> outputs (batch, seq_len, hidden), (h_T, c_T) of the last layer.
         `init_states` = (h0, c0), each (batch, hidden), shared by every layer; None = zeros."""
         self._check_input(input)
-        if self.cell_step_mode:
+        sink = self._fused_step_log()
+        if self.cell_step_mode and sink is None:
             return self._forward_cell_steps(input, init_states)
         h0, c0 = (None, None) if init_states is None else init_states
-        out, h, c = rnn_sequence(self.spec(), input, h0, c0, self.flat_parameters())
+        out, h, c = rnn_sequence(self.spec(), input, h0, c0, self.flat_parameters(), step_log=sink)
         return out, (h, c)
 
     def _forward_cell_steps(self, input, init_states):
@@ -268,9 +309,10 @@ class TTGRU(_TTRNNBase):
     def forward(self, input, init_states=None):
         """input (batch, seq_len, input_size) -> outputs (batch, seq_len, hidden), h_T of the last layer."""
         self._check_input(input)
-        if self.cell_step_mode:
+        sink = self._fused_step_log()
+        if self.cell_step_mode and sink is None:
             return self._forward_cell_steps(input, init_states)
-        out, h = rnn_sequence(self.spec(), input, init_states, None, self.flat_parameters())
+        out, h = rnn_sequence(self.spec(), input, init_states, None, self.flat_parameters(), step_log=sink)
         return out, h
 
     def _forward_cell_steps(self, input, init_states):

@@ -16,11 +16,26 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("case", VARIANTS, ids=[c["name"] for c in VARIANTS])
 def test_variant_matches_reference_fixture(case):
+    """log_grads cases run the FUSED logging path here (sequence kernels + per-step statistics from the BPTT kernel)."""
+    _run_variant(case, fused_logging=True)
+
+
+@pytest.mark.parametrize("case", [c for c in VARIANTS if c["log_grads"]], ids=[c["name"] for c in VARIANTS if c["log_grads"]])
+def test_log_grads_cell_step_hooks_match_reference_fixture(case):
+    """The reference's own mechanism (one cell call per step, forward hooks + tensor hooks) against the same fixtures."""
+    _run_variant(case, fused_logging=False)
+
+
+def _run_variant(case, fused_logging):
     dev = torch.device("cuda:0")
+    tr.ActivGradLogger.reset()
     g = load_golden("variant_" + case["name"])
     m = build_variant(case)
     m.load_state_dict(state_dict_from_golden(g), strict=True)
     m = m.to(dev)
+    m.fused_logging = fused_logging
+    from tensorized_rnn_b200 import _lib
+    _lib.load().ttrnn_launch_count(1)
     x = torch.from_numpy(g["x"]).to(dev).requires_grad_(True)
     lstm = case["cell"] == "lstm"
     init = None
@@ -50,6 +65,11 @@ def test_variant_matches_reference_fixture(case):
             errs["dc0"] = rel_err(init[1].grad, g["f32:dc0"])
     bad = {k: v for k, v in errs.items() if not v <= GRAD_TOL}
     assert not bad, "gradient rel err above %.0e: %s" % (GRAD_TOL, bad)
+    if case["log_grads"] and not case.get("is_naive"):
+        # fused: a handful of launches per layer; cell-step: several per (step, layer)
+        n = int(_lib.load().ttrnn_launch_count(0))
+        T, L = x.shape[1], case["num_layers"]
+        assert (n < 40 * L) if fused_logging else (n >= 4 * T * L), (n, T, L)
     if case["log_grads"]:
         tr.ActivGradLogger.end_minibatch()
         tr.ActivGradLogger.end_epoch()
