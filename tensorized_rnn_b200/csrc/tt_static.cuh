@@ -1249,8 +1249,11 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_bwd_s(const __grid_constant_
     constexpr bool NEED_H = DWI || !SAVEU || (CELL != TTRNN_CELL_LSTM);
     extern __shared__ __align__(16) float smem[];
     using SM = BwdSmem<S, R, TB, DWI, SV>;
-    static_assert(DWI || (CELL == TTRNN_CELL_LSTM && MODE == MODE_XG),
-                  "split backward: delta_hh must equal delta_ih (LSTM) and be written to the xg buffer");
+    // split backward: the kernel writes delta_hh of every step to the xg buffer for the dense accumulation of the hh core
+    // gradients.  Projected input (MODE_XG): the same buffer must carry delta_ih, so delta_hh has to equal delta_ih (LSTM).
+    // Rank-one input: the ih gradients are accumulated in registers (g_weff / g_bih), the buffer carries delta_hh only.
+    static_assert(DWI || MODE == MODE_RANK1 || (CELL == TTRNN_CELL_LSTM && MODE == MODE_XG),
+                  "split backward with a projected input needs delta_hh == delta_ih (LSTM)");
     using FM = typename SM::FM;
     using TL = St<S, S::D - 1>;
     using T0 = St<S, 0>;
@@ -1545,6 +1548,7 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_bwd_s(const __grid_constant_
                         if (MODE == MODE_RANK1) {
                             g_weff[n][g] = fmaf(d_ih[g], x1[b], g_weff[n][g]);
                             g_bih[n][g] += d_ih[g];
+                            if (!DWI && ok) a.xg[row * a.xg_bstride + (long long)t * GH + g * H + h] = d_hh[g];
                         } else if (ok) {
                             a.xg[row * a.xg_bstride + (long long)t * GH + g * H + h] = d_ih[g];
                         }

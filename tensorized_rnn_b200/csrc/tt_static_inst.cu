@@ -188,6 +188,19 @@ const TtsRnnBwdEntry kBwd[] = {
     TTS_BWD_SPLIT_SAVEU(HH_H256_d4r16_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d4r16_split),
     TTS_BWD_SPLIT_SAVEU(HH_H768_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_h768_split),
     TTS_BWD_SPLIT_SAVEU(HH_H768_d2r4_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_h768_split),
+    // d2 r4 chains with a rank-one input (cfg1 / cfg2): dX-only kernels that write delta_hh, hh core gradients on the
+    // tensor cores (dW_hh^T = H_prev^T delta), ih / bias gradients still accumulated in registers
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 2, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 4, tts::MODE_RANK1, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_gru, TTRNN_CELL_GRU, 7, tts::MODE_RANK1, TB_d2),
+    // d2 r4 chain behind a projected input (the rank-padded params_model.py default, cfg3-alt): dX-only kernels, core
+    // gradients on the tensor cores
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d2),
+    TTS_BWD_SPLIT_SAVEU(HH_H256_d2r4_lstm, TTRNN_CELL_LSTM, 4, tts::MODE_XG, TB_d2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 1, tts::MODE_XG, TB_d3_split_R2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 2, tts::MODE_XG, TB_d3_split_R2),
     TTS_BWD_SPLIT_SAVEU(HH_H256_d3r8_lstm, TTRNN_CELL_LSTM, 3, tts::MODE_XG, TB_d3_split_R3),

@@ -446,6 +446,12 @@ bool dense_hh_dw_ok(const ChainPlan &hh) {
     return t_opt.dense_hh && hh.n_out % ttg::BN == 0 && hh.n_in % 4 == 0 && hh.n_in <= 2048;
 }
 
+// kept gates: may the dX-only ("split") BPTT variants be used for this layer?  They need the dense accumulation of the hh
+// core gradients; with a rank-one input the delta buffer must also hold the whole sequence (single-chunk plans)
+bool split_kept_ok(const ChainPlan &hh, int mode, long long Tc, long long T) {
+    return dense_hh_dw_ok(hh) && t_opt.split_kept && (mode != tts::MODE_RANK1 || Tc >= T);
+}
+
 struct DenseIh {
     float *eye, *wt, *w, *w_hi, *w_lo, *wt_hi, *wt_lo, *dwt, *dbias, *part, *pbias;
 };
@@ -511,7 +517,7 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
                 lo->x0f[l] = se->x0_floats;
                 extra1 += r4(B * T * se->x0_floats) + r4(B * T * 4 * H);
             }
-            const int oks = (dense_hh_dw_ok(rp.layer[l].hh) && t_opt.split_kept) ? 1 : 0;
+            const int oks = split_kept_ok(rp.layer[l].hh, mode, tc, T) ? 1 : 0;
             if (tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, 2, oks)) {
                 mode2[l] = 1;
                 extra2 += r4(B * T * 4 * H);
@@ -575,9 +581,10 @@ int build_layout(const ttrnn_rnn_desc *d, const RnnPlan &rp, const DevInfo &dv, 
     if (t_opt.stat)
         for (int l = 0; l < L; ++l) {
             const bool okd = dense_hh_dw_ok(rp.layer[l].hh);
-            const int oks = (okd && t_opt.split_kept) ? 1 : 0;
-            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)t_opt.srows_bwd, 0);
-            const TtsRnnBwdEntry *b2 = tts_find_rnn_bwd(&d->hh[l], d->cell, tts::MODE_XG, B, dv.sms, (int)t_opt.srows_bwd, 2, oks);
+            const int mode = (l == 0 && d->input_size == 1) ? tts::MODE_RANK1 : tts::MODE_XG;
+            const int oks = split_kept_ok(rp.layer[l].hh, mode, tc, T) ? 1 : 0;
+            const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, 0);
+            const TtsRnnBwdEntry *b2 = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, 2, oks);
             if (okd && ((be && be->split) || (b2 && b2->split)) && dense_bwd_floats(rp.layer[l].hh) > dhh)
                 dhh = dense_bwd_floats(rp.layer[l].hh);
         }
@@ -948,7 +955,7 @@ bool group_launches(const ttrnn_rnn_desc *d, const RnnPlan &rp, const RnnLayout 
         const TtsRnnBwdEntry *be = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, Bg, sms, (int)t_opt.srows_bwd);
         if (lo.save_mode[l] != 0)
             if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, Bg, sms, (int)t_opt.srows_bwd, lo.save_mode[l],
-                                                            dense_hh_dw_ok(rp.layer[l].hh) && t_opt.split_kept))
+                                                            split_kept_ok(rp.layer[l].hh, mode, lo.Tc, d->seq_len)))
                 be = bs;
         if (!be) return false;
         const TtsRnnBwdEntry *pe[2] = {be, nullptr};
@@ -1242,7 +1249,7 @@ int ttrnn_rnn_describe(const ttrnn_rnn_desc *d_full, int32_t training, char *buf
             const TtsRnnBwdEntry *be = t_opt.stat ? tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd) : nullptr;
             if (t_opt.stat && lo.save_mode[l] != 0)
                 if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd, lo.save_mode[l],
-                                                                dense_hh_dw_ok(lp.hh) && t_opt.split_kept))
+                                                                split_kept_ok(lp.hh, mode, lo.Tc, d->seq_len)))
                     be = bs;
             if (!be) {
                 put(" bwd_kernel=runtime bwd_rows=0");
@@ -1662,12 +1669,17 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
         if (t_opt.stat && !logging && lo.save_mode[l] != 0 && sv) {
             // forward kept (X_0 and) the hh pre-activations of this layer: use the kernel that consumes them
             if (const TtsRnnBwdEntry *bs = tts_find_rnn_bwd(&d->hh[l], d->cell, mode, B, dv.sms, (int)t_opt.srows_bwd,
-                                                            lo.save_mode[l], dense_hh_dw_ok(lp.hh) && t_opt.split_kept))
+                                                            lo.save_mode[l], split_kept_ok(lp.hh, mode, lo.Tc, T)))
                 be = bs;
         }
-        if (be && be->split && !lstm)
-            return fail("internal: split BPTT variants compute the hh bias gradient from the ih side (LSTM only); %s is "
-                        "registered for a GRU", be->name);
+        // split variants behind a projected input take the hh bias gradient from the ih side (LSTM only); the rank-one
+        // variants keep every bias / W_ih-column gradient in the kernel's own slot and work for both cells
+        const bool split_r1 = be && be->split && mode == tts::MODE_RANK1;
+        if (be && be->split && !lstm && !split_r1)
+            return fail("internal: split BPTT variants with a projected input compute the hh bias gradient from the ih side "
+                        "(LSTM only); %s is registered for a GRU", be->name);
+        if (split_r1 && !dense_hh_dw_ok(lp.hh))
+            return fail("internal: rank-one split BPTT variant %s selected without the dense hh core-gradient route", be->name);
         if (be) {
             // row plan: one phase, or two when a tail variant beats a mostly idle last wave
             const TtsRnnBwdEntry *ph_e[2] = {be, nullptr};
@@ -1733,14 +1745,14 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
             const long long ih_slot = lp.ih.core_floats + GH;
             const long long hhw_slot = lp.hh.core_floats + GH;       // slot layout of the batched hh-dW kernel (split mode)
             int hh_used = 0;
-            CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)(be->split ? hhw_slot * lo.nslots : slot * sgrid) * 4, st));
+            CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)((be->split && !split_r1) ? hhw_slot * lo.nslots : slot * sgrid) * 4, st));
             CU_CHECK(cudaMemsetAsync(part_ih, 0, (size_t)ih_slot * lo.nslots * 4, st));
             tts::RnnBwdSArgs sa;
             memset(&sa, 0, sizeof sa);
             sa.B = B; sa.T = T;
             sa.cores = params + lp.off_hh_cores;
             sa.hs = lout; sa.cs = lcs; sa.h0 = h0; sa.c0 = c0; sa.dhs = dhs;
-            sa.partial = be->split ? nullptr : part_hh;
+            sa.partial = (be->split && !split_r1) ? nullptr : part_hh;
             if (be->saved == 1) { sa.x0_save = sv + lo.sv_x0[l]; sa.x0_bstride = (long long)T * lo.x0f[l]; }
             if (be->saved != 0) { sa.u_save = sv + lo.sv_u[l];   sa.u_bstride = (long long)T * 4 * H; }
             float *aux = ss + lo.b_aux;
@@ -1764,10 +1776,22 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
                 sa.w_eff = aux; sa.bias_ih = b_ih; sa.bias_hh = b_hh;
                 sa.x1 = lin; sa.x1_bstride = T;
                 sa.t0 = 0; sa.steps = T;
+                if (split_r1) { sa.xg = xg; sa.xg_bstride = (long long)T * GH; }      // delta_hh of every step
                 sa.dh_in = (l == L - 1) ? d_hT : nullptr;
                 sa.dc_in = (l == L - 1) ? d_cT : nullptr;
                 sa.dh_out = sdh; sa.dc_out = sdc;
                 if (launch_plan(sa)) return 1;
+                if (split_r1) {
+                    // hh core gradients: dense accumulation dW_hh^T = H_prev^T delta over rows (h_{t-1}, delta_t)
+                    auto hh_dw1 = [&](const float *xp, long long xbs, const float *dyp, long long rows, int rpb) -> int {
+                        if (dense_dw(dvw, rows, rpb, xp, xbs, H, dyp, (long long)T * GH, GH, DH, hh_dense_calls > 0, false, ws))
+                            return 1;
+                        ++hh_dense_calls;
+                        return 0;
+                    };
+                    if (T > 1 && hh_dw1(lout, (long long)T * H, xg + GH, B * (T - 1), T - 1)) return 1;
+                    if (h0 && hh_dw1(h0, H, xg, B, 1)) return 1;
+                }
             } else {
                 sa.bias_hh = lstm ? nullptr : b_hh;
                 const int nchunks = (T + lo.Tc - 1) / lo.Tc;
@@ -1833,12 +1857,36 @@ static int rnn_backward_impl(const ttrnn_rnn_desc *d, const RnnPlan &rp, const R
             }
             // fold the per-CTA slots into the gradient blob
             const long long cf = lp.hh.core_floats;
-            if (be->split) {
+            if (split_r1) {
+                // part_hh holds the kernel's slots (biases, W_ih column) and is reused for the projection of the dense
+                // dW_hh^T onto the cores after those have been folded
+                if (d->has_bias) {
+                    if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, ws)) return 1;
+                    if (reduce_partials(part_hh, sgrid, slot, cf + 2 * GH, GH, d_params + lp.off_ih_bias, ws)) return 1;
+                }
+                if (reduce_partials(part_hh, sgrid, slot, cf + GH, GH, aux_g, ws)) return 1;
+                CU_CHECK(cudaMemsetAsync(part_hh, 0, (size_t)hhw_slot * lo.nslots * 4, ws));
+                if (hh_dense_calls > 0 &&
+                    launch_ttlinear_bwd(lp.hh, dvw, H, H, DH.eye, 0, params + lp.off_hh_cores, DH.dwt, 0, nullptr, 0, part_hh,
+                                        lo.nslots, ss + lo.b_spill, 0, ws, &hh_used, &d->hh[l]))
+                    return 1;
+                if (hh_used > 0) {
+                    if (reduce_partials(part_hh, hh_used, hhw_slot, 0, (int)cf, d_params + lp.off_hh_cores, ws)) return 1;
+                } else {
+                    CU_CHECK(cudaMemsetAsync(d_params + lp.off_hh_cores, 0, (size_t)cf * 4, ws));      // T == 1 without h0
+                }
+                if (launch_ttlinear_bwd(lp.ih, dvw, 1, 1, one, 0, params + lp.off_ih_cores, aux_g, 0, nullptr, 0, part_ih,
+                                        lo.nslots, ss + lo.b_spill, 0, ws, &ih_used))
+                    return 1;
+                if (reduce_partials(part_ih, ih_used, ih_slot, 0, lp.ih.core_floats, d_params + lp.off_ih_cores, ws)) return 1;
+            } else if (be->split) {
                 if (reduce_partials(part_hh, hh_used, hhw_slot, 0, (int)cf, d_params + lp.off_hh_cores, ws)) return 1;
             } else if (reduce_partials(part_hh, sgrid, slot, 0, (int)cf, d_params + lp.off_hh_cores, ws)) {
                 return 1;
             }
-            if (mode == tts::MODE_RANK1) {
+            if (split_r1) {
+                // everything was folded above
+            } else if (mode == tts::MODE_RANK1) {
                 if (d->has_bias) {
                     if (reduce_partials(part_hh, sgrid, slot, cf, GH, d_params + lp.off_hh_bias, ws)) return 1;
                     if (reduce_partials(part_hh, sgrid, slot, cf + 2 * GH, GH, d_params + lp.off_ih_bias, ws)) return 1;
