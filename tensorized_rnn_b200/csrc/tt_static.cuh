@@ -1217,6 +1217,9 @@ TTS_DEV void bwd_chain(float *xs, float *hcur, float *dy0, float *dhc, const flo
     if constexpr (k == S::D - 1) {
         // last stage: dX goes to the dh slot (no aliasing with X_k); split reduction
         if constexpr (WANT_DX) bwd_data_stage<S, k, R, TB::BTM[k], TB::BSP>(dY, wt + WTOff<S, k>::v, dhc, xch, tid);
+        // the cp.async tiles of the NEXT step (h_{t-2}, dOut[:, t-1]) were issued at least one stage ago: waiting for them
+        // here lets this barrier also publish them, so the step loop needs no barrier of its own at the top
+        cp_async_wait_all();
         __syncthreads();
     } else {
         if constexpr (DWI) __syncthreads();               // X_k is overwritten in place by dX_k
@@ -1432,10 +1435,13 @@ __global__ void __launch_bounds__(NTHR, MINB) k_rnn_bwd_s(const __grid_constant_
         }
         if (SAVED) fetch_x0(a.t0 + a.steps - 1);
         cp_async_wait_all();
+        __syncthreads();
         for (int t = a.steps - 1; t >= 0; --t) {
             const int tg = a.t0 + t;
             float *hcur = smem + ((t & 1) ? HOFF1 : HOFF0);
-            __syncthreads();
+            // the last barrier of the previous step's backward chain already ordered everything this step reads (dh chain,
+            // cp.async tiles); only the kept-X_0 kernels issue more cp.async after it
+            if constexpr (SAVED) __syncthreads();
             // operands of this step
             float xin[R][NE][4], x1[R], cprev[R][NE], hprev[R][NE], dho[R][NE], pre[R][NE][4];
 #pragma unroll
