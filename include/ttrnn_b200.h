@@ -26,8 +26,10 @@
 extern "C" {
 #endif
 
-#define TTRNN_ABI_VERSION 3   /* 2: + cell step, ih route query, static kernel table; 3: execution plan carried by
-                                 ttrnn_rnn_workspace, GEMM probe, GE2E head, dense cells */
+#define TTRNN_ABI_VERSION 4   /* 2: + cell step, ih route query, static kernel table; 3: execution plan carried by
+                                 ttrnn_rnn_workspace, GEMM probe, GE2E head, dense cells; 4: row groups in the plan
+                                 (ttrnn_rnn_row_groups, ttrnn_rnn_workspace_bytes_ex), per-step logging entry points,
+                                 per-launch timing records -- additive: every ABI 3 signature is unchanged */
 #define TTRNN_MAX_CORES   6
 #define TTRNN_MAX_LAYERS  8
 

@@ -10,7 +10,7 @@ import ctypes as C
 import os
 from typing import Optional, Sequence
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_CORES = 6
 MAX_LAYERS = 8
 PLAN_WORDS = 24

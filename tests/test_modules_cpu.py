@@ -121,7 +121,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "library does not export %s" % name
     assert declared == set(_lib.SYMBOLS), "python binding and header disagree: %s" % (declared ^ set(_lib.SYMBOLS))
-    assert _lib.load().ttrnn_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.load().ttrnn_abi_version() == _lib.ABI_VERSION == 4
 
 
 def test_struct_layout_matches_header():
@@ -245,7 +245,7 @@ def test_header_is_valid_c_and_matches_the_binding():
         with tempfile.TemporaryDirectory() as td:
             src = os.path.join(td, "t.c")
             with open(src, "w") as f:
-                f.write('#include "ttrnn_b200.h"\nint main(void) { ttrnn_rnn_desc d; (void)d; return TTRNN_ABI_VERSION == 3 ? 0 : 1; }\n')
+                f.write('#include "ttrnn_b200.h"\nint main(void) { ttrnn_rnn_desc d; (void)d; return TTRNN_ABI_VERSION == 4 ? 0 : 1; }\n')
             res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.dirname(hdr), src],
                                  capture_output=True, text=True)
             assert res.returncode == 0, res.stderr
