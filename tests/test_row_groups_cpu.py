@@ -46,3 +46,18 @@ def test_option_switches():
         assert groups(tr.TTGRU, 1, 256, 1, 2, 4, 20, 30) == (1, 20, 0)   # not enough rows for the forced split
     finally:
         lib.ttrnn_set_option(b"row_groups", 1)
+
+
+def test_planner_invariants_over_batches_and_sm_counts():
+    """Whatever the planner decides: one or two groups, row counts that add up to the batch, and a cut at a multiple of
+    4 rows (row-indexed slices of every buffer stay 16-byte aligned)."""
+    for sms in (148, 132, 64):
+        for B in (8, 60, 148, 150, 200, 296, 300, 320, 444, 480, 512, 600, 640, 700, 1000, 1500, 2368, 2400):
+            n, r0, r1 = groups(tr.TTLSTM, 40, 256, 3, 3, 8, B, 160, sms=sms)
+            assert n in (1, 2)
+            if n == 1:
+                assert (r0, r1) == (B, 0)
+            else:
+                assert r0 + r1 == B and r0 % 4 == 0 and r0 >= 4 and r1 >= 1, (sms, B, r0, r1)
+    # the decision is cached per (descriptor, options, SM count): asking again gives the same answer
+    assert groups(tr.TTLSTM, 40, 256, 3, 3, 8, 640, 160) == groups(tr.TTLSTM, 40, 256, 3, 3, 8, 640, 160)
