@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep: key metrics per kernel + top source lines by stall samples.
-usage: python tools_ncu_summary.py report.ncu-rep [--source N]"""
+usage: python tools/ncu_summary.py report.ncu-rep [--source N]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]
 nsrc = int(sys.argv[sys.argv.index("--source") + 1]) if "--source" in sys.argv else 0
