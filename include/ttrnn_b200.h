@@ -13,7 +13,10 @@
  *     data unless stated otherwise; the library never allocates or frees device
  *     memory (the caller owns every buffer, sized by the *_workspace_bytes calls)
  *   - all tensors are dense row-major: x (B, T, I), out (B, T, H), states (B, H)
- *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synced
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synced.
+ *     ttrnn_rnn_forward / ttrnn_rnn_backward may fork library-owned streams from it
+ *     (row groups, backward overlap) and always join them back with an event before
+ *     they return: for the caller the call stays ordered on `stream`
  *   - return 0 on success; non-zero = error, text via ttrnn_last_error()
  *   - there is no CPU path: without a CUDA device every compute call fails
  */
